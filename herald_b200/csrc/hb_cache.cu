@@ -1,0 +1,1890 @@
+// Worker-side embedding cache and owner-side table shard, both resident in HBM.
+//
+// What each call restates (reference file:line):
+//   hb_cache_lookup                  CacheBase::_embeddingLookup            src/hetu_cache/src/cache.cc:60-107
+//   hb_cache_update                  CacheBase::_embeddingUpdate            cache.cc:132-196
+//   hb_cache_update_with_push_keys   CacheBase::_embeddingUpdateWithPushKeys cache.cc:248-334
+//   hb_cache_push_pull               CacheBase::_embeddingPushPull          cache.cc:356-422
+//   sync / push between cache and owner   hetu_client.cc:6-55 + ps-lite/src/PSFhandle_embedding.cc:5-79
+//   replacement policies             lru_cache.cc, lfu_cache.cc, lfuopt_cache.cc
+//
+// The reference walks the sorted unique keys of a batch serially through a hash map and linked
+// lists.  Here the same decisions are made in parallel:
+//   * every policy touch / insert gets a stamp from one monotone clock, in the order the serial
+//     walk would perform it (sorted rank inside a batch), so "position in the list" becomes a
+//     64-bit priority word per slot: (use count << 52) | stamp;
+//   * the victims of a batch of inserts are the k smallest priorities of the policy's victim
+//     class (LRU: all lines; LFU: lines used once; LFUOpt: lines never re-used), found with a
+//     12-bit-per-level radix select over the slot array, plus closed-form handling of the
+//     corner cases in which freshly inserted lines evict each other;
+//   * gradients are accumulated per unique row in occurrence order by one warp (bit-identical
+//     to Line::accumulate, embedding.h:78-91), fused with the push to the owner row.
+#include <algorithm>
+#include <cstring>
+#include <map>
+#include <mutex>
+
+#include "hb_cache.cuh"
+#include "hb_rows.cuh"
+
+namespace hb {
+namespace {
+
+// =====================================================================================
+// small device helpers
+// =====================================================================================
+__device__ __forceinline__ u32 hash_key(u64 k) {
+    k ^= k >> 33;
+    k *= 0xff51afd7ed558ccdull;
+    k ^= k >> 33;
+    k *= 0xc4ceb9fe1a85ec53ull;
+    k ^= k >> 33;
+    return (u32)k;
+}
+
+// returns slot or -1
+__device__ __forceinline__ i32 ht_find(const HtEntry *ht, u32 mask, u64 key) {
+    u32 h = hash_key(key) & mask;
+    for (u32 probes = 0; probes <= mask; probes++) {
+        const ulonglong2 e = *reinterpret_cast<const ulonglong2 *>(&ht[h]);
+        if (e.x == key)
+            return (i32)(u32)e.y;
+        if (e.x == HT_EMPTY)
+            return -1;
+        h = (h + 1) & mask;
+    }
+    return -1;
+}
+
+// key must be absent.  Returns false when the table has no free entry.
+__device__ __forceinline__ bool ht_insert(HtEntry *ht, u32 mask, u64 key, u32 slot, u32 *occupied) {
+    u32 h = hash_key(key) & mask;
+    for (u32 probes = 0; probes <= mask;) {
+        u64 cur = *reinterpret_cast<volatile u64 *>(&ht[h].key);
+        if (cur == HT_EMPTY || cur == HT_TOMB) {
+            u64 old = atomicCAS(&ht[h].key, cur, key);
+            if (old == cur) {
+                ht[h].slot = slot;
+                if (cur == HT_EMPTY)
+                    atomicAdd(occupied, 1u);
+                return true;
+            }
+            continue; // lost the race for this entry: look at it again
+        }
+        h = (h + 1) & mask;
+        probes++;
+    }
+    return false;
+}
+
+__device__ __forceinline__ void ht_erase(HtEntry *ht, u32 mask, u64 key) {
+    u32 h = hash_key(key) & mask;
+    for (u32 probes = 0; probes <= mask; probes++) {
+        u64 cur = ht[h].key;
+        if (cur == key) {
+            ht[h].key = HT_TOMB;
+            return;
+        }
+        if (cur == HT_EMPTY)
+            return;
+        h = (h + 1) & mask;
+    }
+}
+
+// One atomic per warp: every lane of the warp must call this (pred may differ per lane).
+__device__ __forceinline__ u32 warp_append(u32 *counter, bool pred) {
+    unsigned m = __ballot_sync(FULL, pred);
+    if (!m)
+        return 0;
+    int leader = __ffs(m) - 1;
+    u32 base = 0;
+    if ((int)lane_id() == leader)
+        base = atomicAdd(counter, (u32)__popc(m));
+    base = __shfl_sync(FULL, base, leader);
+    return base + __popc(m & lanemask_lt());
+}
+
+__device__ __forceinline__ u32 *block_counter() {
+    __shared__ u32 s_counter;
+    return &s_counter;
+}
+
+__device__ __forceinline__ int class_use_of(int policy) {
+    return policy == HB_POLICY_LFU ? 1 : 0;
+}
+
+__device__ __forceinline__ u64 make_prio(u32 use, u64 stamp) {
+    return ((u64)min(use, kUseSat) << kStampBits) | (stamp & kStampMask);
+}
+
+// =====================================================================================
+// call prologue / epilogue
+// =====================================================================================
+// clk[0..3]: the replacement clock as a chain — stage s of a call reads clk[s] and writes
+// clk[s+1], so no kernel reads a word that another block of the same kernel writes.
+__global__ void op_begin_kernel(CacheRegs *r, u64 *clk) {
+    r->clock0 = r->clock;
+    clk[0] = r->clock;
+    clk[1] = clk[2] = clk[3] = r->clock;
+    r->U = r->M = r->alloc_base = 0;
+    r->pulled = r->pushed = r->flushed = 0;
+    r->E = r->k_old = r->n_drop = r->need_min = r->nv = r->nc = 0;
+    r->U2 = r->M2 = r->alloc_base2 = 0;
+}
+
+__global__ void op_end_kernel(CacheView c, const u64 *clk, int last_stage, PerfRecord *rec, u32 kind,
+                              u32 num_all, int inserted_batch) {
+    CacheRegs *r = c.regs;
+    r->clock = clk[last_stage];
+    if (inserted_batch) {
+        u32 inserted = r->M - r->n_drop;
+        r->size = r->size - r->nv + inserted;
+    }
+    rec->kind = kind;
+    rec->num_all = num_all;
+    if (kind == 0) {
+        rec->num_unique = r->U;
+        rec->num_miss = r->M;
+        rec->num_evict = 0;
+        rec->num_transfered = r->pulled;
+    } else if (kind == 1) {
+        rec->num_unique = r->U;
+        rec->num_miss = r->M;
+        rec->num_evict = r->flushed;
+        rec->num_transfered = r->pushed + r->flushed;
+    } else {
+        rec->num_unique = r->U;
+        rec->num_miss = r->M;
+        rec->num_evict = r->flushed;
+        rec->num_transfered = r->pulled;
+    }
+    rec->size = r->size;
+    rec->error = r->error;
+    rec->ht_occupied = r->ht_occupied;
+    rec->pending = r->pending;
+    rec->limit_full = r->size == c.limit;
+}
+
+// =====================================================================================
+// resolve: policy lookup of every unique key (+ touch), ordered compaction of the misses
+// =====================================================================================
+// batch 0 writes U/M/alloc_base, batch 1 (push side of push_pull) writes U2/M2/alloc_base2.
+__global__ void __launch_bounds__(kScanBlock)
+    resolve_kernel(CacheView c, const u64 *uniq, const u32 *num_unique, i32 *uslot, u32 *miss_list,
+                   int bypass, ScanState st, u32 ntiles, const u64 *clk_in, u64 *clk_out, int batch) {
+    const u32 tile = take_ticket(st.ticket);
+    const u32 U = *num_unique;
+    const u64 base = *clk_in;
+    const u32 i = tile * kScanBlock + threadIdx.x;
+    u32 miss = 0;
+    if (i < U) {
+        const u64 key = uniq[i];
+        i32 s = bypass ? -1 : ht_find(c.ht, c.ht_mask, key);
+        if (key >= c.table_len)
+            atomicMax(&c.regs->error, (u32)E_KEY_RANGE);
+        if (s >= 0) {
+            const u64 stamp = base + i;
+            switch (c.policy) {
+            case HB_POLICY_LRU: // lru_cache.cc:27-39: move to the front
+                c.slot_prio[s] = make_prio(0, stamp);
+                break;
+            case HB_POLICY_LFU: { // lfu_cache.cc:22-29, 52-69: front of the (use+1) list
+                u32 use = c.slot_use[s] + 1;
+                c.slot_use[s] = use;
+                c.slot_prio[s] = make_prio(use, stamp);
+                break;
+            }
+            default: // lfuopt_cache.cc:28-44
+                if (c.slot_state[s] == S_CACHED) {
+                    u32 use = c.slot_use[s];
+                    if (use + 1 < kLfuOptUseMax) {
+                        c.slot_use[s] = use + 1;
+                        c.slot_prio[s] = make_prio(use + 1, stamp);
+                    } else { // promoted to the permanent store
+                        c.slot_state[s] = S_STORE;
+                        c.slot_prio[s] = PRIO_NONE;
+                        atomicAdd(&c.regs->store_size, 1u);
+                    }
+                }
+                break;
+            }
+        } else {
+            miss = 1;
+        }
+        uslot[i] = s;
+    }
+    ScanResult sr = grid_exclusive_scan<kScanBlock>(st, miss, tile);
+    if (miss)
+        miss_list[sr.excl] = i;
+    if (tile == ntiles - 1 && threadIdx.x == 0) {
+        CacheRegs *r = c.regs;
+        u32 M = sr.tile_prefix + sr.tile_total;
+        u32 top = r->free_top;
+        u32 alloc_base = 0;
+        if (M > top) {
+            atomicMax(&r->error, (u32)E_NO_FREE_SLOT);
+            M = top; // keep memory safe; the call is reported as failed
+        }
+        alloc_base = top - M;
+        r->free_top = alloc_base;
+        if (batch == 0) {
+            r->U = U;
+            r->M = M;
+            r->alloc_base = alloc_base;
+        } else {
+            r->U2 = U;
+            r->M2 = M;
+            r->alloc_base2 = alloc_base;
+        }
+        *clk_out = base + U;
+    }
+}
+
+// Give every miss a fresh line (cache.cc:70-76 with data, :146-151 dataless).
+__global__ void alloc_kernel(CacheView c, const u64 *uniq, i32 *uslot, const u32 *miss_list,
+                             int batch, int dataless) {
+    const CacheRegs *r = c.regs;
+    const u32 M = batch == 0 ? r->M : r->M2;
+    const u32 alloc_base = batch == 0 ? r->alloc_base : r->alloc_base2;
+    u32 j = blockIdx.x * blockDim.x + threadIdx.x;
+    for (; j < M; j += gridDim.x * blockDim.x) {
+        const u32 i = miss_list[j];
+        const u32 s = c.free_stack[alloc_base + j];
+        uslot[i] = (i32)s;
+        c.slot_key[s] = uniq[i];
+        c.slot_version[s] = -1; // embedding.h:35,42
+        c.slot_updates[s] = 0;
+        c.slot_prio[s] = PRIO_NONE;
+        c.slot_use[s] = 0;
+        c.slot_state[s] = S_TRANSIENT;
+        c.slot_flags[s] = dataless ? F_DATALESS : 0;
+    }
+}
+
+// =====================================================================================
+// sync with the owner shard: kSyncEmbedding (PSFhandle_embedding.cc:30-64) + client closure
+// (hetu_client.cc:19-32): rows whose version is -1 or more than pull_bound behind are re-read.
+// =====================================================================================
+template <int VEC>
+__global__ void __launch_bounds__(kRowBlock)
+    sync_kernel(CacheView c, const u64 *uniq, const i32 *uslot, i64 pull_bound) {
+    using V = RowVec<VEC>;
+    const unsigned lane = lane_id();
+    const size_t warp_global = (size_t)blockIdx.x * kRowWarps + (threadIdx.x >> 5);
+    const size_t nwarps = (size_t)gridDim.x * kRowWarps;
+    const size_t D = c.width, nvec = D / VEC;
+    const u32 U = c.regs->U;
+    u32 *cnt = block_counter();
+    if (threadIdx.x == 0)
+        *cnt = 0;
+    __syncthreads();
+    u32 pulled = 0;
+    for (size_t i = warp_global; i < U; i += nwarps) {
+        const i32 s = uslot[i];
+        const u64 key = uniq[i];
+        const u64 trow = key - c.row_begin;
+        if (s < 0 || trow >= c.nrows_local)
+            continue;
+        const i64 v = c.slot_version[s];
+        const i64 srv = c.tver[trow];
+        if (!(v == -1 || srv - v > pull_bound))
+            continue;
+        const u8 flags = c.slot_flags[s];
+        const bool addup = flags & F_GRAD;                  // Line::addup (embedding.h:92-96)
+        const bool live_grad = addup && c.slot_updates[s] != 0; // grad store is meaningful
+        const float *src = c.trows + trow * D;
+        float *dst = c.data + (size_t)s * D;
+        const float *g = c.grad + (size_t)s * D;
+        for (size_t k = lane; k < nvec; k += 32) {
+            typename V::T x = V::ld(src + k * VEC);
+            if (addup)
+                x = V::add(x, live_grad ? V::ld(g + k * VEC) : V::zero());
+            V::st(dst + k * VEC, x);
+        }
+        if (lane == 0) {
+            c.slot_version[s] = srv;
+            pulled++;
+        }
+    }
+    if (pulled)
+        atomicAdd(cnt, pulled);
+    __syncthreads();
+    if (threadIdx.x == 0 && *cnt)
+        atomicAdd(&c.regs->pulled, *cnt);
+}
+
+struct IndexFromSlots {
+    const i32 *uslot;
+    const u32 *inverse;
+    __device__ long long operator()(size_t n) const {
+        return (long long)uslot[inverse[n]];
+    }
+};
+
+// =====================================================================================
+// batched insert: plan, select victims, evict, insert  (cache.cc:28-35 + policy insert())
+// =====================================================================================
+__global__ void __launch_bounds__(256)
+    plan_insert_kernel(CacheView c, int bypass, const u64 *clk_in, u64 *clk_out) {
+    for (int b = threadIdx.x; b < kSelBins; b += blockDim.x)
+        c.sel_hist[b] = 0;
+    if (threadIdx.x != 0)
+        return;
+    CacheRegs *r = c.regs;
+    const u32 M = r->M, size_old = r->size, limit = c.limit;
+    u32 E = 0;
+    if (!bypass) {
+        if (c.policy == HB_POLICY_LRU) { // insert, then evict while over limit (lru_cache.cc:9-25)
+            u64 tot = (u64)size_old + M;
+            E = tot > limit ? (u32)(tot - limit) : 0;
+        } else { // evict before insert when full (lfu_cache.cc:9-20, lfuopt_cache.cc:9-26)
+            u32 F = limit > size_old ? limit - size_old : 0;
+            E = M > F ? M - F : 0;
+        }
+    }
+    r->E = E;
+    r->k_old = 0;
+    r->n_drop = bypass ? M : 0;
+    r->need_min = 0;
+    r->nv = 0;
+    r->nc = 0;
+    r->min_use = 0xffffffffu;
+    r->min_prio = ~0ull;
+    const u64 now = *clk_in;
+    r->ins_clock0 = now;
+    *clk_out = now + M;
+    // bins cover [floor, now): (stamp - floor) >> shift < kSelBins
+    const u64 span = now > r->floor ? now - r->floor : 1; // stamp offsets 0 .. span-1
+    const int bits = span > 1 ? 64 - __clzll((long long)(span - 1)) : 0;
+    r->sel_shift = bits > kSelBits ? (u32)(bits - kSelBits) : 0;
+}
+
+__global__ void __launch_bounds__(256) sel_hist_kernel(CacheView c) {
+    const CacheRegs *r = c.regs;
+    if (r->E == 0)
+        return;
+    __shared__ u32 sh[kSelBins];
+    for (int b = threadIdx.x; b < kSelBins; b += blockDim.x)
+        sh[b] = 0;
+    __syncthreads();
+    const u64 floor = r->floor;
+    const u32 shift = r->sel_shift;
+    const u64 cls = (u64)class_use_of(c.policy);
+    for (size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x; s < c.capacity;
+         s += (size_t)gridDim.x * blockDim.x) {
+        const u64 p = c.slot_prio[s];
+        if (p != PRIO_NONE && (p >> kStampBits) == cls) {
+            u64 bin = ((p & kStampMask) - floor) >> shift;
+            atomicAdd(&sh[min(bin, (u64)(kSelBins - 1))], 1u);
+        }
+    }
+    __syncthreads();
+    for (int b = threadIdx.x; b < kSelBins; b += blockDim.x)
+        if (sh[b])
+            atomicAdd(&c.sel_hist[b], sh[b]);
+}
+
+// Block-wide: exclusive prefix of sh[0..kSelBins) in place; returns total.  blockDim.x == 256.
+__device__ __forceinline__ u32 block_scan_bins(u32 *sh) {
+    __shared__ u32 s_part[256];
+    constexpr int PER = kSelBins / 256;
+    u32 local[PER];
+    u32 sum = 0;
+#pragma unroll
+    for (int k = 0; k < PER; k++) {
+        local[k] = sh[threadIdx.x * PER + k];
+        sum += local[k];
+    }
+    s_part[threadIdx.x] = sum;
+    __syncthreads();
+    // Hillis-Steele over 256 partials
+    for (int d = 1; d < 256; d <<= 1) {
+        u32 t = threadIdx.x >= (unsigned)d ? s_part[threadIdx.x - d] : 0;
+        __syncthreads();
+        s_part[threadIdx.x] += t;
+        __syncthreads();
+    }
+    u32 run = s_part[threadIdx.x] - sum;
+#pragma unroll
+    for (int k = 0; k < PER; k++) {
+        sh[threadIdx.x * PER + k] = run;
+        run += local[k];
+    }
+    u32 total = s_part[255];
+    __syncthreads();
+    return total;
+}
+
+__global__ void __launch_bounds__(256) sel_collect_kernel(CacheView c) {
+    CacheRegs *r = c.regs;
+    const u32 E = r->E;
+    if (E == 0)
+        return;
+    __shared__ u32 sh[kSelBins];
+    __shared__ u32 s_bin, s_kold;
+    for (int b = threadIdx.x; b < kSelBins; b += blockDim.x)
+        sh[b] = c.sel_hist[b];
+    __syncthreads();
+    const u32 class_count = block_scan_bins(sh); // sh = exclusive prefix
+    const u32 k_old = min(E, class_count);
+    if (threadIdx.x == 0) {
+        s_kold = k_old;
+        s_bin = 0;
+    }
+    __syncthreads();
+    // threshold bin: the last bin whose exclusive prefix is < k_old (k_old > 0)
+    if (k_old > 0) {
+        for (int b = threadIdx.x; b < kSelBins; b += blockDim.x) {
+            u32 ex = sh[b];
+            u32 nxt = b + 1 < kSelBins ? sh[b + 1] : class_count;
+            if (ex < k_old && nxt >= k_old)
+                s_bin = b; // unique b: prefix is monotone and nxt > ex here
+        }
+    }
+    __syncthreads();
+    const u32 bstar = s_bin;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        const u32 M = r->M, size_old = r->size;
+        const u32 extra = E - k_old;
+        u32 n_drop = 0, need_min = 0;
+        if (extra > 0) {
+            if (c.policy == HB_POLICY_LRU) {
+                n_drop = extra; // the oldest new lines fall off the tail themselves
+            } else {
+                const u32 F = c.limit > size_old ? c.limit - size_old : 0;
+                if (F + class_count == 0) {
+                    const u32 evictable = size_old - r->store_size;
+                    if (evictable > 0) { // one resident line goes, then new lines evict each other
+                        need_min = 1;
+                        n_drop = extra - 1;
+                    } else { // LFUOpt: only the permanent store is populated -> nothing is cached
+                        n_drop = M;
+                    }
+                } else {
+                    n_drop = extra;
+                }
+            }
+        }
+        r->k_old = k_old;
+        r->n_drop = n_drop;
+        r->need_min = need_min;
+        r->sel_bin = bstar;
+        r->sel_rem = k_old > 0 ? k_old - sh[bstar] : 0;
+    }
+    if (k_old == 0)
+        return;
+    const u64 floor = r->floor;
+    const u32 shift = r->sel_shift;
+    const u64 cls = (u64)class_use_of(c.policy);
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    const size_t rounds = (c.capacity + stride - 1) / stride;
+    for (size_t it = 0; it < rounds; it++) {
+        const size_t s = it * stride + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+        bool victim = false, cand = false;
+        u64 p = 0;
+        if (s < c.capacity) {
+            p = c.slot_prio[s];
+            if (p != PRIO_NONE && (p >> kStampBits) == cls) {
+                u64 bin = min(((p & kStampMask) - floor) >> shift, (u64)(kSelBins - 1));
+                victim = bin < bstar;
+                cand = bin == bstar;
+            }
+        }
+        u32 vpos = warp_append(&r->nv, victim);
+        if (victim)
+            c.victims[vpos] = (u32)s;
+        u32 cpos = warp_append(&r->nc, cand);
+        if (cand) {
+            c.cand_prio[cpos] = p & kStampMask;
+            c.cand_slot[cpos] = (u32)s;
+        }
+    }
+}
+
+// One block finishes the selection inside the threshold bin: 12 more bits per round.
+__global__ void __launch_bounds__(1024) sel_refine_kernel(CacheView c) {
+    CacheRegs *r = c.regs;
+    if (r->E == 0 || r->k_old == 0)
+        return;
+    __shared__ u32 sh[kSelBins];
+    __shared__ u32 s_part[1024];
+    __shared__ u32 s_bin, s_next_n, s_vbase;
+    u32 nc = r->nc, rem = r->sel_rem, shift = r->sel_shift;
+    u64 lo = r->floor + ((u64)r->sel_bin << shift);
+    int cur = 0;
+    const size_t cap = c.capacity;
+    while (rem > 0) {
+        const u64 *cp = c.cand_prio + (size_t)cur * cap;
+        const u32 *cs = c.cand_slot + (size_t)cur * cap;
+        if (nc <= rem || shift == 0) { // everything left is a victim
+            if (threadIdx.x == 0)
+                s_vbase = atomicAdd(&r->nv, nc);
+            __syncthreads();
+            for (u32 k = threadIdx.x; k < nc; k += blockDim.x)
+                c.victims[s_vbase + k] = cs[k];
+            break;
+        }
+        const u32 nshift = shift > kSelBits ? shift - kSelBits : 0;
+        for (int b = threadIdx.x; b < kSelBins; b += blockDim.x)
+            sh[b] = 0;
+        if (threadIdx.x == 0) {
+            s_next_n = 0;
+            s_bin = 0;
+        }
+        __syncthreads();
+        for (u32 k = threadIdx.x; k < nc; k += blockDim.x)
+            atomicAdd(&sh[min((cp[k] - lo) >> nshift, (u64)(kSelBins - 1))], 1u);
+        __syncthreads();
+        // exclusive prefix of the 4096 bins with 1024 threads (4 bins each)
+        u32 local[4], sum = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            local[k] = sh[threadIdx.x * 4 + k];
+            sum += local[k];
+        }
+        s_part[threadIdx.x] = sum;
+        __syncthreads();
+        for (int d = 1; d < 1024; d <<= 1) {
+            u32 t = threadIdx.x >= (unsigned)d ? s_part[threadIdx.x - d] : 0;
+            __syncthreads();
+            s_part[threadIdx.x] += t;
+            __syncthreads();
+        }
+        u32 run = s_part[threadIdx.x] - sum;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            u32 ex = run, nxt = run + local[k];
+            if (ex < rem && nxt >= rem)
+                s_bin = threadIdx.x * 4 + k;
+            sh[threadIdx.x * 4 + k] = ex;
+            run = nxt;
+        }
+        __syncthreads();
+        const u32 b2 = s_bin;
+        const u32 below = sh[b2];
+        if (threadIdx.x == 0)
+            s_vbase = atomicAdd(&r->nv, below);
+        __syncthreads();
+        // victims below the bin, survivors of the bin go to the other candidate buffer
+        u64 *np = c.cand_prio + (size_t)(cur ^ 1) * cap;
+        u32 *ns = c.cand_slot + (size_t)(cur ^ 1) * cap;
+        __shared__ u32 s_vcount;
+        if (threadIdx.x == 0)
+            s_vcount = 0;
+        __syncthreads();
+        for (u32 k0 = 0; k0 < nc; k0 += blockDim.x) {
+            const u32 k = k0 + threadIdx.x;
+            bool victim = false, keep = false;
+            u64 p = 0;
+            u32 s = 0;
+            if (k < nc) {
+                p = cp[k];
+                s = cs[k];
+                u32 bin = (u32)min((p - lo) >> nshift, (u64)(kSelBins - 1));
+                victim = bin < b2;
+                keep = bin == b2;
+            }
+            u32 vpos = warp_append(&s_vcount, victim);
+            if (victim)
+                c.victims[s_vbase + vpos] = s;
+            u32 kpos = warp_append(&s_next_n, keep);
+            if (keep) {
+                np[kpos] = p;
+                ns[kpos] = s;
+            }
+        }
+        __syncthreads();
+        rem -= below;
+        nc = s_next_n;
+        lo += (u64)b2 << nshift;
+        shift = nshift;
+        cur ^= 1;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0)
+        r->floor = lo; // every line of the class below `lo` has just been evicted
+}
+
+// LFU corner: the single resident line with the smallest (use, stamp).
+__global__ void min_use_kernel(CacheView c) {
+    CacheRegs *r = c.regs;
+    if (!r->need_min)
+        return;
+    u32 best = 0xffffffffu;
+    for (size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x; s < c.capacity;
+         s += (size_t)gridDim.x * blockDim.x)
+        if (c.slot_state[s] == S_CACHED)
+            best = min(best, c.slot_use[s]);
+    for (int d = 16; d > 0; d >>= 1)
+        best = min(best, __shfl_xor_sync(FULL, best, d));
+    if (lane_id() == 0 && best != 0xffffffffu)
+        atomicMin(&r->min_use, best);
+}
+__global__ void min_prio_kernel(CacheView c) {
+    CacheRegs *r = c.regs;
+    if (!r->need_min)
+        return;
+    const u32 mu = r->min_use;
+    u64 best = ~0ull;
+    for (size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x; s < c.capacity;
+         s += (size_t)gridDim.x * blockDim.x)
+        if (c.slot_state[s] == S_CACHED && c.slot_use[s] == mu)
+            best = min(best, c.slot_prio[s] & kStampMask);
+    for (int d = 16; d > 0; d >>= 1)
+        best = min(best, __shfl_xor_sync(FULL, best, d));
+    if (lane_id() == 0 && best != ~0ull)
+        atomicMin(&r->min_prio, best);
+}
+__global__ void min_pick_kernel(CacheView c) {
+    CacheRegs *r = c.regs;
+    if (!r->need_min)
+        return;
+    const u32 mu = r->min_use;
+    const u64 mp = r->min_prio;
+    for (size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x; s < c.capacity;
+         s += (size_t)gridDim.x * blockDim.x)
+        if (c.slot_state[s] == S_CACHED && c.slot_use[s] == mu &&
+            (c.slot_prio[s] & kStampMask) == mp)
+            c.victims[atomicAdd(&r->nv, 1u)] = (u32)s;
+}
+
+// Remove the victims from the index; dirty ones wait for the next push (evict_), clean ones
+// are freed (lru_cache.cc:17-24).
+__global__ void evict_apply_kernel(CacheView c) {
+    CacheRegs *r = c.regs;
+    const u32 nv = r->nv;
+    for (u32 v = blockIdx.x * blockDim.x + threadIdx.x; v < nv; v += gridDim.x * blockDim.x) {
+        const u32 s = c.victims[v];
+        ht_erase(c.ht, c.ht_mask, c.slot_key[s]);
+        c.slot_prio[s] = PRIO_NONE;
+        if (c.slot_updates[s] != 0) {
+            c.slot_state[s] = S_PENDING;
+            u32 pos = atomicAdd(&r->pending, 1u);
+            if (pos < c.capacity)
+                c.pending_list[pos] = s;
+            else
+                atomicMax(&r->error, (u32)E_EVICT_OVERFLOW);
+        } else {
+            c.slot_state[s] = S_FREE;
+            c.free_stack[atomicAdd(&r->free_top, 1u)] = s;
+        }
+    }
+}
+
+__global__ void insert_new_kernel(CacheView c, const i32 *uslot, const u32 *miss_list) {
+    CacheRegs *r = c.regs;
+    const u32 M = r->M, n_drop = r->n_drop;
+    const u64 clock0 = r->ins_clock0;
+    const u32 use0 = c.policy == HB_POLICY_LFU ? 1u : 0u;
+    for (u32 j = blockIdx.x * blockDim.x + threadIdx.x; j < M; j += gridDim.x * blockDim.x) {
+        const u32 s = (u32)uslot[miss_list[j]];
+        if (j < n_drop) { // served to the caller but never resident after the call
+            c.slot_state[s] = S_FREE;
+            c.free_stack[atomicAdd(&r->free_top, 1u)] = s;
+            continue;
+        }
+        if (!ht_insert(c.ht, c.ht_mask, c.slot_key[s], s, &r->ht_occupied))
+            atomicMax(&r->error, (u32)E_INDEX_FULL);
+        c.slot_use[s] = use0;
+        c.slot_prio[s] = make_prio(use0, clock0 + j);
+        c.slot_state[s] = S_CACHED;
+    }
+}
+
+// =====================================================================================
+// update: accumulate per unique row in occurrence order, fused with the push to the owner
+// =====================================================================================
+template <int VEC>
+struct AccumulatePush {
+    using V = RowVec<VEC>;
+    struct Acc {
+        typename V::T d, g;
+    };
+    struct Ctx {
+        i32 s;
+        u64 trow;
+        i32 upd0, upd;
+        bool dataless, pushed, local;
+    };
+    CacheView c;
+    const u64 *uniq;
+    const i32 *uslot;
+    i64 push_bound;
+    const u64 *push_keys; // non-null: Laia/Herald plan (cache.cc:286-301)
+    u32 n_push;
+
+    __device__ void kernel_begin() const {
+        u32 *cnt = block_counter();
+        if (threadIdx.x == 0)
+            *cnt = 0;
+        __syncthreads();
+    }
+    __device__ void kernel_end() const {
+        u32 *cnt = block_counter();
+        __syncthreads();
+        if (threadIdx.x == 0 && *cnt)
+            atomicAdd(&c.regs->pushed, *cnt);
+    }
+    __device__ bool in_plan(u64 key) const {
+        u32 lo = 0, hi = n_push;
+        while (lo < hi) {
+            u32 mid = (lo + hi) >> 1;
+            if (push_keys[mid] < key)
+                lo = mid + 1;
+            else
+                hi = mid;
+        }
+        return lo < n_push && push_keys[lo] == key;
+    }
+    __device__ bool begin(size_t u, u32 cnt, Ctx &x) const {
+        x.s = uslot[u];
+        if (x.s < 0)
+            return false;
+        const u64 key = uniq[u];
+        x.trow = key - c.row_begin;
+        x.local = x.trow < c.nrows_local;
+        x.upd0 = c.slot_updates[x.s];
+        x.upd = x.upd0 + (i32)cnt;
+        x.dataless = c.slot_flags[x.s] & F_DATALESS;
+        if (push_keys)
+            x.pushed = !x.dataless && in_plan(key); // cache.cc:296
+        else
+            x.pushed = (i64)x.upd > push_bound || x.dataless; // cache.cc:157
+        return true;
+    }
+    __device__ Acc load(const Ctx &x, size_t k) const {
+        Acc a;
+        const size_t o = (size_t)x.s * c.width + k * VEC;
+        a.d = x.dataless ? V::zero() : V::ld(c.data + o);
+        a.g = x.upd0 != 0 ? V::ld(c.grad + o) : V::zero();
+        return a;
+    }
+    __device__ Acc step(const Acc &a, const typename V::T &g) const {
+        Acc r; // embedding.h:78-91: grad_ += g; data_ += g  (per occurrence, in order)
+        r.g = V::add(a.g, g);
+        r.d = V::add(a.d, g);
+        return r;
+    }
+    __device__ void store(const Ctx &x, size_t k, const Acc &a) const {
+        const size_t o = (size_t)x.s * c.width + k * VEC;
+        if (!x.dataless)
+            V::st(c.data + o, a.d);
+        if (x.pushed && x.local) { // PSFhandle_embedding.cc:25-26: row += pushed grad
+            float *t = c.trows + x.trow * c.width + k * VEC;
+            V::st(t, V::add(V::ld(t), a.g));
+        } else {
+            V::st(c.grad + o, a.g);
+        }
+    }
+    __device__ void end(const Ctx &x) const {
+        if (lane_id() != 0)
+            return;
+        c.slot_flags[x.s] |= F_GRAD;
+        if (x.pushed) {
+            if (x.local)
+                c.tver[x.trow] += x.upd; // PSFhandle_embedding.cc:24
+            atomicAdd(block_counter(), 1u);
+        }
+        if (push_keys) { // cache.cc:308-314: every touched line, every call
+            c.slot_version[x.s] += x.upd;
+            c.slot_updates[x.s] = x.pushed ? 0 : x.upd;
+        } else if (x.pushed && !x.dataless) { // cache.cc:171-177
+            c.slot_version[x.s] += x.upd;
+            c.slot_updates[x.s] = 0;
+        } else {
+            c.slot_updates[x.s] = x.upd;
+        }
+    }
+};
+
+// Flush the dirty victims collected since the last push (evict_, cache.cc:142-166): their whole
+// pending gradient and update count go to the owner row; the slot is freed.
+template <int VEC>
+struct FlushPending {
+    using V = RowVec<VEC>;
+    CacheView c;
+    u32 count;
+    __device__ bool begin(size_t) const {
+        return true;
+    }
+    __device__ void apply(size_t e, size_t k) const {
+        const u32 s = c.pending_list[e];
+        const u64 trow = c.slot_key[s] - c.row_begin;
+        if (trow >= c.nrows_local)
+            return;
+        float *t = c.trows + trow * c.width + k * VEC;
+        V::st(t, V::add(V::ld(t), V::ld(c.grad + (size_t)s * c.width + k * VEC)));
+    }
+    __device__ void end(size_t e) const {
+        if (lane_id() != 0)
+            return;
+        const u32 s = c.pending_list[e];
+        const u64 trow = c.slot_key[s] - c.row_begin;
+        if (trow < c.nrows_local)
+            c.tver[trow] += c.slot_updates[s];
+        c.slot_updates[s] = 0;
+        c.slot_state[s] = S_FREE;
+        c.free_stack[atomicAdd(&c.regs->free_top, 1u)] = s;
+    }
+};
+
+__global__ void flush_begin_kernel(CacheRegs *r) {
+    r->flushed = r->pending;
+}
+__global__ void flush_end_kernel(CacheRegs *r) {
+    r->pending = 0;
+}
+
+// dataless lines are dropped after the push (never inserted)
+__global__ void free_transient_kernel(CacheView c, const i32 *uslot, const u32 *miss_list, int batch) {
+    CacheRegs *r = c.regs;
+    const u32 M = batch == 0 ? r->M : r->M2;
+    for (u32 j = blockIdx.x * blockDim.x + threadIdx.x; j < M; j += gridDim.x * blockDim.x) {
+        const u32 s = (u32)uslot[miss_list[j]];
+        c.slot_state[s] = S_FREE;
+        c.slot_updates[s] = 0;
+        c.slot_flags[s] = 0;
+        c.free_stack[atomicAdd(&r->free_top, 1u)] = s;
+    }
+}
+
+__global__ void convert_keys_kernel(const float *in, u64 *out, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n)
+        out[i] = key_from_f32(in[i]);
+}
+
+// =====================================================================================
+// maintenance / debug kernels
+// =====================================================================================
+__global__ void init_slots_kernel(CacheView c) {
+    for (size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x; s < c.capacity;
+         s += (size_t)gridDim.x * blockDim.x) {
+        c.slot_prio[s] = PRIO_NONE;
+        c.slot_state[s] = S_FREE;
+        c.slot_flags[s] = 0;
+        c.slot_updates[s] = 0;
+        c.slot_use[s] = 0;
+        c.slot_version[s] = -1;
+        c.slot_key[s] = HT_EMPTY;
+        c.free_stack[s] = (u32)(c.capacity - 1 - s); // slot 0 is handed out first
+    }
+}
+
+__global__ void rebuild_index_kernel(CacheView c) {
+    for (size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x; s < c.capacity;
+         s += (size_t)gridDim.x * blockDim.x) {
+        u8 stt = c.slot_state[s];
+        if (stt == S_CACHED || stt == S_STORE)
+            if (!ht_insert(c.ht, c.ht_mask, c.slot_key[s], (u32)s, &c.regs->ht_occupied))
+                atomicMax(&c.regs->error, (u32)E_INDEX_FULL);
+    }
+}
+
+__global__ void collect_keys_kernel(CacheView c, u64 *out, u32 *count) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    const size_t rounds = (c.capacity + stride - 1) / stride;
+    for (size_t it = 0; it < rounds; it++) {
+        const size_t s = it * stride + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+        bool in = false;
+        if (s < c.capacity) {
+            u8 stt = c.slot_state[s];
+            in = stt == S_CACHED || stt == S_STORE;
+        }
+        u32 pos = warp_append(count, in);
+        if (in)
+            out[pos] = c.slot_key[s];
+    }
+}
+
+struct PeekResult {
+    i32 slot;
+    i32 updates;
+    i64 version;
+    u32 flags;
+    u32 state;
+};
+__global__ void peek_kernel(CacheView c, u64 key, PeekResult *out) {
+    i32 s = ht_find(c.ht, c.ht_mask, key);
+    out->slot = s;
+    if (s >= 0) {
+        out->updates = c.slot_updates[s];
+        out->version = c.slot_version[s];
+        out->flags = c.slot_flags[s];
+        out->state = c.slot_state[s];
+    }
+}
+
+// single-line insert(Embedding) support: overwrite or stage one line
+__global__ void set_line_kernel(CacheView c, i32 slot, i64 version, const float *data) {
+    for (u32 k = threadIdx.x; k < c.width; k += blockDim.x)
+        c.data[(size_t)slot * c.width + k] = data[k];
+    if (threadIdx.x == 0) {
+        c.slot_version[slot] = version;
+        c.slot_updates[slot] = 0;
+        c.slot_flags[slot] = 0;
+    }
+}
+// policy effect of re-inserting a resident key (lru_cache.cc:11-16, lfu_cache.cc:16-19,
+// lfuopt_cache.cc:10-17)
+__global__ void reinsert_touch_kernel(CacheView c, i32 s) {
+    CacheRegs *r = c.regs;
+    const u64 stamp = r->clock;
+    if (c.policy == HB_POLICY_LRU) {
+        c.slot_prio[s] = make_prio(0, stamp);
+        r->clock = stamp + 1;
+    } else if (c.policy == HB_POLICY_LFU) {
+        u32 use = c.slot_use[s] + 1;
+        c.slot_use[s] = use;
+        c.slot_prio[s] = make_prio(use, stamp);
+        r->clock = stamp + 1;
+    }
+}
+__global__ void single_key_kernel(u64 *uniq, u32 *num_unique, u64 key) {
+    uniq[0] = key;
+    *num_unique = 1;
+}
+__global__ void read_slot_kernel(const i32 *uslot, i32 *out) {
+    *out = uslot[0];
+}
+
+// ---- table init: counter-based generator (splitmix64 of (seed, element index)) -----------
+__host__ __device__ __forceinline__ u64 splitmix64(u64 x) {
+    x += 0x9e3779b97f4a7c15ull;
+    x = (x ^ (x >> 30)) * 0xbf58476d1ce4e5b9ull;
+    x = (x ^ (x >> 27)) * 0x94d049bb133111ebull;
+    return x ^ (x >> 31);
+}
+__device__ __forceinline__ float u01(u64 bits) { // (0,1]
+    return ((float)(bits >> 40) + 1.0f) * (1.0f / 16777216.0f);
+}
+__global__ void table_init_kernel(float *rows, size_t nelem, size_t elem_begin, int init_type,
+                                  float a, float b, u64 seed) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nelem;
+         i += (size_t)gridDim.x * blockDim.x) {
+        const u64 g = elem_begin + i;
+        float v;
+        if (init_type == 0) {
+            v = a;
+        } else if (init_type == 1) {
+            float u = u01(splitmix64(seed ^ (g * 2))) - (1.0f / 33554432.0f);
+            v = a + (b - a) * u;
+        } else {
+            u64 ctr = 0;
+            while (true) { // Box-Muller; truncated normal redraws outside 2 sigma
+                float u1 = u01(splitmix64(seed ^ (g * 2) ^ (ctr << 56)));
+                float u2 = u01(splitmix64(seed ^ (g * 2 + 1) ^ (ctr << 56)));
+                float z = sqrtf(-2.0f * logf(u1)) * cospif(2.0f * u2);
+                v = a + b * z;
+                if (init_type != 3 || fabsf(z) <= 2.0f)
+                    break;
+                ctr++;
+            }
+        }
+        rows[i] = v;
+    }
+}
+
+// =====================================================================================
+// host side
+// =====================================================================================
+std::mutex g_tables_mtx;
+std::map<int, hb_table *> g_tables;
+
+bool is_device_ptr(const void *p) {
+    cudaPointerAttributes at;
+    cudaError_t e = cudaPointerGetAttributes(&at, p);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+
+template <typename T>
+void dmalloc(T *&p, size_t count) {
+    HB_CUDA(cudaMalloc((void **)&p, std::max<size_t>(count, 1) * sizeof(T)));
+}
+template <typename T>
+void dfree(T *&p) {
+    if (p)
+        cudaFree(p);
+    p = nullptr;
+}
+
+inline int lin_grid(size_t n, int block = 256) {
+    size_t b = (n + block - 1) / block;
+    return (int)std::max<size_t>(1, std::min<size_t>(b, (size_t)sm_count() * 16));
+}
+
+struct Guard { // select the cache's device for the duration of a call
+    int prev = 0;
+    explicit Guard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev)
+            cudaSetDevice(dev);
+        else
+            prev = -1;
+    }
+    ~Guard() {
+        if (prev >= 0)
+            cudaSetDevice(prev);
+    }
+};
+
+u64 *clk_of(hb_cache *c) {
+    // four u64 right behind the perf record in the same device allocation
+    return reinterpret_cast<u64 *>(reinterpret_cast<char *>(c->dev_record) + 64);
+}
+
+void ensure_batch(hb_cache *c, size_t n) {
+    if (n <= c->batch_cap)
+        return;
+    HB_CUDA(cudaStreamSynchronize(c->stream));
+    size_t cap = std::max<size_t>(n, 4096);
+    for (int b = 0; b < 2; b++) {
+        c->ws[b].reserve(cap);
+        dfree(c->uslot[b]);
+        dfree(c->miss_list[b]);
+        dmalloc(c->uslot[b], c->ws[b].cap);
+        dmalloc(c->miss_list[b], c->ws[b].cap);
+    }
+    c->batch_cap = c->ws[0].cap;
+}
+
+// keys as given by the caller -> device pointer (staged when they live in host memory)
+const void *stage_keys(hb_cache *c, const void *keys, int kind, size_t n, int which) {
+    if (n == 0 || is_device_ptr(keys))
+        return keys;
+    size_t bytes = n * (kind == HB_KEYS_F32 ? 4 : 8);
+    if (bytes > c->keys_stage_cap) {
+        HB_CUDA(cudaStreamSynchronize(c->stream));
+        for (int b = 0; b < 2; b++) {
+            if (c->keys_stage[b])
+                cudaFree(c->keys_stage[b]);
+            HB_CUDA(cudaMalloc(&c->keys_stage[b], n * 8));
+        }
+        c->keys_stage_cap = n * 8;
+    }
+    HB_CUDA(cudaMemcpyAsync(c->keys_stage[which], keys, bytes, cudaMemcpyHostToDevice, c->stream));
+    return c->keys_stage[which];
+}
+
+float *rows_stage(hb_cache *c, size_t n, int which) {
+    size_t need = n * c->width;
+    if (need > c->rows_stage_cap[which]) {
+        HB_CUDA(cudaStreamSynchronize(c->stream));
+        dfree(c->rows_stage[which]);
+        dmalloc(c->rows_stage[which], need);
+        c->rows_stage_cap[which] = need;
+    }
+    return c->rows_stage[which];
+}
+
+void maybe_rebuild_index(hb_cache *c, size_t incoming) {
+    c->occ_upper += incoming;
+    if (c->occ_upper * 4 <= c->ht_size * 3)
+        return;
+    HB_CUDA(cudaStreamSynchronize(c->stream));
+    CacheRegs regs;
+    HB_CUDA(cudaMemcpy(&regs, c->view.regs, sizeof(regs), cudaMemcpyDeviceToHost));
+    if ((size_t)regs.ht_occupied + incoming > c->ht_size * 3 / 4) {
+        // tombstones have piled up: clear and re-insert the resident lines
+        HB_CUDA(cudaMemsetAsync(c->view.ht, 0xff, c->ht_size * sizeof(HtEntry), c->stream));
+        HB_CUDA(cudaMemsetAsync(&c->view.regs->ht_occupied, 0, sizeof(u32), c->stream));
+        rebuild_index_kernel<<<lin_grid(c->view.capacity), 256, 0, c->stream>>>(c->view);
+        HB_LAUNCHED();
+        c->occ_upper = regs.size + incoming;
+    } else {
+        c->occ_upper = regs.ht_occupied + incoming;
+    }
+}
+
+void begin_call(hb_cache *c) {
+    int idx = (int)(c->calls % hb_cache::kRing);
+    HB_CUDA(cudaEventRecord(c->ev_begin[idx], c->stream));
+    op_begin_kernel<<<1, 1, 0, c->stream>>>(c->view.regs, clk_of(c));
+    HB_LAUNCHED();
+}
+
+void end_call(hb_cache *c, int last_stage, u32 kind, size_t n, bool inserted) {
+    int idx = (int)(c->calls % hb_cache::kRing);
+    op_end_kernel<<<1, 1, 0, c->stream>>>(c->view, clk_of(c), last_stage, c->dev_record, kind, (u32)n,
+                                          inserted ? 1 : 0);
+    HB_LAUNCHED();
+    HB_CUDA(cudaMemcpyAsync(&c->ring[idx], c->dev_record, sizeof(PerfRecord), cudaMemcpyDeviceToHost,
+                            c->stream));
+    HB_CUDA(cudaEventRecord(c->ev_end[idx], c->stream));
+    c->calls++;
+}
+
+// sort + unique + resolve (+ alloc) of one key batch
+void resolve_batch(hb_cache *c, const void *dev_keys, int kind, size_t n, int batch, bool dataless,
+                   int clk_stage) {
+    KeyWorkspace &ws = c->ws[batch];
+    cudaStream_t st = c->stream;
+    ws.reset_scans(st);
+    SortedKeys sk{nullptr, nullptr};
+    if (n)
+        sk = radix_sort_keys(ws, dev_keys, kind, n, c->key_bits, st);
+    c->sorted[batch] = sk;
+    unique_from_sorted(ws, sk, n, st);
+    u32 ntiles = (u32)std::max(1, ceil_div(n, kScanBlock));
+    u64 *clk = clk_of(c);
+    resolve_kernel<<<ntiles, kScanBlock, 0, st>>>(c->view, ws.uniq, ws.num_unique, c->uslot[batch],
+                                                  c->miss_list[batch], c->bypass ? 1 : 0,
+                                                  ws.next_scan(), ntiles, clk + clk_stage,
+                                                  clk + clk_stage + 1, batch);
+    HB_LAUNCHED();
+    if (n) {
+        alloc_kernel<<<lin_grid(n), 256, 0, st>>>(c->view, ws.uniq, c->uslot[batch],
+                                                  c->miss_list[batch], batch, dataless ? 1 : 0);
+        HB_LAUNCHED();
+    }
+}
+
+bool vec4(const hb_cache *c, const void *user_rows) {
+    return c->width % 4 == 0 && reinterpret_cast<uintptr_t>(user_rows) % 16 == 0;
+}
+
+void run_sync(hb_cache *c, size_t n) {
+    if (!n)
+        return;
+    int grid = row_grid(n);
+    if (c->width % 4 == 0)
+        sync_kernel<4><<<grid, kRowBlock, 0, c->stream>>>(c->view, c->ws[0].uniq, c->uslot[0],
+                                                          c->pull_bound);
+    else
+        sync_kernel<1><<<grid, kRowBlock, 0, c->stream>>>(c->view, c->ws[0].uniq, c->uslot[0],
+                                                          c->pull_bound);
+    HB_LAUNCHED();
+}
+
+void run_gather(hb_cache *c, size_t n, float *dev_dest) {
+    if (!n)
+        return;
+    IndexFromSlots idx{c->uslot[0], c->ws[0].inverse};
+    int grid = row_grid((n + 3) / 4);
+    if (vec4(c, dev_dest))
+        gather_rows_kernel<4, 4, IndexFromSlots>
+            <<<grid, kRowBlock, 0, c->stream>>>(c->view.data, dev_dest, n, c->width, idx);
+    else
+        gather_rows_kernel<1, 4, IndexFromSlots>
+            <<<grid, kRowBlock, 0, c->stream>>>(c->view.data, dev_dest, n, c->width, idx);
+    HB_LAUNCHED();
+}
+
+void run_insert(hb_cache *c, size_t n, int clk_stage) {
+    cudaStream_t st = c->stream;
+    u64 *clk = clk_of(c);
+    plan_insert_kernel<<<1, 256, 0, st>>>(c->view, c->bypass ? 1 : 0, clk + clk_stage,
+                                          clk + clk_stage + 1);
+    HB_LAUNCHED();
+    if (!n)
+        return;
+    int sgrid = lin_grid(c->view.capacity);
+    sel_hist_kernel<<<sgrid, 256, 0, st>>>(c->view);
+    HB_LAUNCHED();
+    sel_collect_kernel<<<sgrid, 256, 0, st>>>(c->view);
+    HB_LAUNCHED();
+    sel_refine_kernel<<<1, 1024, 0, st>>>(c->view);
+    HB_LAUNCHED();
+    if (c->policy != HB_POLICY_LRU) {
+        min_use_kernel<<<sgrid, 256, 0, st>>>(c->view);
+        HB_LAUNCHED();
+        min_prio_kernel<<<sgrid, 256, 0, st>>>(c->view);
+        HB_LAUNCHED();
+        min_pick_kernel<<<sgrid, 256, 0, st>>>(c->view);
+        HB_LAUNCHED();
+    }
+    evict_apply_kernel<<<lin_grid(n), 256, 0, st>>>(c->view);
+    HB_LAUNCHED();
+    insert_new_kernel<<<lin_grid(n), 256, 0, st>>>(c->view, c->uslot[0], c->miss_list[0]);
+    HB_LAUNCHED();
+}
+
+// accumulate + push of batch `batch`, then flush of pending victims, then drop dataless lines
+void run_accumulate(hb_cache *c, size_t n, int batch, const float *dev_grads, const u64 *dev_push_keys,
+                    size_t n_push, bool use_plan) {
+    cudaStream_t st = c->stream;
+    KeyWorkspace &ws = c->ws[batch];
+    flush_begin_kernel<<<1, 1, 0, st>>>(c->view.regs);
+    HB_LAUNCHED();
+    if (n) {
+        int grid = row_grid(n);
+        const u32 *p = c->sorted[batch].perm;
+        if (vec4(c, dev_grads)) {
+            AccumulatePush<4> f{c->view, ws.uniq, c->uslot[batch], c->push_bound,
+                                use_plan ? dev_push_keys : nullptr, (u32)n_push};
+            if (use_plan && !dev_push_keys) // empty plan: nothing is pushed
+                f.push_keys = reinterpret_cast<const u64 *>(ws.uniq), f.n_push = 0;
+            segment_rows_kernel<4, AccumulatePush<4>>
+                <<<grid, kRowBlock, 0, st>>>(ws.seg_start, p, ws.num_unique, dev_grads, c->width, f);
+        } else {
+            AccumulatePush<1> f{c->view, ws.uniq, c->uslot[batch], c->push_bound,
+                                use_plan ? dev_push_keys : nullptr, (u32)n_push};
+            if (use_plan && !dev_push_keys)
+                f.push_keys = reinterpret_cast<const u64 *>(ws.uniq), f.n_push = 0;
+            segment_rows_kernel<1, AccumulatePush<1>>
+                <<<grid, kRowBlock, 0, st>>>(ws.seg_start, p, ws.num_unique, dev_grads, c->width, f);
+        }
+        HB_LAUNCHED();
+    }
+    // pending victims (count is device-side; bound the grid with the host's upper bound)
+    size_t pend = std::min<size_t>(c->pending_upper, c->view.capacity);
+    if (pend) {
+        int grid = row_grid(pend);
+        if (c->width % 4 == 0) {
+            FlushPending<4> f{c->view, 0};
+            foreach_row_kernel<4, FlushPending<4>>
+                <<<grid, kRowBlock, 0, st>>>(0, &c->view.regs->flushed, c->width, f);
+        } else {
+            FlushPending<1> f{c->view, 0};
+            foreach_row_kernel<1, FlushPending<1>>
+                <<<grid, kRowBlock, 0, st>>>(0, &c->view.regs->flushed, c->width, f);
+        }
+        HB_LAUNCHED();
+    }
+    flush_end_kernel<<<1, 1, 0, st>>>(c->view.regs);
+    HB_LAUNCHED();
+    c->pending_upper = 0;
+    if (n) {
+        free_transient_kernel<<<lin_grid(n), 256, 0, st>>>(c->view, c->uslot[batch],
+                                                           c->miss_list[batch], batch);
+        HB_LAUNCHED();
+    }
+}
+
+const u64 *stage_push_keys(hb_cache *c, const void *push_keys, int kind, size_t n_push) {
+    if (!n_push)
+        return nullptr;
+    cudaStream_t st = c->stream;
+    size_t need = n_push * 8 * 2;
+    if (need > c->push_keys_stage_cap) {
+        HB_CUDA(cudaStreamSynchronize(st));
+        if (c->push_keys_stage)
+            cudaFree(c->push_keys_stage);
+        HB_CUDA(cudaMalloc(&c->push_keys_stage, need));
+        c->push_keys_stage_cap = need;
+    }
+    u64 *out = reinterpret_cast<u64 *>(c->push_keys_stage);
+    char *raw = reinterpret_cast<char *>(c->push_keys_stage) + n_push * 8;
+    const void *dev = push_keys;
+    if (!is_device_ptr(push_keys)) {
+        HB_CUDA(cudaMemcpyAsync(raw, push_keys, n_push * (kind == HB_KEYS_F32 ? 4 : 8),
+                                cudaMemcpyHostToDevice, st));
+        dev = raw;
+    }
+    if (kind == HB_KEYS_F32) {
+        convert_keys_kernel<<<ceil_div(n_push, 256), 256, 0, st>>>((const float *)dev, out, n_push);
+        HB_LAUNCHED();
+        return out;
+    }
+    return reinterpret_cast<const u64 *>(dev);
+}
+
+void do_update(hb_cache *c, const void *keys, int kind, size_t n, const float *grads,
+               const void *push_keys, int push_kind, size_t n_push, bool use_plan) {
+    Guard g(c->device);
+    ensure_batch(c, n);
+    cudaStream_t st = c->stream;
+    const void *dkeys = stage_keys(c, keys, kind, n, 0);
+    const float *dgrads = grads;
+    if (n && !is_device_ptr(grads)) {
+        float *stage = rows_stage(c, n, 1);
+        HB_CUDA(cudaMemcpyAsync(stage, grads, n * c->width * sizeof(float), cudaMemcpyHostToDevice, st));
+        dgrads = stage;
+    }
+    const u64 *dpush = use_plan ? stage_push_keys(c, push_keys, push_kind, n_push) : nullptr;
+    begin_call(c);
+    resolve_batch(c, dkeys, kind, n, 0, /*dataless=*/true, 0);
+    run_accumulate(c, n, 0, dgrads, dpush, n_push, use_plan);
+    end_call(c, 1, 1, n, false);
+}
+
+} // namespace
+} // namespace hb
+
+using namespace hb;
+
+// =====================================================================================
+// C ABI
+// =====================================================================================
+extern "C" {
+
+int hb_table_create(int node_id, size_t length, size_t width, int device, hb_table **out) {
+    HB_API_BEGIN();
+    HB_CHECK(length > 0 && width > 0, "empty table");
+    std::lock_guard<std::mutex> lock(g_tables_mtx);
+    HB_CHECK(!g_tables.count(node_id), "table id already registered");
+    Guard g(device);
+    auto *t = new hb_table();
+    t->node_id = node_id;
+    t->device = device;
+    t->length = length;
+    t->width = width;
+    int rank = 0, world = 1;
+    hb_comm_rank(&rank, &world);
+    // AveragePartitioner: len/S rows each, the first len%S shards one more (partitioner.h:46-57)
+    size_t per = length / world, rem = length % world;
+    t->row_begin = (size_t)rank * per + std::min<size_t>(rank, rem);
+    t->nrows = per + ((size_t)rank < rem ? 1 : 0);
+    dmalloc(t->rows, t->nrows * width);
+    dmalloc(t->ver, t->nrows);
+    HB_CUDA(cudaMemset(t->rows, 0, std::max<size_t>(t->nrows * width, 1) * sizeof(float)));
+    HB_CUDA(cudaMemset(t->ver, 0, std::max<size_t>(t->nrows, 1) * sizeof(i64)));
+    g_tables[node_id] = t;
+    if (out)
+        *out = t;
+    HB_API_END();
+}
+
+int hb_table_get(int node_id, hb_table **out) {
+    HB_API_BEGIN();
+    std::lock_guard<std::mutex> lock(g_tables_mtx);
+    auto it = g_tables.find(node_id);
+    HB_CHECK(it != g_tables.end(), "no table with this node_id (InitTensor first)");
+    *out = it->second;
+    HB_API_END();
+}
+
+int hb_table_destroy(hb_table *t) {
+    HB_API_BEGIN();
+    if (t) {
+        std::lock_guard<std::mutex> lock(g_tables_mtx);
+        g_tables.erase(t->node_id);
+        Guard g(t->device);
+        HB_CUDA(cudaDeviceSynchronize());
+        dfree(t->rows);
+        dfree(t->ver);
+        delete t;
+    }
+    HB_API_END();
+}
+
+int hb_table_init(hb_table *t, int init_type, double a, double b, unsigned long long seed) {
+    HB_API_BEGIN();
+    HB_CHECK(init_type >= 0 && init_type <= 3, "unknown init_type");
+    Guard g(t->device);
+    size_t nelem = t->nrows * t->width;
+    if (nelem) {
+        table_init_kernel<<<lin_grid(nelem), 256>>>(t->rows, nelem, t->row_begin * t->width, init_type,
+                                                    (float)a, (float)b, splitmix64(seed));
+        HB_LAUNCHED();
+        HB_CUDA(cudaDeviceSynchronize());
+    }
+    HB_API_END();
+}
+
+static void clip_range(const hb_table *t, size_t row_begin, size_t nrows, size_t &lo, size_t &hi) {
+    lo = std::max(row_begin, t->row_begin);
+    hi = std::min(row_begin + nrows, t->row_begin + t->nrows);
+}
+
+int hb_table_load_rows(hb_table *t, size_t row_begin, size_t nrows, const float *rows) {
+    HB_API_BEGIN();
+    HB_CHECK(row_begin + nrows <= t->length, "row range outside the table");
+    Guard g(t->device);
+    size_t lo, hi;
+    clip_range(t, row_begin, nrows, lo, hi);
+    if (lo < hi)
+        HB_CUDA(cudaMemcpy(t->rows + (lo - t->row_begin) * t->width, rows + (lo - row_begin) * t->width,
+                           (hi - lo) * t->width * sizeof(float), cudaMemcpyDefault));
+    HB_API_END();
+}
+
+int hb_table_read_rows(hb_table *t, size_t row_begin, size_t nrows, float *rows) {
+    HB_API_BEGIN();
+    HB_CHECK(row_begin + nrows <= t->length, "row range outside the table");
+    Guard g(t->device);
+    HB_CUDA(cudaDeviceSynchronize());
+    size_t lo, hi;
+    clip_range(t, row_begin, nrows, lo, hi);
+    if (lo < hi)
+        HB_CUDA(cudaMemcpy(rows + (lo - row_begin) * t->width, t->rows + (lo - t->row_begin) * t->width,
+                           (hi - lo) * t->width * sizeof(float), cudaMemcpyDefault));
+    HB_API_END();
+}
+
+int hb_table_read_versions(hb_table *t, size_t row_begin, size_t nrows, int64_t *versions) {
+    HB_API_BEGIN();
+    HB_CHECK(row_begin + nrows <= t->length, "row range outside the table");
+    Guard g(t->device);
+    HB_CUDA(cudaDeviceSynchronize());
+    size_t lo, hi;
+    clip_range(t, row_begin, nrows, lo, hi);
+    if (lo < hi)
+        HB_CUDA(cudaMemcpy(versions + (lo - row_begin), t->ver + (lo - t->row_begin),
+                           (hi - lo) * sizeof(i64), cudaMemcpyDefault));
+    HB_API_END();
+}
+
+int hb_table_shard(hb_table *t, size_t *row_begin, size_t *nrows, float **dev_rows,
+                   int64_t **dev_versions) {
+    HB_API_BEGIN();
+    if (row_begin)
+        *row_begin = t->row_begin;
+    if (nrows)
+        *nrows = t->nrows;
+    if (dev_rows)
+        *dev_rows = t->rows;
+    if (dev_versions)
+        *dev_versions = reinterpret_cast<int64_t *>(t->ver);
+    HB_API_END();
+}
+
+// ---------------------------------------------------------------------------------------
+int hb_cache_create(int policy, size_t limit, size_t length, size_t width, int node_id,
+                    hb_cache **out) {
+    HB_API_BEGIN();
+    HB_CHECK(policy >= HB_POLICY_LRU && policy <= HB_POLICY_LFUOPT, "unknown policy");
+    HB_CHECK(limit < (1ull << 31), "limit too large");
+    hb_table *t = nullptr;
+    HB_CHECK(hb_table_get(node_id, &t) == 0, "no table with this node_id (InitTensor first)");
+    HB_CHECK(t->width == width, "cache width differs from the table's");
+    Guard g(t->device);
+    auto *c = new hb_cache();
+    c->policy = policy;
+    c->limit = limit;
+    c->length = length;
+    c->width = width;
+    c->node_id = node_id;
+    c->device = t->device;
+    c->table = t;
+    c->key_bits = bits_for(std::max<size_t>(length, t->length));
+    HB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    // row store: limit resident lines + slack for the running call's fresh lines and for dirty
+    // victims waiting for the next push
+    c->slack = std::max<size_t>(1 << 16, std::min<size_t>(limit, 1 << 22));
+    size_t cap = limit + c->slack;
+    CacheView &v = c->view;
+    v.capacity = (u32)cap;
+    v.limit = (u32)limit;
+    v.width = (u32)width;
+    v.policy = policy;
+    size_t hs = 1024;
+    while (hs < 2 * std::max<size_t>(limit, 1))
+        hs <<= 1;
+    c->ht_size = hs;
+    v.ht_mask = (u32)(hs - 1);
+    dmalloc(v.slot_key, cap);
+    dmalloc(v.slot_version, cap);
+    dmalloc(v.slot_updates, cap);
+    dmalloc(v.slot_prio, cap);
+    dmalloc(v.slot_use, cap);
+    dmalloc(v.slot_state, cap);
+    dmalloc(v.slot_flags, cap);
+    dmalloc(v.data, cap * width);
+    dmalloc(v.grad, cap * width);
+    dmalloc(v.ht, hs);
+    dmalloc(v.free_stack, cap);
+    dmalloc(v.pending_list, cap);
+    dmalloc(v.victims, cap);
+    dmalloc(v.cand_prio, 2 * cap);
+    dmalloc(v.cand_slot, 2 * cap);
+    dmalloc(v.sel_hist, kSelBins);
+    dmalloc(v.regs, 1);
+    v.trows = t->rows;
+    v.tver = t->ver;
+    v.row_begin = t->row_begin;
+    v.nrows_local = t->nrows;
+    v.table_len = t->length;
+    HB_CUDA(cudaMemset(v.ht, 0xff, hs * sizeof(HtEntry)));
+    CacheRegs regs;
+    std::memset(&regs, 0, sizeof(regs));
+    regs.free_top = (u32)cap;
+    HB_CUDA(cudaMemcpy(v.regs, &regs, sizeof(regs), cudaMemcpyHostToDevice));
+    init_slots_kernel<<<lin_grid(cap), 256>>>(v);
+    HB_LAUNCHED();
+    char *rec = nullptr;
+    HB_CUDA(cudaMalloc((void **)&rec, 128));
+    HB_CUDA(cudaMemset(rec, 0, 128));
+    c->dev_record = reinterpret_cast<PerfRecord *>(rec);
+    HB_CUDA(cudaHostAlloc((void **)&c->ring, sizeof(PerfRecord) * hb_cache::kRing, cudaHostAllocDefault));
+    std::memset(c->ring, 0, sizeof(PerfRecord) * hb_cache::kRing);
+    c->ev_begin.resize(hb_cache::kRing);
+    c->ev_end.resize(hb_cache::kRing);
+    for (int i = 0; i < hb_cache::kRing; i++) {
+        HB_CUDA(cudaEventCreate(&c->ev_begin[i]));
+        HB_CUDA(cudaEventCreate(&c->ev_end[i]));
+    }
+    HB_CUDA(cudaDeviceSynchronize());
+    *out = c;
+    HB_API_END();
+}
+
+int hb_cache_destroy(hb_cache *c) {
+    HB_API_BEGIN();
+    if (c) {
+        Guard g(c->device);
+        HB_CUDA(cudaStreamSynchronize(c->stream));
+        CacheView &v = c->view;
+        dfree(v.slot_key);
+        dfree(v.slot_version);
+        dfree(v.slot_updates);
+        dfree(v.slot_prio);
+        dfree(v.slot_use);
+        dfree(v.slot_state);
+        dfree(v.slot_flags);
+        dfree(v.data);
+        dfree(v.grad);
+        dfree(v.ht);
+        dfree(v.free_stack);
+        dfree(v.pending_list);
+        dfree(v.victims);
+        dfree(v.cand_prio);
+        dfree(v.cand_slot);
+        dfree(v.sel_hist);
+        dfree(v.regs);
+        for (int b = 0; b < 2; b++) {
+            c->ws[b].release();
+            dfree(c->uslot[b]);
+            dfree(c->miss_list[b]);
+            if (c->keys_stage[b])
+                cudaFree(c->keys_stage[b]);
+            dfree(c->rows_stage[b]);
+        }
+        if (c->push_keys_stage)
+            cudaFree(c->push_keys_stage);
+        cudaFree(c->dev_record);
+        cudaFreeHost(c->ring);
+        for (auto &e : c->ev_begin)
+            cudaEventDestroy(e);
+        for (auto &e : c->ev_end)
+            cudaEventDestroy(e);
+        cudaStreamDestroy(c->stream);
+        delete c;
+    }
+    HB_API_END();
+}
+
+int hb_cache_set_bounds(hb_cache *c, int64_t pull_bound, int64_t push_bound) {
+    HB_API_BEGIN();
+    c->pull_bound = pull_bound;
+    c->push_bound = push_bound;
+    HB_API_END();
+}
+
+int hb_cache_get_bounds(hb_cache *c, int64_t *pull_bound, int64_t *push_bound) {
+    HB_API_BEGIN();
+    *pull_bound = c->pull_bound;
+    *push_bound = c->push_bound;
+    HB_API_END();
+}
+
+int hb_cache_set_bypass(hb_cache *c, int on) {
+    HB_API_BEGIN();
+    c->bypass = on != 0;
+    HB_API_END();
+}
+
+int hb_cache_reserve(hb_cache *c, size_t max_keys) {
+    HB_API_BEGIN();
+    Guard g(c->device);
+    ensure_batch(c, max_keys);
+    HB_API_END();
+}
+
+int hb_cache_stream(hb_cache *c, void **stream) {
+    HB_API_BEGIN();
+    *stream = (void *)c->stream;
+    HB_API_END();
+}
+
+int hb_cache_lookup(hb_cache *c, const void *keys, int key_kind, size_t n, float *dest) {
+    HB_API_BEGIN();
+    Guard g(c->device);
+    HB_CHECK(n < (1ull << 31), "too many keys in one call");
+    ensure_batch(c, n);
+    maybe_rebuild_index(c, n);
+    const void *dkeys = stage_keys(c, keys, key_kind, n, 0);
+    bool host_dest = n && !is_device_ptr(dest);
+    float *ddest = host_dest ? rows_stage(c, n, 0) : dest;
+    begin_call(c);
+    resolve_batch(c, dkeys, key_kind, n, 0, /*dataless=*/false, 0);
+    run_sync(c, n);
+    run_gather(c, n, ddest);
+    run_insert(c, n, 1);
+    c->pending_upper += n;
+    end_call(c, 2, 0, n, true);
+    if (host_dest)
+        HB_CUDA(cudaMemcpyAsync(dest, ddest, n * c->width * sizeof(float), cudaMemcpyDeviceToHost,
+                                c->stream));
+    HB_API_END();
+}
+
+int hb_cache_update(hb_cache *c, const void *keys, int key_kind, size_t n, const float *grads) {
+    HB_API_BEGIN();
+    HB_CHECK(n < (1ull << 31), "too many keys in one call");
+    do_update(c, keys, key_kind, n, grads, nullptr, 0, 0, false);
+    HB_API_END();
+}
+
+int hb_cache_update_with_push_keys(hb_cache *c, const void *keys, int key_kind, size_t n,
+                                   const void *push_keys, int push_key_kind, size_t n_push,
+                                   const float *grads) {
+    HB_API_BEGIN();
+    HB_CHECK(n < (1ull << 31), "too many keys in one call");
+    do_update(c, keys, key_kind, n, grads, push_keys, push_key_kind, n_push, true);
+    HB_API_END();
+}
+
+int hb_cache_push_pull(hb_cache *c, const void *pull_keys, int pull_kind, size_t n_pull, float *dest,
+                       const void *push_keys, int push_kind, size_t n_push, const float *grads) {
+    HB_API_BEGIN();
+    Guard g(c->device);
+    HB_CHECK(n_pull < (1ull << 31) && n_push < (1ull << 31), "too many keys in one call");
+    ensure_batch(c, std::max(n_pull, n_push));
+    maybe_rebuild_index(c, n_pull);
+    cudaStream_t st = c->stream;
+    const void *dpull = stage_keys(c, pull_keys, pull_kind, n_pull, 0);
+    const void *dpush = stage_keys(c, push_keys, push_kind, n_push, 1);
+    bool host_dest = n_pull && !is_device_ptr(dest);
+    float *ddest = host_dest ? rows_stage(c, n_pull, 0) : dest;
+    const float *dgrads = grads;
+    if (n_push && !is_device_ptr(grads)) {
+        float *stage = rows_stage(c, n_push, 1);
+        HB_CUDA(cudaMemcpyAsync(stage, grads, n_push * c->width * sizeof(float),
+                                cudaMemcpyHostToDevice, st));
+        dgrads = stage;
+    }
+    begin_call(c);
+    // cache.cc:360-391: pull-side lookup, then push-side lookup + accumulate
+    resolve_batch(c, dpull, pull_kind, n_pull, 0, /*dataless=*/false, 0);
+    resolve_batch(c, dpush, push_kind, n_push, 1, /*dataless=*/true, 1);
+    // server order (PSFhandle_embedding.cc:66-79): push first, then sync
+    run_accumulate(c, n_push, 1, dgrads, nullptr, 0, false);
+    run_sync(c, n_pull);
+    run_gather(c, n_pull, ddest);
+    run_insert(c, n_pull, 2);
+    c->pending_upper += n_pull;
+    end_call(c, 3, 2, n_pull, true);
+    if (host_dest)
+        HB_CUDA(cudaMemcpyAsync(dest, ddest, n_pull * c->width * sizeof(float),
+                                cudaMemcpyDeviceToHost, st));
+    HB_API_END();
+}
+
+static void fill_perf(hb_cache *c, uint64_t call, hb_perf *perf) {
+    int idx = (int)(call % hb_cache::kRing);
+    const PerfRecord &r = c->ring[idx];
+    std::memset(perf, 0, sizeof(*perf));
+    perf->num_all = r.num_all;
+    perf->num_unique = r.num_unique;
+    perf->num_miss = r.num_miss;
+    perf->num_evict = r.num_evict;
+    perf->num_transfered = r.num_transfered;
+    perf->is_full = r.limit_full;
+    perf->size = r.size;
+    perf->error = r.error;
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, c->ev_begin[idx], c->ev_end[idx]) == cudaSuccess)
+        perf->time_ms = ms;
+    else
+        cudaGetLastError();
+}
+
+int hb_cache_wait(hb_cache *c, hb_perf *perf) {
+    HB_API_BEGIN();
+    Guard g(c->device);
+    HB_CUDA(cudaStreamSynchronize(c->stream));
+    if (c->calls) {
+        int idx = (int)((c->calls - 1) % hb_cache::kRing);
+        const PerfRecord &r = c->ring[idx];
+        c->occ_upper = r.ht_occupied;
+        c->pending_upper = std::max<size_t>(c->pending_upper, r.pending);
+        if (perf)
+            fill_perf(c, c->calls - 1, perf);
+        if (r.error) {
+            static const char *names[] = {"", "row store slack exhausted (too many transient/pending lines)",
+                                          "cache index full", "key outside the table",
+                                          "pending-eviction list overflow"};
+            throw Error(std::string("device-side cache failure: ") + names[std::min<u32>(r.error, 4)]);
+        }
+    } else if (perf) {
+        std::memset(perf, 0, sizeof(*perf));
+    }
+    HB_API_END();
+}
+
+int hb_cache_perf_history(hb_cache *c, hb_perf *out, int *kinds, int max, int *written) {
+    HB_API_BEGIN();
+    Guard g(c->device);
+    HB_CUDA(cudaStreamSynchronize(c->stream));
+    uint64_t avail = std::min<uint64_t>(c->calls, hb_cache::kRing);
+    uint64_t take = std::min<uint64_t>(avail, (uint64_t)std::max(max, 0));
+    for (uint64_t k = 0; k < take; k++) {
+        uint64_t call = c->calls - take + k;
+        fill_perf(c, call, &out[k]);
+        if (kinds)
+            kinds[k] = (int)c->ring[call % hb_cache::kRing].kind;
+    }
+    *written = (int)take;
+    HB_API_END();
+}
+
+int hb_cache_size(hb_cache *c, size_t *size) {
+    HB_API_BEGIN();
+    Guard g(c->device);
+    HB_CUDA(cudaStreamSynchronize(c->stream));
+    CacheRegs regs;
+    HB_CUDA(cudaMemcpy(&regs, c->view.regs, sizeof(regs), cudaMemcpyDeviceToHost));
+    *size = regs.size;
+    HB_API_END();
+}
+
+static PeekResult peek(hb_cache *c, uint64_t key) {
+    PeekResult *d = nullptr, h;
+    HB_CUDA(cudaMalloc((void **)&d, sizeof(PeekResult)));
+    peek_kernel<<<1, 1, 0, c->stream>>>(c->view, key, d);
+    g_launches++;
+    cudaError_t e = cudaMemcpyAsync(&h, d, sizeof(h), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess)
+        e = cudaStreamSynchronize(c->stream);
+    cudaFree(d);
+    HB_CUDA(e);
+    return h;
+}
+
+int hb_cache_count(hb_cache *c, uint64_t key, int *count) {
+    HB_API_BEGIN();
+    Guard g(c->device);
+    *count = peek(c, key).slot >= 0 ? 1 : 0;
+    HB_API_END();
+}
+
+int hb_cache_keys(hb_cache *c, uint64_t *keys, size_t capacity, size_t *n) {
+    HB_API_BEGIN();
+    Guard g(c->device);
+    u64 *dkeys = nullptr;
+    u32 *dcount = nullptr;
+    dmalloc(dkeys, c->view.capacity);
+    dmalloc(dcount, 1);
+    HB_CUDA(cudaMemsetAsync(dcount, 0, sizeof(u32), c->stream));
+    collect_keys_kernel<<<lin_grid(c->view.capacity), 256, 0, c->stream>>>(c->view, dkeys, dcount);
+    HB_LAUNCHED();
+    u32 count = 0;
+    HB_CUDA(cudaMemcpyAsync(&count, dcount, sizeof(u32), cudaMemcpyDeviceToHost, c->stream));
+    HB_CUDA(cudaStreamSynchronize(c->stream));
+    *n = count;
+    size_t take = std::min<size_t>(count, capacity);
+    std::vector<u64> host(count);
+    if (count)
+        HB_CUDA(cudaMemcpy(host.data(), dkeys, count * sizeof(u64), cudaMemcpyDeviceToHost));
+    std::sort(host.begin(), host.end()); // LRUCache::PyAPI_keys sorts (lru_cache.cc:41-48)
+    for (size_t i = 0; i < take; i++)
+        keys[i] = host[i];
+    dfree(dkeys);
+    dfree(dcount);
+    HB_API_END();
+}
+
+int hb_cache_peek(hb_cache *c, uint64_t key, int *found, int64_t *version, int64_t *updates,
+                  float *data, float *grad) {
+    HB_API_BEGIN();
+    Guard g(c->device);
+    PeekResult r = peek(c, key);
+    *found = r.slot >= 0;
+    if (r.slot >= 0) {
+        if (version)
+            *version = r.version;
+        if (updates)
+            *updates = r.updates;
+        if (data)
+            HB_CUDA(cudaMemcpy(data, c->view.data + (size_t)r.slot * c->width, c->width * sizeof(float),
+                               cudaMemcpyDeviceToHost));
+        if (grad) {
+            if (r.updates != 0)
+                HB_CUDA(cudaMemcpy(grad, c->view.grad + (size_t)r.slot * c->width,
+                                   c->width * sizeof(float), cudaMemcpyDeviceToHost));
+            else
+                std::memset(grad, 0, c->width * sizeof(float)); // logically zero after a push
+        }
+    }
+    HB_API_END();
+}
+
+int hb_cache_touch(hb_cache *c, uint64_t key, int *found, int64_t *version, float *data) {
+    HB_API_BEGIN();
+    Guard g(c->device);
+    ensure_batch(c, 1);
+    cudaStream_t st = c->stream;
+    KeyWorkspace &ws = c->ws[0];
+    // a batched lookup of one key without the insert/sync half: CacheBase::lookup via python
+    begin_call(c);
+    ws.reset_scans(st);
+    single_key_kernel<<<1, 1, 0, st>>>(ws.uniq, ws.num_unique, key);
+    HB_LAUNCHED();
+    u64 *clk = clk_of(c);
+    resolve_kernel<<<1, kScanBlock, 0, st>>>(c->view, ws.uniq, ws.num_unique, c->uslot[0],
+                                             c->miss_list[0], c->bypass ? 1 : 0, ws.next_scan(), 1,
+                                             clk, clk + 1, 0);
+    HB_LAUNCHED();
+    // a miss reserved a slot for a fresh line; materialise and hand it back (lookup() alone
+    // allocates nothing)
+    alloc_kernel<<<1, 32, 0, st>>>(c->view, ws.uniq, c->uslot[0], c->miss_list[0], 0, 0);
+    HB_LAUNCHED();
+    free_transient_kernel<<<1, 32, 0, st>>>(c->view, c->uslot[0], c->miss_list[0], 0);
+    HB_LAUNCHED();
+    end_call(c, 1, 0, 1, false);
+    HB_CUDA(cudaStreamSynchronize(st));
+    PeekResult r = peek(c, key);
+    *found = r.slot >= 0;
+    if (r.slot >= 0) {
+        if (version)
+            *version = r.version;
+        if (data)
+            HB_CUDA(cudaMemcpy(data, c->view.data + (size_t)r.slot * c->width, c->width * sizeof(float),
+                               cudaMemcpyDeviceToHost));
+    }
+    HB_API_END();
+}
+
+int hb_cache_insert(hb_cache *c, uint64_t key, int64_t version, const float *data) {
+    HB_API_BEGIN();
+    Guard g(c->device);
+    ensure_batch(c, 1);
+    maybe_rebuild_index(c, 1);
+    cudaStream_t st = c->stream;
+    float *ddata = rows_stage(c, 1, 1);
+    HB_CUDA(cudaMemcpyAsync(ddata, data, c->width * sizeof(float), cudaMemcpyDefault, st));
+    PeekResult r = peek(c, key);
+    if (r.slot >= 0) {
+        set_line_kernel<<<1, 128, 0, st>>>(c->view, r.slot, version, ddata);
+        HB_LAUNCHED();
+        if (r.state == S_CACHED) {
+            reinsert_touch_kernel<<<1, 1, 0, st>>>(c->view, r.slot);
+            HB_LAUNCHED();
+        }
+    } else {
+        KeyWorkspace &ws = c->ws[0];
+        begin_call(c);
+        ws.reset_scans(st);
+        single_key_kernel<<<1, 1, 0, st>>>(ws.uniq, ws.num_unique, key);
+        HB_LAUNCHED();
+        u64 *clk = clk_of(c);
+        // bypass=1: resolve as a miss without touching anything, which allocates the fresh line
+        resolve_kernel<<<1, kScanBlock, 0, st>>>(c->view, ws.uniq, ws.num_unique, c->uslot[0],
+                                                 c->miss_list[0], 1, ws.next_scan(), 1, clk, clk, 0);
+        HB_LAUNCHED();
+        alloc_kernel<<<1, 32, 0, st>>>(c->view, ws.uniq, c->uslot[0], c->miss_list[0], 0, 0);
+        HB_LAUNCHED();
+        i32 *dslot = nullptr, hslot = -1;
+        dmalloc(dslot, 1);
+        read_slot_kernel<<<1, 1, 0, st>>>(c->uslot[0], dslot);
+        HB_LAUNCHED();
+        HB_CUDA(cudaMemcpyAsync(&hslot, dslot, sizeof(i32), cudaMemcpyDeviceToHost, st));
+        HB_CUDA(cudaStreamSynchronize(st));
+        dfree(dslot);
+        HB_CHECK(hslot >= 0, "no free slot for insert");
+        set_line_kernel<<<1, 128, 0, st>>>(c->view, hslot, version, ddata);
+        HB_LAUNCHED();
+        run_insert(c, 1, 0);
+        c->pending_upper += 1;
+        end_call(c, 1, 0, 1, true);
+    }
+    HB_CUDA(cudaStreamSynchronize(st));
+    HB_API_END();
+}
+
+} // extern "C"

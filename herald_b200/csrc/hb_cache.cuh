@@ -1,0 +1,179 @@
+// Device-resident worker cache + owner table shard (types shared by hb_cache.cu / hb_comm.cu).
+//
+// Replaces, on one B200:
+//   worker side  src/hetu_cache (LRU/LFU/LFUOpt + CacheBase)                      -> hb_cache
+//   owner side   ps-lite CacheTable + PSFhandle_embedding.cc handlers             -> hb_table
+// Both live in HBM; a "pull" or "push" between them is a row copy / row add inside one kernel.
+#pragma once
+
+#include <vector>
+
+#include "hb_common.cuh"
+#include "hb_sort.cuh"
+
+struct hb_table {
+    int node_id = 0;
+    int device = 0;
+    size_t length = 0, width = 0; // global table geometry
+    size_t row_begin = 0, nrows = 0; // rows owned by this rank
+    float *rows = nullptr;           // [nrows, width]
+    hb::i64 *ver = nullptr;          // [nrows]  (ps-lite/include/ps/server/param.h:124)
+};
+
+namespace hb {
+
+// ---- open-addressing index: key -> slot ------------------------------------------------
+struct __align__(16) HtEntry {
+    u64 key;
+    u32 slot;
+    u32 pad;
+};
+constexpr u64 HT_EMPTY = ~0ull;
+constexpr u64 HT_TOMB = ~0ull - 1;
+
+// slot states
+enum : u8 {
+    S_FREE = 0,
+    S_CACHED = 1,    // in the index, evictable
+    S_STORE = 2,     // in the index, LFUOpt permanent store (never evicted)
+    S_TRANSIENT = 3, // line of the running call, not (yet) in the index
+    S_PENDING = 4    // evicted while dirty: waits for the next push (CacheBase::evict_)
+};
+// slot flags
+enum : u8 {
+    F_GRAD = 1,    // Line::grad_ has been allocated (embedding.h:120-123): addup() adds it
+    F_DATALESS = 2 // Line built with init_data=false by an update miss (cache.cc:146-151)
+};
+
+// replacement priority word: (min(use, kUseSat) << 52) | stamp, ~0 for slots that cannot be evicted
+constexpr int kStampBits = 52;
+constexpr u64 kStampMask = (1ull << kStampBits) - 1;
+constexpr u32 kUseSat = 4095;
+constexpr u64 PRIO_NONE = ~0ull;
+constexpr int kSelBins = 4096; // radix of the victim selection
+constexpr int kSelBits = 12;
+constexpr u32 kLfuOptUseMax = 10; // src/hetu_cache/include/lfuopt_cache.h:25
+
+// device error codes (hb_perf.error)
+enum : u32 {
+    E_NONE = 0,
+    E_NO_FREE_SLOT = 1,  // transient + pending lines exceeded the slack of the row store
+    E_INDEX_FULL = 2,    // open-addressing index could not place a key
+    E_KEY_RANGE = 3,     // key >= table length
+    E_EVICT_OVERFLOW = 4 // pending-eviction list overflow
+};
+
+// Mutable scalars of one cache, resident in device memory (one cache line or two).
+struct CacheRegs {
+    // persistent
+    u32 size;        // lines in the index (evictable + store)
+    u32 store_size;  // LFUOpt permanent lines
+    u32 free_top;    // height of the free-slot stack
+    u32 pending;     // dirty victims awaiting a push
+    u32 ht_occupied; // non-EMPTY index entries (live + tombstones)
+    u32 error;
+    u64 clock; // replacement clock: one tick per policy touch / insert
+    u64 floor; // lower bound of the stamps of the policy's victim class
+    // per call (zeroed by op_begin)
+    u64 clock0;     // clock at call start
+    u32 U;          // unique keys of the batch being resolved
+    u32 M;          // misses among them
+    u32 alloc_base; // free_stack[alloc_base + j] is the slot of miss j
+    u32 pulled;     // rows transferred by the sync
+    u32 pushed;     // lines pushed by the update
+    u32 flushed;    // pending victims flushed by the update
+    // insert planning
+    u32 E;         // evictions required by the policy
+    u32 k_old;     // of which: resident lines selected by stamp
+    u32 n_drop;    // new lines that do not survive the call (first n_drop misses)
+    u32 need_min;  // LFU corner: evict the global minimum (use, stamp) line
+    u32 nv;        // victims collected so far
+    u32 nc;        // boundary candidates collected
+    u32 sel_shift; // bin shift of the first selection level
+    u32 sel_bin;   // threshold bin
+    u32 sel_rem;   // victims still to take from the threshold bin
+    u32 min_use;   // scratch of the global-minimum search
+    u64 min_prio;
+    u64 ins_clock0; // stamps of inserted lines start here
+    // second batch of a push_pull call
+    u32 U2, M2, alloc_base2, pad2;
+};
+
+// Everything a kernel needs to address the cache (passed by value).
+struct CacheView {
+    // geometry
+    u32 capacity; // slots in the row store (limit + slack)
+    u32 limit;
+    u32 width;
+    u32 ht_mask;
+    int policy;
+    // slot arrays
+    u64 *slot_key;
+    i64 *slot_version;
+    i32 *slot_updates;
+    u64 *slot_prio;
+    u32 *slot_use;
+    u8 *slot_state;
+    u8 *slot_flags;
+    float *data;
+    float *grad;
+    HtEntry *ht;
+    u32 *free_stack;
+    u32 *pending_list;
+    u32 *victims;    // [capacity]
+    u64 *cand_prio;  // [2][capacity] boundary candidates (ping-pong)
+    u32 *cand_slot;  // [2][capacity]
+    u32 *sel_hist;   // [kSelBins]
+    CacheRegs *regs;
+    // owner shard (same GPU)
+    float *trows;
+    i64 *tver;
+    u64 row_begin, nrows_local, table_len;
+};
+
+// counters copied to pinned host memory at the end of every call
+struct PerfRecord {
+    u32 kind; // 0 pull, 1 push, 2 push_pull
+    u32 num_all, num_unique, num_miss, num_evict, num_transfered;
+    u32 size, error, ht_occupied, pending, limit_full;
+    u32 pad;
+};
+
+} // namespace hb
+
+struct hb_cache {
+    int policy = 0;
+    size_t limit = 0, length = 0, width = 0;
+    int node_id = 0;
+    int device = 0;
+    hb::i64 pull_bound = 5, push_bound = 5;
+    bool bypass = false;
+    hb_table *table = nullptr;
+    cudaStream_t stream = nullptr;
+    hb::CacheView view{};
+    size_t ht_size = 0;
+    size_t slack = 0;
+    hb::KeyWorkspace ws[2];
+    hb::SortedKeys sorted[2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+    // per-batch resolve results (sized with the workspaces)
+    hb::i32 *uslot[2] = {nullptr, nullptr};
+    hb::u32 *miss_list[2] = {nullptr, nullptr};
+    size_t batch_cap = 0;
+    // staging for host-memory callers
+    void *keys_stage[2] = {nullptr, nullptr};
+    size_t keys_stage_cap = 0;
+    float *rows_stage[2] = {nullptr, nullptr};
+    size_t rows_stage_cap[2] = {0, 0};
+    void *push_keys_stage = nullptr;
+    size_t push_keys_stage_cap = 0;
+    // perf ring (pinned host) + events
+    hb::PerfRecord *ring = nullptr;
+    hb::PerfRecord *dev_record = nullptr;
+    static constexpr int kRing = 1024;
+    uint64_t calls = 0;
+    std::vector<cudaEvent_t> ev_begin, ev_end;
+    // host-side upper bound of index occupancy (refreshed at wait)
+    size_t occ_upper = 0;
+    size_t pending_upper = 0;
+    int key_bits = 64;
+};

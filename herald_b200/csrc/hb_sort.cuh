@@ -1,0 +1,60 @@
+// Device-side sorted-unique machinery: stable LSD radix sort of (key, index) pairs, then a
+// single-pass scan that emits ascending unique keys, the inverse map and the occurrence
+// segments.  Replaces the host-side dedup of both reference variants:
+//   Unique<T> (argsort + scan)           src/hetu_cache/include/unqiue_tools.h:9-48
+//   np.unique(return_inverse=True)       python/hetu/ndarray.py:532-536
+// Both produce ASCENDING unique ids; the stable sort additionally yields, for every unique
+// key, its occurrences in ascending original index, which is the order the reference
+// accumulates gradients in (src/hetu_cache/src/cache.cc:145-154).
+#pragma once
+
+#include "hb_common.cuh"
+
+namespace hb {
+
+constexpr int kScanSlots = 12;  // independent grid-scan states per workspace
+constexpr int kScanBlock = 256; // threads per scan tile
+
+// Per-call scratch, sized for `cap` keys.  All device memory.
+struct KeyWorkspace {
+    size_t cap = 0;
+    u64 *keys[2] = {nullptr, nullptr}; // ping-pong sort buffers (keys)
+    u32 *vals[2] = {nullptr, nullptr}; // ping-pong sort buffers (original index)
+    u32 *blk_hist = nullptr;           // [RADIX][nblk] digit counts / offsets
+    size_t nblk_cap = 0;
+    // results of unique_from_sorted
+    u64 *uniq = nullptr;      // [cap]   ascending unique keys
+    u32 *inverse = nullptr;   // [cap]   rank of keys[i] in uniq
+    u32 *seg_start = nullptr; // [cap+1] first sorted position of each unique key
+    u32 *num_unique = nullptr; // device scalar
+    // scan arena: kScanSlots x (ticket + status[ntile_cap])
+    u64 *scan_arena = nullptr;
+    size_t ntile_cap = 0;
+    int scan_next = 0;
+
+    void reserve(size_t n);
+    void release();
+    size_t scan_slot_words() const {
+        return ntile_cap + 1;
+    }
+    // zero every scan slot (one memset) — call once at the start of an op
+    void reset_scans(cudaStream_t st);
+    ScanState next_scan();
+};
+
+struct SortedKeys {
+    const u64 *keys; // ascending
+    const u32 *perm; // perm[p] = original index of sorted position p (stable)
+};
+
+// keys_in: n keys of `key_kind` (HB_KEYS_U64 / HB_KEYS_F32) in device memory.
+// key_bits: keys are < 2^key_bits (fewer bits = fewer passes).
+SortedKeys radix_sort_keys(KeyWorkspace &ws, const void *keys_in, int key_kind, size_t n,
+                           int key_bits, cudaStream_t st);
+
+// Fills ws.uniq / ws.inverse / ws.seg_start / ws.num_unique from a sorted sequence.
+void unique_from_sorted(KeyWorkspace &ws, const SortedKeys &sk, size_t n, cudaStream_t st);
+
+int bits_for(u64 max_key_exclusive);
+
+} // namespace hb

@@ -1,0 +1,350 @@
+"""`hetu_cache` — the reference's pybind module surface (src/hetu_cache/src/python_api.cc:10-79)
+on top of the hb_cache_* C-ABI.  Import it as ``from herald_b200 import hetu_cache`` where the
+reference does ``import hetu_cache`` (python/hetu/cstable.py:23-24).
+
+The cache, its index and the rows live in HBM.  Every batch method accepts host memory (the
+reference's contract: numpy arrays or raw host pointers) or device pointers, returns immediately
+with a ``_waittype`` and completes on ``.wait()``; callers keep keys/dest/grads alive until
+then, exactly as the reference requires (cstable.py:38-45).
+"""
+import ctypes
+
+import numpy as np
+
+from ._base import _LIB, check_call
+
+_sz = ctypes.c_size_t
+_vp = ctypes.c_void_p
+
+KEYS_U64, KEYS_F32 = 0, 1
+_POLICY = {"lru": 0, "lfu": 1, "lfuopt": 2}
+
+
+class hb_perf(ctypes.Structure):
+    _fields_ = [("num_all", ctypes.c_int64), ("num_unique", ctypes.c_int64),
+                ("num_miss", ctypes.c_int64), ("num_evict", ctypes.c_int64),
+                ("num_transfered", ctypes.c_int64), ("is_full", ctypes.c_int64),
+                ("size", ctypes.c_int64), ("error", ctypes.c_int64),
+                ("time_ms", ctypes.c_float), ("sort_ms", ctypes.c_float),
+                ("lookup_ms", ctypes.c_float), ("transfer_ms", ctypes.c_float),
+                ("copy_ms", ctypes.c_float), ("insert_ms", ctypes.c_float)]
+
+
+def _proto():
+    L = _LIB
+    L.hb_cache_create.argtypes = [ctypes.c_int, _sz, _sz, _sz, ctypes.c_int, ctypes.POINTER(_vp)]
+    L.hb_cache_destroy.argtypes = [_vp]
+    L.hb_cache_set_bounds.argtypes = [_vp, ctypes.c_int64, ctypes.c_int64]
+    L.hb_cache_get_bounds.argtypes = [_vp, ctypes.POINTER(ctypes.c_int64),
+                                      ctypes.POINTER(ctypes.c_int64)]
+    L.hb_cache_set_bypass.argtypes = [_vp, ctypes.c_int]
+    L.hb_cache_reserve.argtypes = [_vp, _sz]
+    L.hb_cache_stream.argtypes = [_vp, ctypes.POINTER(_vp)]
+    L.hb_cache_lookup.argtypes = [_vp, _vp, ctypes.c_int, _sz, _vp]
+    L.hb_cache_update.argtypes = [_vp, _vp, ctypes.c_int, _sz, _vp]
+    L.hb_cache_update_with_push_keys.argtypes = [_vp, _vp, ctypes.c_int, _sz, _vp, ctypes.c_int,
+                                                 _sz, _vp]
+    L.hb_cache_push_pull.argtypes = [_vp, _vp, ctypes.c_int, _sz, _vp, _vp, ctypes.c_int, _sz, _vp]
+    L.hb_cache_wait.argtypes = [_vp, ctypes.POINTER(hb_perf)]
+    L.hb_cache_perf_history.argtypes = [_vp, ctypes.POINTER(hb_perf), ctypes.POINTER(ctypes.c_int),
+                                        ctypes.c_int, ctypes.POINTER(ctypes.c_int)]
+    L.hb_cache_size.argtypes = [_vp, ctypes.POINTER(_sz)]
+    L.hb_cache_count.argtypes = [_vp, ctypes.c_uint64, ctypes.POINTER(ctypes.c_int)]
+    L.hb_cache_keys.argtypes = [_vp, _vp, _sz, ctypes.POINTER(_sz)]
+    L.hb_cache_peek.argtypes = [_vp, ctypes.c_uint64, ctypes.POINTER(ctypes.c_int),
+                                ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64),
+                                _vp, _vp]
+    L.hb_cache_touch.argtypes = [_vp, ctypes.c_uint64, ctypes.POINTER(ctypes.c_int),
+                                 ctypes.POINTER(ctypes.c_int64), _vp]
+    L.hb_cache_insert.argtypes = [_vp, ctypes.c_uint64, ctypes.c_int64, _vp]
+
+
+_proto()
+
+
+def _check_c_contiguous(arr, what):
+    # binding.h:51-57 raises std::runtime_error("Array not continuous in C: ...")
+    if not arr.flags["C_CONTIGUOUS"]:
+        raise RuntimeError("Array not continuous in C: " + what)
+
+
+class _waittype(object):
+    """Handle of an enqueued cache call (python_api.cc:16-19): ``wait()`` blocks until it — and
+    everything enqueued on the cache before it — has finished, then records the perf entry."""
+
+    def __init__(self, cache, keepalive):
+        self._cache = cache
+        self._keep = keepalive
+        self._seq = cache._issued
+
+    def wait(self):
+        self._cache._drain()
+        self._keep = None
+
+
+class Embedding(object):
+    """One cache line as seen from Python (python_api.cc:21-30)."""
+
+    def __init__(self, key, version, data, grad=None, updates=0):
+        data = np.ascontiguousarray(data, dtype=np.float32)
+        assert data.ndim == 1
+        self.key = int(key)
+        self.version = int(version)
+        self.data = data
+        self.grad = np.zeros_like(data) if grad is None else grad
+        self.updates = int(updates)
+
+    def mean(self):
+        return float(np.sum(self.data.astype(np.float64)) / self.data.size)
+
+    def var(self):
+        d = self.data.astype(np.float64)
+        return float(np.sum((d - d.mean()) ** 2) / d.size)
+
+    def __repr__(self):
+        return "<hetu.Embedding : key:%d, len:%d, version:%d, mean:%g, var:%g>" % (
+            self.key, self.data.size, self.version, self.mean(), self.var())
+
+
+class CacheBase(object):
+    _policy = None
+
+    def __init__(self, limit, length, width, node_id):
+        self._h = _vp()
+        self._limit, self._length, self._width, self._node_id = (int(limit), int(length),
+                                                                 int(width), int(node_id))
+        check_call(_LIB.hb_cache_create(_POLICY[self._policy], self._limit, self._length,
+                                        self._width, self._node_id, ctypes.byref(self._h)))
+        self._perf = []
+        self._perf_enabled = False
+        self._issued = 0    # calls enqueued
+        self._recorded = 0  # calls whose perf entry has been collected
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h and _LIB is not None:
+            _LIB.hb_cache_destroy(h)
+            self._h = None
+
+    # ---- properties (python_api.cc:32-41) ------------------------------------------------
+    @property
+    def limit(self):
+        return self._limit
+
+    @property
+    def width(self):
+        return self._width
+
+    @property
+    def perf(self):
+        self._drain()
+        return self._perf
+
+    @property
+    def perf_enabled(self):
+        return self._perf_enabled
+
+    @perf_enabled.setter
+    def perf_enabled(self, value):
+        self._drain()
+        self._perf_enabled = bool(value)
+
+    def _bounds(self):
+        a, b = ctypes.c_int64(), ctypes.c_int64()
+        check_call(_LIB.hb_cache_get_bounds(self._h, ctypes.byref(a), ctypes.byref(b)))
+        return a.value, b.value
+
+    @property
+    def pull_bound(self):
+        return self._bounds()[0]
+
+    @pull_bound.setter
+    def pull_bound(self, v):
+        check_call(_LIB.hb_cache_set_bounds(self._h, int(v), self._bounds()[1]))
+
+    @property
+    def push_bound(self):
+        return self._bounds()[1]
+
+    @push_bound.setter
+    def push_bound(self, v):
+        check_call(_LIB.hb_cache_set_bounds(self._h, self._bounds()[0], int(v)))
+
+    def bypass(self):
+        check_call(_LIB.hb_cache_set_bypass(self._h, 1))
+
+    def undo_bypass(self):
+        check_call(_LIB.hb_cache_set_bypass(self._h, 0))
+
+    def reserve(self, max_keys):
+        check_call(_LIB.hb_cache_reserve(self._h, int(max_keys)))
+
+    @property
+    def stream(self):
+        """cudaStream_t (as int) that orders this cache's work — for device-pointer callers."""
+        s = _vp()
+        check_call(_LIB.hb_cache_stream(self._h, ctypes.byref(s)))
+        return s.value
+
+    # ---- completion / perf -------------------------------------------------------------
+    def _drain(self):
+        """Synchronise and collect the perf entries of finished calls (cache.cc:89-106,179-196)."""
+        if self._recorded == self._issued and self._issued:
+            return
+        last = hb_perf()
+        check_call(_LIB.hb_cache_wait(self._h, ctypes.byref(last)))
+        pending = self._issued - self._recorded
+        if pending and self._perf_enabled:
+            buf = (hb_perf * pending)()
+            kinds = (ctypes.c_int * pending)()
+            got = ctypes.c_int()
+            check_call(_LIB.hb_cache_perf_history(self._h, buf, kinds, pending, ctypes.byref(got)))
+            for k in range(got.value):
+                p = buf[k]
+                if kinds[k] == 2:   # push_pull records nothing in the reference
+                    continue
+                d = {"type": "Pull" if kinds[k] == 0 else "Push", "is_full": bool(p.is_full),
+                     "num_all": int(p.num_all), "num_unique": int(p.num_unique),
+                     "num_miss": int(p.num_miss), "num_transfered": int(p.num_transfered),
+                     "time": float(p.time_ms), "sort_time": float(p.sort_ms),
+                     "lookup_time": float(p.lookup_ms), "transfer_time": float(p.transfer_ms),
+                     "copy_time": float(p.copy_ms)}
+                if kinds[k] == 0:
+                    d["prepare_time"] = 0.0
+                    d["insert_time"] = float(p.insert_ms)
+                else:
+                    d["num_evict"] = int(p.num_evict)
+                    d["cleanup_time"] = 0.0
+                self._perf.append(d)
+        self._recorded = self._issued
+
+    def _issue(self, *keepalive):
+        self._issued += 1
+        return _waittype(self, keepalive)
+
+    # ---- numpy entry points (uint64 keys) ------------------------------------------------
+    def embedding_lookup(self, keys, dest):
+        _check_c_contiguous(keys, "keys")
+        _check_c_contiguous(dest, "dest")
+        assert keys.dtype == np.uint64 and dest.dtype == np.float32
+        assert dest.size == keys.size * self._width
+        check_call(_LIB.hb_cache_lookup(self._h, keys.ctypes.data, KEYS_U64, keys.size,
+                                        dest.ctypes.data))
+        return self._issue(keys, dest)
+
+    def embedding_update(self, keys, grads):
+        _check_c_contiguous(keys, "keys")
+        _check_c_contiguous(grads, "grads")
+        assert keys.dtype == np.uint64 and grads.dtype == np.float32
+        assert grads.size == keys.size * self._width
+        check_call(_LIB.hb_cache_update(self._h, keys.ctypes.data, KEYS_U64, keys.size,
+                                        grads.ctypes.data))
+        return self._issue(keys, grads)
+
+    def embedding_update_with_push_keys(self, keys, push_keys, grads):
+        for a, w in ((keys, "keys"), (push_keys, "push_keys"), (grads, "grads")):
+            _check_c_contiguous(a, w)
+        assert keys.dtype == np.uint64 and push_keys.dtype == np.uint64
+        assert grads.dtype == np.float32 and grads.size == keys.size * self._width
+        check_call(_LIB.hb_cache_update_with_push_keys(
+            self._h, keys.ctypes.data, KEYS_U64, keys.size, push_keys.ctypes.data, KEYS_U64,
+            push_keys.size, grads.ctypes.data))
+        return self._issue(keys, push_keys, grads)
+
+    # ---- raw-pointer entry points (float32-carried ids; host OR device pointers) ----------
+    def embedding_lookup_raw(self, keys_ptr, dest_ptr, num_keys):
+        check_call(_LIB.hb_cache_lookup(self._h, keys_ptr, KEYS_F32, int(num_keys), dest_ptr))
+        return self._issue()
+
+    def embedding_update_raw(self, keys_ptr, grads_ptr, num_keys):
+        check_call(_LIB.hb_cache_update(self._h, keys_ptr, KEYS_F32, int(num_keys), grads_ptr))
+        return self._issue()
+
+    def embedding_push_pull_raw(self, pullkeys_ptr, dest_ptr, num_pull_keys, pushkeys_ptr,
+                                grads_ptr, num_push_keys):
+        check_call(_LIB.hb_cache_push_pull(self._h, pullkeys_ptr, KEYS_F32, int(num_pull_keys),
+                                           dest_ptr, pushkeys_ptr, KEYS_F32, int(num_push_keys),
+                                           grads_ptr))
+        return self._issue()
+
+    def embedding_update_with_push_keys_np_raw(self, keys_ptr, push_keys, grads_ptr, num_keys):
+        _check_c_contiguous(push_keys, "push_keys")
+        assert push_keys.dtype == np.uint64
+        check_call(_LIB.hb_cache_update_with_push_keys(
+            self._h, keys_ptr, KEYS_F32, int(num_keys), push_keys.ctypes.data, KEYS_U64,
+            push_keys.size, grads_ptr))
+        return self._issue(push_keys)
+
+    def embedding_update_with_push_keys_raw(self, keys_ptr, push_keys_ptr, grads_ptr, num_keys,
+                                            num_push_keys):
+        check_call(_LIB.hb_cache_update_with_push_keys(
+            self._h, keys_ptr, KEYS_F32, int(num_keys), push_keys_ptr, KEYS_F32,
+            int(num_push_keys), grads_ptr))
+        return self._issue()
+
+    # ---- debug surface (python_api.cc:56-60) -----------------------------------------------
+    def size(self):
+        self._drain()
+        n = _sz()
+        check_call(_LIB.hb_cache_size(self._h, ctypes.byref(n)))
+        return n.value
+
+    def count(self, k):
+        self._drain()
+        out = ctypes.c_int()
+        check_call(_LIB.hb_cache_count(self._h, int(k), ctypes.byref(out)))
+        return out.value
+
+    def keys(self):
+        self._drain()
+        cap = self.size()
+        buf = np.empty(max(cap, 1), np.uint64)
+        n = _sz()
+        check_call(_LIB.hb_cache_keys(self._h, buf.ctypes.data, buf.size, ctypes.byref(n)))
+        return buf[:n.value].copy()
+
+    def lookup(self, k):
+        """Policy lookup of one key (touches replacement state, like the reference)."""
+        self._drain()
+        found, ver = ctypes.c_int(), ctypes.c_int64()
+        data = np.zeros(self._width, np.float32)
+        check_call(_LIB.hb_cache_touch(self._h, int(k), ctypes.byref(found), ctypes.byref(ver),
+                                       data.ctypes.data))
+        return Embedding(k, ver.value, data) if found.value else None
+
+    def peek(self, k):
+        """Read one line WITHOUT touching replacement state (not in the reference)."""
+        self._drain()
+        found, ver, upd = ctypes.c_int(), ctypes.c_int64(), ctypes.c_int64()
+        data = np.zeros(self._width, np.float32)
+        grad = np.zeros(self._width, np.float32)
+        check_call(_LIB.hb_cache_peek(self._h, int(k), ctypes.byref(found), ctypes.byref(ver),
+                                      ctypes.byref(upd), data.ctypes.data, grad.ctypes.data))
+        return Embedding(k, ver.value, data, grad, upd.value) if found.value else None
+
+    def insert(self, e):
+        self._drain()
+        assert e.data.size == self._width
+        check_call(_LIB.hb_cache_insert(self._h, e.key, e.version, e.data.ctypes.data))
+
+    def __repr__(self):
+        pull, push = self._bounds()
+        return "<Cache : %d/%d , id:%d , width:%d , bound:%d %d>" % (
+            self.size(), self._limit, self._node_id, self._width, pull, push)
+
+
+class LRUCache(CacheBase):
+    _policy = "lru"
+
+
+class LFUCache(CacheBase):
+    _policy = "lfu"
+
+
+class LFUOptCache(CacheBase):
+    _policy = "lfuopt"
+
+
+def debug():
+    from ._base import version
+    print("herald_b200 hetu_cache: %s" % version())

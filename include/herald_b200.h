@@ -1,0 +1,261 @@
+/*
+ * herald_b200.h — C-ABI of libherald_b200.so, the B200 (sm_100a) implementation of
+ * Herald/Hetu's data-parallel embedding hot path.
+ *
+ * Plain C: pointers and sizes only.  Two groups of entry points:
+ *
+ *  (b1) the symbols Hetu's link layer binds from libc_runtime_api.so through
+ *       ctypes (python/hetu/_base.py:66-77), with the reference's names, argument
+ *       order and DLArray/DLStream structs — a drop-in for those symbols;
+ *  (b2) hb_* functions: the owner-side table shard and the worker-side cache, which
+ *       replace the pybind module `hetu_cache` (src/hetu_cache/src/python_api.cc)
+ *       and the three ps-lite transport calls below it
+ *       (ps-lite/include/ps/worker/hetu_binding.h:14-28).  The Python module
+ *       herald_b200.hetu_cache presents the reference's class surface on top.
+ *
+ * Conventions: every function returns 0 on success and -1 on failure;
+ * HBGetLastError() returns the message of the calling thread's last failure
+ * (the reference returns -1 from API_BEGIN/API_END, src/common/runtime_base.h:13-47).
+ * All device work is asynchronous with respect to the host and ordered on the
+ * stream named in the call (NULL = the legacy default stream for b1, the cache's
+ * own stream for b2).  All citations are relative to the reference root.
+ */
+#ifndef HERALD_B200_H_
+#define HERALD_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------------- */
+/* DLArray ABI — replaces src/common/dlarray.h:22-65                           */
+/* ------------------------------------------------------------------------- */
+typedef enum { kCPU = 1, kGPU = 2 } DLDeviceType;
+typedef struct {
+    int device_id;
+    DLDeviceType device_type;
+} DLContext;
+typedef struct {
+    void *data;
+    DLContext ctx;
+    int ndim;
+    int64_t *shape;
+    int64_t *stride;
+} DLArray;
+typedef struct {
+    int device_id;
+    void *handle; /* points to a cudaStream_t (src/ops/EmbeddingLookup.cu:46) */
+} DLStream;
+typedef struct {
+    int device_id;
+    void *handle; /* points to a cudaEvent_t */
+} DLEvent;
+typedef int64_t index_t;
+typedef DLArray *DLArrayHandle;
+typedef DLStream *DLStreamHandle;
+typedef DLEvent *DLEventHandle;
+
+const char *HBGetLastError(void);
+/* Library/arch identification: "herald_b200 <ver> sm_100a". */
+const char *HBVersion(void);
+/* Number of kernels this library has launched in this process (bench `gpu_launches`). */
+uint64_t HBKernelLaunchCount(void);
+
+/* ---- runtime plumbing: src/common/c_runtime_api.h:28-77 ------------------- */
+int DLStreamCreate(size_t dev_id, DLStreamHandle *handle);
+int DLStreamDestroy(DLStreamHandle handle);
+int DLStreamSync(DLStreamHandle handle);
+int DLEventCreate(size_t dev_id, DLEventHandle *handle);
+int DLEventDestroy(DLEventHandle handle);
+int DLEventRecord(DLStreamHandle stream_handle, DLEventHandle event_handle);
+int DLEventSync(DLEventHandle handle);
+int DLEventElapsedTime(DLEventHandle start, DLEventHandle ending, float *duration);
+/* CPU arrays are allocated in pinned host memory so that H2D/D2H copies are async. */
+int DLArrayAlloc(const index_t *shape, const index_t *stride, index_t ndim, DLContext ctx,
+                 DLArrayHandle *out);
+int DLArrayFree(DLArrayHandle handle);
+int DLArrayCopyFromTo(DLArrayHandle from, DLArrayHandle to, DLStreamHandle stream);
+int DLGpuArraySet(DLArrayHandle arr, float value, DLStreamHandle stream_handle);
+
+/* ---- op-level hot path (table resident in HBM; ids are float32 arrays) ---- */
+/* src/common/c_runtime_api.h:308-310; kernel src/ops/EmbeddingLookup.cu:3-52 */
+int DLGpuEmbeddingLookUp(const DLArrayHandle input, const DLArrayHandle ids,
+                         DLArrayHandle output, DLStreamHandle stream_handle);
+/* c_runtime_api.h:312-314; src/ops/EmbeddingLookup.cu:54-131 (zero + scatter-add) */
+int DLGpuEmbeddingLookUp_Gradient(const DLArrayHandle output_grad, const DLArrayHandle ids,
+                                  DLArrayHandle input_grad, DLStreamHandle stream_handle);
+/* c_runtime_api.h:700-702; src/ops/OptimizersSparse.cu:282-329 */
+int DeduplicateIndexedSlices(const DLArrayHandle origin, const DLArrayHandle inverse,
+                             DLArrayHandle compressed, DLStreamHandle stream_handle);
+/* c_runtime_api.h:704-706; src/ops/OptimizersSparse.cu:233-280 */
+int IndexedSlices2Dense(const DLArrayHandle values, const DLArrayHandle indices,
+                        DLArrayHandle new_values, DLStreamHandle stream_handle);
+/* c_runtime_api.h:569-571; src/ops/IndexedSlices.cu:3-48 */
+int IndexedSlicesOneSideAdd(const DLArrayHandle indices, const DLArrayHandle values,
+                            DLArrayHandle output, DLStreamHandle stream_handle);
+/* c_runtime_api.h:639-642; src/ops/OptimizersSparse.cu:3-51 */
+int AddL2RegularizationSparse(const DLArrayHandle param, const DLArrayHandle grad_indices,
+                              DLArrayHandle grad_values, float l2reg,
+                              DLStreamHandle stream_handle);
+/* c_runtime_api.h:645-648; src/ops/OptimizersSparse.cu:53-99 (duplicate ids allowed) */
+int SGDOptimizerSparseUpdate(DLArrayHandle param, const DLArrayHandle grad_indices,
+                             const DLArrayHandle grad_values, float lr,
+                             DLStreamHandle stream_handle);
+/* c_runtime_api.h:653-656; src/ops/OptimizersSparse.cu:101-229 */
+int MomentumOptimizerSparseUpdate(DLArrayHandle param, const DLArrayHandle grad_indices,
+                                  const DLArrayHandle grad_values, DLArrayHandle velocity,
+                                  float lr, float momentum, bool nesterov,
+                                  DLStreamHandle stream_handle);
+/* c_runtime_api.h:661-664; src/ops/OptimizersSparse.cu:331-389 (ids unique) */
+int AdaGradOptimizerSparseUpdate(DLArrayHandle param, const DLArrayHandle grad_indices,
+                                 const DLArrayHandle grad_values, DLArrayHandle acc, float lr,
+                                 float eps, DLStreamHandle stream_handle);
+/* c_runtime_api.h:670-674; src/ops/OptimizersSparse.cu:391-455 (ids unique) */
+int AdamOptimizerSparseUpdate(DLArrayHandle param, const DLArrayHandle grad_indices,
+                              const DLArrayHandle grad_values, DLArrayHandle expavg,
+                              DLArrayHandle expavgsq, float lr, float beta1, float beta2,
+                              float beta1t, float beta2t, float eps,
+                              DLStreamHandle stream_handle);
+/* c_runtime_api.h:681-686; src/ops/OptimizersSparse.cu:457-522 (ids unique) */
+int AdamWOptimizerSparseUpdate(DLArrayHandle param, const DLArrayHandle grad_indices,
+                               const DLArrayHandle grad_values, DLArrayHandle expavg,
+                               DLArrayHandle expavgsq, float lr, float beta1, float beta2,
+                               float beta1t, float beta2t, float eps, float weight_decay,
+                               DLStreamHandle stream_handle);
+
+/* ---- device-side dedup: replaces the host np.unique round trip of
+ *      IndexedSlices.deduplicate (python/hetu/ndarray.py:532-554) ----------- */
+/* ids: float32[n] on the GPU.  unique_ids: float32[>=n] (ascending), inverse: float32[n]
+ * (rank of ids[i] in unique_ids, carried as float32 like the reference), num_unique: one
+ * int64 in DEVICE memory.  Everything stays on `stream_handle`; no host sync. */
+int HBUniqueIndexedSlices(const DLArrayHandle ids, DLArrayHandle unique_ids,
+                          DLArrayHandle inverse, int64_t *num_unique_dev,
+                          DLStreamHandle stream_handle);
+/* Fused np.unique + DeduplicateIndexedSlices + AdamOptimizerSparseUpdate on ids with
+ * duplicates: one sort, one deterministic segment reduce, one row update. */
+int HBAdamSparseUpdateFused(DLArrayHandle param, const DLArrayHandle grad_indices,
+                            const DLArrayHandle grad_values, DLArrayHandle expavg,
+                            DLArrayHandle expavgsq, float lr, float beta1, float beta2,
+                            float beta1t, float beta2t, float eps,
+                            DLStreamHandle stream_handle);
+
+/* ------------------------------------------------------------------------- */
+/* (b2) owner-side table shard — replaces the PS server's CacheTable           */
+/*      ps-lite/include/ps/server/param.h:119-138 and the handlers              */
+/*      ps-lite/src/PSFhandle_embedding.cc:5-79                                 */
+/* ------------------------------------------------------------------------- */
+typedef struct hb_table hb_table;
+typedef struct hb_cache hb_cache;
+
+/* Register table `node_id` (the server key, as InitTensor: ps-lite/src/python_binding.cc:94)
+ * of `length` x `width` fp32 rows on `device`.  In a multi-GPU group (hb_comm_init called
+ * first) each rank allocates only its AveragePartitioner row range
+ * (ps-lite/include/ps/partitioner.h:46-57).  Rows and versions start at zero. */
+int hb_table_create(int node_id, size_t length, size_t width, int device, hb_table **out);
+int hb_table_get(int node_id, hb_table **out);
+int hb_table_destroy(hb_table *t);
+/* init_type as ps::InitType (ps-lite/include/ps/psf/misc.h:7-12): 0 constant(a),
+ * 1 uniform[a,b), 2 normal(a,b), 3 truncated normal(a,b) within 2 sigma.  Counter-based
+ * generator keyed on (seed, global row, column): independent of the sharding. */
+int hb_table_init(hb_table *t, int init_type, double a, double b, unsigned long long seed);
+/* Copy rows [row_begin, row_begin+nrows) of the GLOBAL table from/to host or device memory;
+ * only the part owned by this rank is touched.  Synchronous. */
+int hb_table_load_rows(hb_table *t, size_t row_begin, size_t nrows, const float *rows);
+int hb_table_read_rows(hb_table *t, size_t row_begin, size_t nrows, float *rows);
+int hb_table_read_versions(hb_table *t, size_t row_begin, size_t nrows, int64_t *versions);
+/* local shard geometry */
+int hb_table_shard(hb_table *t, size_t *row_begin, size_t *nrows, float **dev_rows,
+                   int64_t **dev_versions);
+
+/* ------------------------------------------------------------------------- */
+/* (b2) worker-side cache — replaces hetu_cache LRUCache/LFUCache/LFUOptCache  */
+/*      src/hetu_cache/src/python_api.cc:32-76, src/hetu_cache/src/cache.cc     */
+/* ------------------------------------------------------------------------- */
+enum { HB_POLICY_LRU = 0, HB_POLICY_LFU = 1, HB_POLICY_LFUOPT = 2 };
+/* key encodings accepted by the batch entry points */
+enum {
+    HB_KEYS_U64 = 0, /* uint64 keys: the numpy path (python/hetu/cstable.py:51-55) */
+    HB_KEYS_F32 = 1  /* float32-carried ids, key = (uint64)(float)id: the NDArray "raw"
+                        path (src/hetu_cache/src/cache.cc:49-58) */
+};
+
+/* counters of one call — the hit/miss parity surface (cache.cc:89-106, :179-196) */
+typedef struct {
+    int64_t num_all;        /* keys in the call                                     */
+    int64_t num_unique;     /* distinct keys                                        */
+    int64_t num_miss;       /* unique keys not found by the policy lookup           */
+    int64_t num_evict;      /* dirty victims flushed by this push (Push only)       */
+    int64_t num_transfered; /* Pull: rows the owner returned; Push: lines pushed    */
+    int64_t is_full;        /* size() == limit after the call                       */
+    int64_t size;           /* lines resident after the call                        */
+    int64_t error;          /* non-zero: device-side failure code (see hb_cache.cu) */
+    float time_ms;          /* device time of the call (CUDA events)                */
+    float sort_ms, lookup_ms, transfer_ms, copy_ms, insert_ms; /* phase split      */
+} hb_perf;
+
+/* limit/len/width/node_id as the reference constructors (python_api.cc:54-76).
+ * The table `node_id` must exist.  pull_bound = push_bound = 5 initially (cache.h:26-27). */
+int hb_cache_create(int policy, size_t limit, size_t length, size_t width, int node_id,
+                    hb_cache **out);
+int hb_cache_destroy(hb_cache *c);
+int hb_cache_set_bounds(hb_cache *c, int64_t pull_bound, int64_t push_bound);
+int hb_cache_get_bounds(hb_cache *c, int64_t *pull_bound, int64_t *push_bound);
+int hb_cache_set_bypass(hb_cache *c, int on);                   /* cache.cc:15-35 */
+/* Reserve workspace for calls of up to max_keys keys (grows on demand otherwise). */
+int hb_cache_reserve(hb_cache *c, size_t max_keys);
+/* The CUDA stream (cudaStream_t) all of this cache's work is ordered on. */
+int hb_cache_stream(hb_cache *c, void **stream);
+
+/* embedding_lookup[_raw]: cache.cc:37-107.  keys: n keys (host or device memory, encoding
+ * `key_kind`); dest: n*width floats (host or device).  Asynchronous: returns after
+ * enqueueing; hb_cache_wait() completes it and fills `perf` (may be NULL). Caller keeps
+ * keys/dest alive until then (python/hetu/cstable.py:38-45). */
+int hb_cache_lookup(hb_cache *c, const void *keys, int key_kind, size_t n, float *dest);
+/* embedding_update[_raw]: cache.cc:109-196.  grads: n*width floats, already scaled by -lr
+ * (python/hetu/gpu_ops/ParameterServerCommunicate.py:24,58-59). */
+int hb_cache_update(hb_cache *c, const void *keys, int key_kind, size_t n, const float *grads);
+/* embedding_update_with_push_keys[_np_raw|_raw]: cache.cc:198-334.  push_keys ascending. */
+int hb_cache_update_with_push_keys(hb_cache *c, const void *keys, int key_kind, size_t n,
+                                   const void *push_keys, int push_key_kind, size_t n_push,
+                                   const float *grads);
+/* embedding_push_pull_raw: cache.cc:336-422 */
+int hb_cache_push_pull(hb_cache *c, const void *pull_keys, int pull_kind, size_t n_pull,
+                       float *dest, const void *push_keys, int push_kind, size_t n_push,
+                       const float *grads);
+/* Block until every call enqueued so far has completed; *perf receives the counters of the
+ * most recent call.  Returns -1 if any of them failed on the device. */
+int hb_cache_wait(hb_cache *c, hb_perf *perf);
+/* Counters of the last `max` completed calls, oldest first; returns how many were written. */
+int hb_cache_perf_history(hb_cache *c, hb_perf *out, int *kinds, int max, int *written);
+
+/* debug surface: python_api.cc:56-60 */
+int hb_cache_size(hb_cache *c, size_t *size);
+int hb_cache_count(hb_cache *c, uint64_t key, int *count);
+int hb_cache_keys(hb_cache *c, uint64_t *keys, size_t capacity, size_t *n); /* ascending */
+/* read one line without touching replacement state; *found = 0 if absent */
+int hb_cache_peek(hb_cache *c, uint64_t key, int *found, int64_t *version, int64_t *updates,
+                  float *data, float *grad);
+/* single-key policy lookup (touches replacement state like CacheBase::lookup) */
+int hb_cache_touch(hb_cache *c, uint64_t key, int *found, int64_t *version, float *data);
+/* insert(Embedding): policy insert of one line with given version and data */
+int hb_cache_insert(hb_cache *c, uint64_t key, int64_t version, const float *data);
+
+/* ------------------------------------------------------------------------- */
+/* multi-GPU: one process per GPU; replaces ps-lite's worker<->server transport */
+/* (PSAgent row-range split ps-lite/include/ps/worker/PSAgent.h:537-627) with   */
+/* NCCL grouped send/recv over NVLink.                                          */
+/* ------------------------------------------------------------------------- */
+/* 128-byte ncclUniqueId made on rank 0 and distributed by the launcher. */
+int hb_comm_unique_id(void *id128);
+int hb_comm_init(const void *id128, int rank, int world, int device);
+int hb_comm_rank(int *rank, int *world);
+int hb_comm_barrier(void); /* BarrierWorker (python/hetu/cstable.py:36) */
+int hb_comm_finalize(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HERALD_B200_H_ */
