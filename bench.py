@@ -1,0 +1,438 @@
+#!/usr/bin/env python
+"""bench.py — WDL-Criteo embedding step (BASELINE.json metric) on N B200s of one node.
+
+One step = the hot path over one batch, in the order Hetu's BSP-prefetch loop issues it
+(python/hetu/gpu_ops/ParameterServerCommunicate.py:48-52):
+    embedding_update(batch t: ids [B,26], grads [B,26,D])      coalesce + SGD-folded push
+    embedding_lookup(batch t+1: ids [B,26]) -> [B,26,D]         dedup, cache resolve, gather
+through the reference-facing cache API (herald_b200.cstable.CacheSparseTable).
+
+  value   samples/s with ids / grads / dest resident in HBM (device pointers), calls enqueued
+          back to back, timed with CUDA events on the cache's stream, max over ranks
+  e2e     the same step with HOST (pinned) buffers: ids + grads H2D and gathered rows D2H inside
+          the timed region, `.wait()` after every call as the reference's loop does
+  roofline   dominant kernel's algorithmic bytes / its CUDA-event time, vs MEASURED_PEAKS.json
+  cpu_baseline / --impl reference   the reference's own CPU cache + PS handler (oracle/_ref, the
+          reference sources compiled unmodified; falls back to the C++ port) on this box's host
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+For N > 1 launch with torchrun (one rank per GPU); rank 0 prints ONE JSON line.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FIELDS = 26
+VOCAB = 33762577          # examples/ctr/models/wdl_criteo.py:9
+ZIPF_A = 1.05
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="herald_b200", choices=["herald_b200", "reference"])
+    ap.add_argument("--batch", type=int, default=8192)
+    ap.add_argument("--dim", type=int, default=128)
+    ap.add_argument("--vocab", type=int, default=VOCAB)
+    ap.add_argument("--policy", default="lru")
+    ap.add_argument("--bound", type=int, default=0)
+    ap.add_argument("--ratio", type=float, default=0.1)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cpu-steps", type=int, default=8)
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------------------------
+# synthetic Criteo-shaped ids: unified Zipf(1.05) over the single [V, D] table, carried as float32
+# exactly like Hetu's dataloader (python/hetu/dataloader.py:14) — ids above 2^24 round.
+# ----------------------------------------------------------------------------------------------
+def make_ids(step, batch, vocab, rank=0):
+    rng = np.random.default_rng(1234 + step + 100003 * rank)
+    z = rng.zipf(ZIPF_A, (batch, FIELDS))
+    return ((z - 1) % vocab).astype(np.float32)
+
+
+def cache_limit(vocab, ratio):
+    return int(ratio * (vocab - 1)) + 1          # examples/ctr/run_hetu.py:256
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        super().__init__(daemon=True)
+        self.gpu_index = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + self.Q,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([x.strip() for x in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+        self.join(timeout=2)
+        sm, smax, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                smax.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6),
+                              ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
+                if len(r) > col and r[col].lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(smax)),
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak_hbm():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
+
+
+def ncu_traffic(kernel_key):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        with open(path) as f:
+            return json.load(f).get(kernel_key)
+    except Exception:
+        return None
+
+
+# ----------------------------------------------------------------------------------------------
+# reference arm: the reference's CPU cache + in-process PS handler, driven synchronously
+# ----------------------------------------------------------------------------------------------
+def host_mem_available_gb():
+    try:
+        with open("/proc/meminfo") as f:
+            for line in f:
+                if line.startswith("MemAvailable"):
+                    return int(line.split()[1]) / 1e6
+    except Exception:
+        pass
+    return 0.0
+
+
+def run_cpu_reference(args, steps, warmup):
+    """-> dict(value, ms_per_step, kind, cores, sample, vocab).  One pool thread does each call
+    (ps-lite/src/thread_pool.cc:4 has 5 threads but a call runs on one; the cache PSFs are serial
+    on the server: ps-lite/src/PSFhandle_embedding.cc:23-27)."""
+    from oracle import port, ref
+    kind = "reference" if ref.available() else "port"
+    impl = ref if kind == "reference" else port
+    vocab, D, B = args.vocab, args.dim, args.batch
+    need_gb = vocab * D * 4 / 1e9 * 1.3 + 8
+    folded = False
+    if host_mem_available_gb() < need_gb:
+        vocab, folded = 4_000_000, True
+    limit = cache_limit(vocab, args.ratio)
+    if kind == "reference":
+        srv = impl.Server(vocab, D, init=(2, 0.0, 0.01, 123))   # Normal(0, 0.01): wdl_criteo.py:13-14
+    else:
+        srv = impl.Server(vocab, D)
+    cache = impl.Cache(srv, args.policy, limit, args.bound)
+    # fill the cache with the hottest ids (under (zipf-1) % V the small ids are the hot ones)
+    t0 = time.perf_counter()
+    chunk = 1 << 20
+    for lo in range(0, limit, chunk):
+        cache.embedding_lookup(np.arange(lo, min(lo + chunk, limit), dtype=np.uint64))
+    fill_s = time.perf_counter() - t0
+    N = B * FIELDS
+    grads = (np.random.default_rng(7).normal(0, 1e-3, (N, D)) * 1e-2).astype(np.float32)
+    dest = np.empty((N, D), np.float32)
+    ids = [make_ids(s, B, vocab).reshape(-1).astype(np.uint64) for s in range(steps + warmup + 1)]
+    cache.embedding_lookup(ids[0], dest)
+    times = []
+    for s in range(steps + warmup):
+        t0 = time.perf_counter()
+        cache.embedding_update(ids[s], grads)
+        cache.embedding_lookup(ids[s + 1], dest)
+        dt = time.perf_counter() - t0
+        if s >= warmup:
+            times.append(dt)
+    total = float(np.sum(times))
+    sample = ("%d timed + %d warm-up steps of the same workload (B=%d, 26 fields, D=%d, V=%d%s, "
+              "%s limit %d, bound %d) after filling the cache with the %d hottest ids (%.1f s); "
+              "synchronous calls, in-process PS (no ZMQ/RDMA), median step %.1f ms" %
+              (steps, warmup, B, D, vocab, " folded: host RAM" if folded else "", args.policy,
+               limit, args.bound, limit, fill_s, 1e3 * float(np.median(times))))
+    return dict(value=B * steps / total, ms_per_step=1e3 * total / steps, kind=kind, cores=1,
+                sample=sample, vocab=vocab)
+
+
+def reference_main(args, rank, world):
+    if rank != 0:
+        return
+    res = run_cpu_reference(args, args.steps, args.warmup)
+    line = {
+        "impl": "reference", "metric": "wdl_criteo_embedding_step_samples_per_sec",
+        "value": res["value"], "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, res["vocab"]),
+        "cpu_baseline": {"value": res["value"], "unit": "samples/s", "cores": res["cores"],
+                         "kind": res["kind"], "sample": res["sample"]},
+        "e2e": {"value": res["value"], "unit": "samples/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, vocab=None):
+    return {"workload": "wdl_criteo embedding step: update(batch t) + lookup(batch t+1), "
+                        "%s cache ratio %.2f, bound %d" % (args.policy.upper(), args.ratio, args.bound),
+            "batch_per_gpu": args.batch, "fields": FIELDS, "emb_dim": args.dim,
+            "table_rows": vocab or args.vocab, "cache_limit": cache_limit(vocab or args.vocab, args.ratio),
+            "ids": "Zipf(%.2f) unified, float32-carried" % ZIPF_A,
+            "l2": "inputs larger than L2: 3 rotating grads/dest buffer pairs of 2x%.0f MB, "
+                  "17 GB table" % (args.batch * FIELDS * args.dim * 4 / 1e6),
+            "parallelism": "dp%d row-sharded" % args.gpus}
+
+
+# ----------------------------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------------------------
+def dl_stream_of(cuda_stream_value):
+    from herald_b200.stream import DLStream
+    holder = ctypes.c_void_p(cuda_stream_value)
+    st = DLStream()
+    st.device_id = 0
+    st.handle = ctypes.cast(ctypes.pointer(holder), ctypes.c_void_p)
+
+    class _S(object):
+        pass
+
+    s = _S()
+    s.handle = ctypes.pointer(st)
+    s._keep = (holder, st)
+    return s
+
+
+def herald_main(args, rank, world, local_rank):
+    import herald_b200 as hb
+    from herald_b200 import ps, stream as hstream
+    from herald_b200._base import _LIB, check_call, kernel_launch_count
+    from herald_b200.cstable import CacheSparseTable
+
+    dist = None
+    if world > 1:
+        import torch.distributed as dist                       # rendezvous + barrier only (gloo)
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        idbuf = (ctypes.c_char * 128)()
+        if rank == 0:
+            check_call(_LIB.hb_comm_unique_id(idbuf))
+        obj = [bytes(idbuf.raw)]
+        dist.broadcast_object_list(obj, src=0)
+        check_call(_LIB.hb_comm_init(obj[0], rank, world, local_rank))
+
+    dev = hb.gpu(local_rank)
+    B, D, V = args.batch, args.dim, args.vocab
+    N = B * FIELDS
+    limit = cache_limit(V, args.ratio)
+    comm = hb.worker_init(local_rank)
+    table = comm.InitTensor(0, ps.kCacheTable, V, D, ps.Normal, 0.0, 0.01, 123)
+    cst = CacheSparseTable(limit, V, D, 0, args.policy, args.bound)
+    cst.cache.reserve(max(N, 1 << 20))
+    stream = dl_stream_of(cst.cache.stream)
+    ev = [hstream.create_event_handle(dev) for _ in range(4)]
+
+    # ---- inputs ----
+    K, W = args.steps, args.warmup
+    total = K + W + 1
+    ids_np = [make_ids(s, B, V, rank) for s in range(total)]
+    ids_dev = [hb.array(a, dev) for a in ids_np]
+    rng = np.random.default_rng(7 + rank)
+    R = 3
+    grads_np = (rng.normal(0, 1e-3, (B, FIELDS, D)) * 1e-2).astype(np.float32)   # already x(-lr)
+    grads_dev = [hb.array(grads_np, dev) for _ in range(R)]
+    dest_dev = [hb.empty((B, FIELDS, D), dev) for _ in range(R)]
+
+    # ---- fill the cache with the hottest ids (setup, untimed) ----
+    chunk = 1 << 20
+    for lo in range(0, limit, chunk):
+        n = min(chunk, limit - lo)
+        k = hb.array(np.arange(lo, lo + n, dtype=np.float32), dev)
+        d = hb.empty((n, D), dev)
+        cst.embedding_lookup(k, d, sync=True)
+        del k, d
+    cst.embedding_lookup(ids_dev[0], dest_dev[0], sync=True)
+
+    def step(s, keys, grads, dests, sync):
+        w1 = cst.embedding_update(keys[s], grads[s % len(grads)], sync=sync)
+        w2 = cst.embedding_lookup(keys[s + 1], dests[s % len(dests)], sync=sync)
+        return w1, w2
+
+    def barrier():
+        check_call(_LIB.DLStreamSync(stream.handle))
+        if dist is not None:
+            dist.barrier()
+
+    # ---- warm-up (untimed) ----
+    for s in range(W):
+        step(s, ids_dev, grads_dev, dest_dev, False)
+    cst.perf_enabled(True)
+    barrier()
+
+    # ---- timed region: K steps, device-resident inputs ----
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    launches0 = kernel_launch_count()
+    barrier()
+    ev[0].record(stream)
+    last = None
+    for s in range(W, W + K):
+        last = step(s, ids_dev, grads_dev, dest_dev, False)
+    ev[1].record(stream)
+    last[1].wait()
+    barrier()
+    launches = kernel_launch_count() - launches0
+    ms = ev[1].time_since(ev[0])
+    perf = list(cst.perf)[-2 * K:]
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- end to end with host buffers (pinned NDArrays: the reference's calling convention) ----
+    e2e = None
+    if not args.no_e2e:
+        cst.perf_enabled(False)
+        Ke = min(K, 20)
+        host = hb.cpu(0)
+        ids_host = [hb.array(ids_np[W + s], host) for s in range(Ke + 1)]
+        grads_host = [hb.array(grads_np, host) for _ in range(2)]
+        dest_host = [hb.empty((B, FIELDS, D), host) for _ in range(2)]
+        cst.embedding_lookup(ids_host[0], dest_host[0], sync=True)
+        step(0, ids_host, grads_host, dest_host, True)          # warm the staging buffers
+        barrier()
+        ev[2].record(stream)
+        for s in range(1, Ke):
+            step(s, ids_host, grads_host, dest_host, True)
+        ev[3].record(stream)
+        barrier()
+        e2e_ms = ev[3].time_since(ev[2])
+        checksum = float(dest_host[0].asnumpy()[0, 0, 0])       # the result is read on the host
+        e2e = {"ms": e2e_ms, "steps": Ke - 1, "checksum": checksum}
+
+    # ---- max over ranks ----
+    if dist is not None:
+        import torch
+        t = torch.tensor([ms, e2e["ms"] / e2e["steps"] if e2e else 0.0], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t[0])
+        if e2e:
+            e2e["ms"] = float(t[1]) * e2e["steps"]
+
+    if rank == 0:
+        peak, peak_src = measured_peak_hbm()
+        pulls = [p for p in perf if p["type"] == "Pull"]
+        pushes = [p for p in perf if p["type"] == "Push"]
+        U_pull = float(np.mean([p["num_unique"] for p in pulls]))
+        U_push = float(np.mean([p["num_unique"] for p in pushes]))
+        t_gather = float(np.mean([p["copy_time"] for p in pulls]))        # ms, gather kernel
+        t_accum = float(np.mean([p["copy_time"] for p in pushes]))        # ms, accumulate+push kernel
+        row = D * 4
+        gather_bytes = (U_pull + N) * row
+        accum_bytes = (N + 2 * U_push) * row                              # SURVEY §8(d), bound 0
+        pushed = float(np.mean([p["num_transfered"] - p["num_evict"] for p in pushes]))
+        accum_bytes_owner = accum_bytes + 2 * pushed * row                # + owner row RMW (a9)
+        kernels = {
+            "gather_rows_kernel": {"ms": t_gather, "algorithmic_bytes": gather_bytes,
+                                   "gbs": gather_bytes / t_gather / 1e6 if t_gather else None},
+            "segment_rows_kernel<AccumulatePush>": {
+                "ms": t_accum, "algorithmic_bytes": accum_bytes,
+                "gbs": accum_bytes / t_accum / 1e6 if t_accum else None,
+                "algorithmic_bytes_with_owner_row_rmw": accum_bytes_owner,
+                "gbs_with_owner_row_rmw": accum_bytes_owner / t_accum / 1e6 if t_accum else None},
+        }
+        dom = max(kernels, key=lambda k: kernels[k]["ms"] or 0.0)
+        achieved = kernels[dom]["gbs"] or 0.0
+        phase = {
+            "pull_ms": {k: float(np.mean([p[k] for p in pulls])) for k in
+                        ("time", "sort_time", "lookup_time", "transfer_time", "copy_time", "insert_time")},
+            "push_ms": {k: float(np.mean([p[k] for p in pushes])) for k in
+                        ("time", "sort_time", "lookup_time", "copy_time", "transfer_time")},
+            "unique_per_lookup": U_pull, "miss_per_lookup": float(np.mean([p["num_miss"] for p in pulls])),
+            "rows_pulled_per_lookup": float(np.mean([p["num_transfered"] for p in pulls])),
+            "lines_pushed_per_update": float(np.mean([p["num_transfered"] for p in pushes])),
+        }
+        line = {
+            "metric": "wdl_criteo_embedding_step_samples_per_sec",
+            "value": world * B * K / (ms / 1e3), "unit": "samples/s", "n_gpus": world, "steps": K,
+            "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args), "clocks": clocks, "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(dom),
+                         "peak_source": peak_src, "kernels": kernels},
+            "phases": phase,
+        }
+        if e2e:
+            line["e2e"] = {"value": world * B * e2e["steps"] / (e2e["ms"] / 1e3), "unit": "samples/s",
+                           "h2d_bytes_per_step": 2 * N * 4 + N * D * 4, "d2h_bytes_per_step": N * D * 4,
+                           "ms_per_step": e2e["ms"] / e2e["steps"]}
+        if world == 1 and not args.no_cpu_baseline:
+            cpu = run_cpu_reference(args, args.cpu_steps, 2)
+            line["cpu_baseline"] = {"value": cpu["value"], "unit": "samples/s", "cores": cpu["cores"],
+                                    "kind": cpu["kind"], "sample": cpu["sample"]}
+        print(json.dumps(line), flush=True)
+
+    del cst
+    comm.ClearTensor(0)
+    if dist is not None:
+        check_call(_LIB.hb_comm_finalize())
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world == 1 and args.gpus > 1:
+        # launched without torchrun: re-launch one rank per GPU
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
+               "--nproc-per-node", str(args.gpus), "--master-addr", "127.0.0.1",
+               "--master-port", str(29500 + os.getpid() % 1000), os.path.abspath(__file__)] + sys.argv[1:]
+        sys.exit(subprocess.call(cmd))
+    if args.impl == "reference":
+        reference_main(args, rank, world)
+    else:
+        herald_main(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

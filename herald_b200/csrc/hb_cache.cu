@@ -712,6 +712,11 @@ struct AccumulatePush {
     i64 push_bound;
     const u64 *push_keys; // non-null: Laia/Herald plan (cache.cc:286-301)
     u32 n_push;
+    // push_pull (cache.cc:356-422) syncs and inserts BEFORE the post-push cleanup: a pushed line
+    // keeps its update count and gradient until cleanup_pushed_kernel, so the sync sees it stale
+    // and adds the gradient again, and an eviction in between counts it as dirty — as the
+    // reference does.
+    bool defer_cleanup;
 
     __device__ void kernel_begin() const {
         u32 *cnt = block_counter();
@@ -772,9 +777,9 @@ struct AccumulatePush {
         if (x.pushed && x.local) { // PSFhandle_embedding.cc:25-26: row += pushed grad
             float *t = c.trows + x.trow * c.width + k * VEC;
             V::st(t, V::add(V::ld(t), a.g));
-        } else {
-            V::st(c.grad + o, a.g);
         }
+        if (!x.pushed || (defer_cleanup && !x.dataless))
+            V::st(c.grad + o, a.g);
     }
     __device__ void end(const Ctx &x) const {
         if (lane_id() != 0)
@@ -784,6 +789,10 @@ struct AccumulatePush {
             if (x.local)
                 c.tver[x.trow] += x.upd; // PSFhandle_embedding.cc:24
             atomicAdd(block_counter(), 1u);
+        }
+        if (defer_cleanup) {
+            c.slot_updates[x.s] = x.upd;
+            return;
         }
         if (push_keys) { // cache.cc:308-314: every touched line, every call
             c.slot_version[x.s] += x.upd;
@@ -810,7 +819,9 @@ struct FlushPending {
     __device__ void apply(size_t e, size_t k) const {
         const u32 s = c.pending_list[e];
         const u64 trow = c.slot_key[s] - c.row_begin;
-        if (trow >= c.nrows_local)
+        // updates == 0: a line that push_pull evicted right after pushing it; the reference
+        // re-pushes its zeroed gradient, which changes nothing
+        if (trow >= c.nrows_local || c.slot_updates[s] == 0)
             return;
         float *t = c.trows + trow * c.width + k * VEC;
         V::st(t, V::add(V::ld(t), V::ld(c.grad + (size_t)s * c.width + k * VEC)));
@@ -845,6 +856,22 @@ __global__ void free_transient_kernel(CacheView c, const i32 *uslot, const u32 *
         c.slot_updates[s] = 0;
         c.slot_flags[s] = 0;
         c.free_stack[atomicAdd(&r->free_top, 1u)] = s;
+    }
+}
+
+// Deferred cleanup of push_pull (cache.cc:413-421): version += updates; zeroGrad — on every line
+// of the push batch that was pushed and holds data, wherever it is now (resident or evicted).
+__global__ void cleanup_pushed_kernel(CacheView c, const i32 *uslot, i64 push_bound) {
+    const u32 U = c.regs->U2;
+    for (u32 u = blockIdx.x * blockDim.x + threadIdx.x; u < U; u += gridDim.x * blockDim.x) {
+        const i32 s = uslot[u];
+        if (s < 0 || c.slot_state[s] == S_FREE) // dataless lines were dropped after the push
+            continue;
+        const i32 upd = c.slot_updates[s];
+        if ((i64)upd > push_bound) {
+            c.slot_version[s] += upd;
+            c.slot_updates[s] = 0;
+        }
     }
 }
 
@@ -1052,20 +1079,28 @@ void ensure_batch(hb_cache *c, size_t n) {
     c->batch_cap = c->ws[0].cap;
 }
 
+// Both key staging buffers hold at least n keys (called once per call, before any staging, so a
+// later batch of the same call never reallocates under an earlier one).
+void ensure_keys_stage(hb_cache *c, size_t n) {
+    if (n * 8 <= c->keys_stage_cap)
+        return;
+    HB_CUDA(cudaStreamSynchronize(c->stream));
+    size_t cap = std::max<size_t>(n, 4096) * 8;
+    for (int b = 0; b < 2; b++) {
+        if (c->keys_stage[b])
+            cudaFree(c->keys_stage[b]);
+        c->keys_stage[b] = nullptr;
+        HB_CUDA(cudaMalloc(&c->keys_stage[b], cap));
+    }
+    c->keys_stage_cap = cap;
+}
+
 // keys as given by the caller -> device pointer (staged when they live in host memory)
 const void *stage_keys(hb_cache *c, const void *keys, int kind, size_t n, int which) {
     if (n == 0 || is_device_ptr(keys))
         return keys;
     size_t bytes = n * (kind == HB_KEYS_F32 ? 4 : 8);
-    if (bytes > c->keys_stage_cap) {
-        HB_CUDA(cudaStreamSynchronize(c->stream));
-        for (int b = 0; b < 2; b++) {
-            if (c->keys_stage[b])
-                cudaFree(c->keys_stage[b]);
-            HB_CUDA(cudaMalloc(&c->keys_stage[b], n * 8));
-        }
-        c->keys_stage_cap = n * 8;
-    }
+    HB_CHECK(bytes <= c->keys_stage_cap, "key staging buffer not reserved");
     HB_CUDA(cudaMemcpyAsync(c->keys_stage[which], keys, bytes, cudaMemcpyHostToDevice, c->stream));
     return c->keys_stage[which];
 }
@@ -1100,8 +1135,18 @@ void maybe_rebuild_index(hb_cache *c, size_t incoming) {
     }
 }
 
+// phase boundary k of the running call (only when perf is enabled: cache.cc:89-106 timings)
+void mark(hb_cache *c, int k) {
+    if (!c->perf_phases)
+        return;
+    int idx = (int)(c->calls % hb_cache::kRing);
+    HB_CUDA(cudaEventRecord(c->ev_phase[idx * hb_cache::kPhases + k], c->stream));
+    c->phase_mask[idx] |= 1u << k;
+}
+
 void begin_call(hb_cache *c) {
     int idx = (int)(c->calls % hb_cache::kRing);
+    c->phase_mask[idx] = 0;
     HB_CUDA(cudaEventRecord(c->ev_begin[idx], c->stream));
     op_begin_kernel<<<1, 1, 0, c->stream>>>(c->view.regs, clk_of(c));
     HB_LAUNCHED();
@@ -1120,7 +1165,7 @@ void end_call(hb_cache *c, int last_stage, u32 kind, size_t n, bool inserted) {
 
 // sort + unique + resolve (+ alloc) of one key batch
 void resolve_batch(hb_cache *c, const void *dev_keys, int kind, size_t n, int batch, bool dataless,
-                   int clk_stage) {
+                   int clk_stage, bool marks = true) {
     KeyWorkspace &ws = c->ws[batch];
     cudaStream_t st = c->stream;
     ws.reset_scans(st);
@@ -1129,6 +1174,8 @@ void resolve_batch(hb_cache *c, const void *dev_keys, int kind, size_t n, int ba
         sk = radix_sort_keys(ws, dev_keys, kind, n, c->key_bits, st);
     c->sorted[batch] = sk;
     unique_from_sorted(ws, sk, n, st);
+    if (marks)
+        mark(c, 0);
     u32 ntiles = (u32)std::max(1, ceil_div(n, kScanBlock));
     u64 *clk = clk_of(c);
     resolve_kernel<<<ntiles, kScanBlock, 0, st>>>(c->view, ws.uniq, ws.num_unique, c->uslot[batch],
@@ -1141,6 +1188,8 @@ void resolve_batch(hb_cache *c, const void *dev_keys, int kind, size_t n, int ba
                                                   c->miss_list[batch], batch, dataless ? 1 : 0);
         HB_LAUNCHED();
     }
+    if (marks)
+        mark(c, 1);
 }
 
 bool vec4(const hb_cache *c, const void *user_rows) {
@@ -1205,7 +1254,7 @@ void run_insert(hb_cache *c, size_t n, int clk_stage) {
 
 // accumulate + push of batch `batch`, then flush of pending victims, then drop dataless lines
 void run_accumulate(hb_cache *c, size_t n, int batch, const float *dev_grads, const u64 *dev_push_keys,
-                    size_t n_push, bool use_plan) {
+                    size_t n_push, bool use_plan, bool defer_cleanup = false) {
     cudaStream_t st = c->stream;
     KeyWorkspace &ws = c->ws[batch];
     flush_begin_kernel<<<1, 1, 0, st>>>(c->view.regs);
@@ -1215,14 +1264,14 @@ void run_accumulate(hb_cache *c, size_t n, int batch, const float *dev_grads, co
         const u32 *p = c->sorted[batch].perm;
         if (vec4(c, dev_grads)) {
             AccumulatePush<4> f{c->view, ws.uniq, c->uslot[batch], c->push_bound,
-                                use_plan ? dev_push_keys : nullptr, (u32)n_push};
+                                use_plan ? dev_push_keys : nullptr, (u32)n_push, defer_cleanup};
             if (use_plan && !dev_push_keys) // empty plan: nothing is pushed
                 f.push_keys = reinterpret_cast<const u64 *>(ws.uniq), f.n_push = 0;
             segment_rows_kernel<4, AccumulatePush<4>>
                 <<<grid, kRowBlock, 0, st>>>(ws.seg_start, p, ws.num_unique, dev_grads, c->width, f);
         } else {
             AccumulatePush<1> f{c->view, ws.uniq, c->uslot[batch], c->push_bound,
-                                use_plan ? dev_push_keys : nullptr, (u32)n_push};
+                                use_plan ? dev_push_keys : nullptr, (u32)n_push, defer_cleanup};
             if (use_plan && !dev_push_keys)
                 f.push_keys = reinterpret_cast<const u64 *>(ws.uniq), f.n_push = 0;
             segment_rows_kernel<1, AccumulatePush<1>>
@@ -1230,6 +1279,8 @@ void run_accumulate(hb_cache *c, size_t n, int batch, const float *dev_grads, co
         }
         HB_LAUNCHED();
     }
+    if (batch == 0)
+        mark(c, 2);
     // pending victims (count is device-side; bound the grid with the host's upper bound)
     size_t pend = std::min<size_t>(c->pending_upper, c->view.capacity);
     if (pend) {
@@ -1287,6 +1338,7 @@ void do_update(hb_cache *c, const void *keys, int kind, size_t n, const float *g
                const void *push_keys, int push_kind, size_t n_push, bool use_plan) {
     Guard g(c->device);
     ensure_batch(c, n);
+    ensure_keys_stage(c, n);
     cudaStream_t st = c->stream;
     const void *dkeys = stage_keys(c, keys, kind, n, 0);
     const float *dgrads = grads;
@@ -1508,6 +1560,10 @@ int hb_cache_create(int policy, size_t limit, size_t length, size_t width, int n
         HB_CUDA(cudaEventCreate(&c->ev_begin[i]));
         HB_CUDA(cudaEventCreate(&c->ev_end[i]));
     }
+    c->ev_phase.resize((size_t)hb_cache::kRing * hb_cache::kPhases);
+    for (auto &e : c->ev_phase)
+        HB_CUDA(cudaEventCreate(&e));
+    c->phase_mask.assign(hb_cache::kRing, 0);
     HB_CUDA(cudaDeviceSynchronize());
     *out = c;
     HB_API_END();
@@ -1552,6 +1608,8 @@ int hb_cache_destroy(hb_cache *c) {
             cudaEventDestroy(e);
         for (auto &e : c->ev_end)
             cudaEventDestroy(e);
+        for (auto &e : c->ev_phase)
+            cudaEventDestroy(e);
         cudaStreamDestroy(c->stream);
         delete c;
     }
@@ -1578,6 +1636,12 @@ int hb_cache_set_bypass(hb_cache *c, int on) {
     HB_API_END();
 }
 
+int hb_cache_set_perf(hb_cache *c, int on) {
+    HB_API_BEGIN();
+    c->perf_phases = on != 0;
+    HB_API_END();
+}
+
 int hb_cache_reserve(hb_cache *c, size_t max_keys) {
     HB_API_BEGIN();
     Guard g(c->device);
@@ -1596,6 +1660,7 @@ int hb_cache_lookup(hb_cache *c, const void *keys, int key_kind, size_t n, float
     Guard g(c->device);
     HB_CHECK(n < (1ull << 31), "too many keys in one call");
     ensure_batch(c, n);
+    ensure_keys_stage(c, n);
     maybe_rebuild_index(c, n);
     const void *dkeys = stage_keys(c, keys, key_kind, n, 0);
     bool host_dest = n && !is_device_ptr(dest);
@@ -1603,7 +1668,9 @@ int hb_cache_lookup(hb_cache *c, const void *keys, int key_kind, size_t n, float
     begin_call(c);
     resolve_batch(c, dkeys, key_kind, n, 0, /*dataless=*/false, 0);
     run_sync(c, n);
+    mark(c, 2);
     run_gather(c, n, ddest);
+    mark(c, 3);
     run_insert(c, n, 1);
     c->pending_upper += n;
     end_call(c, 2, 0, n, true);
@@ -1635,6 +1702,7 @@ int hb_cache_push_pull(hb_cache *c, const void *pull_keys, int pull_kind, size_t
     Guard g(c->device);
     HB_CHECK(n_pull < (1ull << 31) && n_push < (1ull << 31), "too many keys in one call");
     ensure_batch(c, std::max(n_pull, n_push));
+    ensure_keys_stage(c, std::max(n_pull, n_push));
     maybe_rebuild_index(c, n_pull);
     cudaStream_t st = c->stream;
     const void *dpull = stage_keys(c, pull_keys, pull_kind, n_pull, 0);
@@ -1650,13 +1718,17 @@ int hb_cache_push_pull(hb_cache *c, const void *pull_keys, int pull_kind, size_t
     }
     begin_call(c);
     // cache.cc:360-391: pull-side lookup, then push-side lookup + accumulate
-    resolve_batch(c, dpull, pull_kind, n_pull, 0, /*dataless=*/false, 0);
-    resolve_batch(c, dpush, push_kind, n_push, 1, /*dataless=*/true, 1);
+    resolve_batch(c, dpull, pull_kind, n_pull, 0, /*dataless=*/false, 0, false);
+    resolve_batch(c, dpush, push_kind, n_push, 1, /*dataless=*/true, 1, false);
     // server order (PSFhandle_embedding.cc:66-79): push first, then sync
-    run_accumulate(c, n_push, 1, dgrads, nullptr, 0, false);
+    run_accumulate(c, n_push, 1, dgrads, nullptr, 0, false, /*defer_cleanup=*/true);
     run_sync(c, n_pull);
     run_gather(c, n_pull, ddest);
     run_insert(c, n_pull, 2);
+    if (n_push) {
+        cleanup_pushed_kernel<<<lin_grid(n_push), 256, 0, st>>>(c->view, c->uslot[1], c->push_bound);
+        HB_LAUNCHED();
+    }
     c->pending_upper += n_pull;
     end_call(c, 3, 2, n_pull, true);
     if (host_dest)
@@ -1682,6 +1754,29 @@ static void fill_perf(hb_cache *c, uint64_t call, hb_perf *perf) {
         perf->time_ms = ms;
     else
         cudaGetLastError();
+    // phase split (reference perf dict: sort/lookup/transfer/copy/insert, cache.cc:99-104, :189-193)
+    const uint32_t mask = c->phase_mask[idx];
+    auto span = [&](cudaEvent_t a, cudaEvent_t b) {
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, a, b) != cudaSuccess) {
+            cudaGetLastError();
+            t = 0.f;
+        }
+        return t;
+    };
+    cudaEvent_t *ph = &c->ev_phase[idx * hb_cache::kPhases];
+    if ((mask & 3u) == 3u) {
+        perf->sort_ms = span(c->ev_begin[idx], ph[0]);
+        perf->lookup_ms = span(ph[0], ph[1]);
+        if (r.kind == 0 && (mask & 12u) == 12u) {
+            perf->transfer_ms = span(ph[1], ph[2]); // sync with the owner
+            perf->copy_ms = span(ph[2], ph[3]);     // gather into dest
+            perf->insert_ms = span(ph[3], c->ev_end[idx]);
+        } else if (r.kind == 1 && (mask & 4u)) {
+            perf->copy_ms = span(ph[1], ph[2]);     // accumulate (+ fused push)
+            perf->transfer_ms = span(ph[2], c->ev_end[idx]); // flush of evicted lines + cleanup
+        }
+    }
 }
 
 int hb_cache_wait(hb_cache *c, hb_perf *perf) {

@@ -172,6 +172,10 @@ struct hb_cache {
     static constexpr int kRing = 1024;
     uint64_t calls = 0;
     std::vector<cudaEvent_t> ev_begin, ev_end;
+    static constexpr int kPhases = 4;
+    std::vector<cudaEvent_t> ev_phase; // [kRing][kPhases] phase boundaries (perf enabled only)
+    std::vector<uint32_t> phase_mask;
+    bool perf_phases = false;
     // host-side upper bound of index occupancy (refreshed at wait)
     size_t occ_upper = 0;
     size_t pending_upper = 0;

@@ -38,6 +38,7 @@ def _proto():
     L.hb_cache_get_bounds.argtypes = [_vp, ctypes.POINTER(ctypes.c_int64),
                                       ctypes.POINTER(ctypes.c_int64)]
     L.hb_cache_set_bypass.argtypes = [_vp, ctypes.c_int]
+    L.hb_cache_set_perf.argtypes = [_vp, ctypes.c_int]
     L.hb_cache_reserve.argtypes = [_vp, _sz]
     L.hb_cache_stream.argtypes = [_vp, ctypes.POINTER(_vp)]
     L.hb_cache_lookup.argtypes = [_vp, _vp, ctypes.c_int, _sz, _vp]
@@ -148,6 +149,7 @@ class CacheBase(object):
     def perf_enabled(self, value):
         self._drain()
         self._perf_enabled = bool(value)
+        check_call(_LIB.hb_cache_set_perf(self._h, int(self._perf_enabled)))
 
     def _bounds(self):
         a, b = ctypes.c_int64(), ctypes.c_int64()

@@ -204,6 +204,9 @@ int hb_cache_destroy(hb_cache *c);
 int hb_cache_set_bounds(hb_cache *c, int64_t pull_bound, int64_t push_bound);
 int hb_cache_get_bounds(hb_cache *c, int64_t *pull_bound, int64_t *push_bound);
 int hb_cache_set_bypass(hb_cache *c, int on);                   /* cache.cc:15-35 */
+/* perf_enabled (python_api.cc:40-41): also records the per-phase CUDA events behind
+ * hb_perf.sort_ms / lookup_ms / transfer_ms / copy_ms / insert_ms. */
+int hb_cache_set_perf(hb_cache *c, int on);
 /* Reserve workspace for calls of up to max_keys keys (grows on demand otherwise). */
 int hb_cache_reserve(hb_cache *c, size_t max_keys);
 /* The CUDA stream (cudaStream_t) all of this cache's work is ordered on. */

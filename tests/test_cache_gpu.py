@@ -118,7 +118,7 @@ def test_semantics_s3_dirty_eviction_flushed_by_next_update(oracle_impl):
 
 def test_semantics_s4_limit_smaller_than_batch(oracle_impl):
     rng = np.random.default_rng(2)
-    h = GpuHarness(oracle_impl, "lru", 2, 3, _rows(rng, 50, 8))
+    h = GpuHarness(oracle_impl, "lru", 2, 0, _rows(rng, 50, 8))
     try:
         keys = np.array([4, 9, 14, 19], np.uint64)
         h.lookup(keys)

@@ -141,8 +141,8 @@ def test_adam_sparse_after_dedup(hb):
         param, m, v = ops_port.adam_sparse_update(param, uniq, cg, m, v, 0.01, 0.9, 0.999, b1t,
                                                   b2t, 1e-7)
     np.testing.assert_allclose(pd.asnumpy(), param, rtol=RTOL, atol=1e-7)
-    np.testing.assert_allclose(md.asnumpy(), m, rtol=RTOL, atol=1e-9)
-    np.testing.assert_allclose(vd.asnumpy(), v, rtol=RTOL, atol=1e-12)
+    np.testing.assert_allclose(md.asnumpy(), m, rtol=RTOL, atol=1e-7)
+    np.testing.assert_allclose(vd.asnumpy(), v, rtol=RTOL, atol=1e-9)
 
 
 def test_adam_fused_equals_dedup_then_adam(hb):
@@ -233,10 +233,11 @@ def test_oneside_add_lookup_gradient_to_dense_l2(hb):
     uvals = rng.normal(size=(40, D)).astype(np.float32)
     dense = hb.empty((V, D), hb.gpu(0))
     gpu_links.array_set(dense, 0.0)
-    check_call(_LIB.IndexedSlices2Dense(_dev(hb, uvals).handle, _dev(hb, uids).handle, dense.handle, None))
+    d_uvals, d_uids, d_base = _dev(hb, uvals), _dev(hb, uids), _dev(hb, base)   # keep alive
+    check_call(_LIB.IndexedSlices2Dense(d_uvals.handle, d_uids.handle, dense.handle, None))
     assert_bits_equal(dense.asnumpy(), ops_port.indexedslices_to_dense(uvals, uids, (V, D)), "to dense")
     gv = _dev(hb, uvals)
-    check_call(_LIB.AddL2RegularizationSparse(_dev(hb, base).handle, _dev(hb, uids).handle, gv.handle,
+    check_call(_LIB.AddL2RegularizationSparse(d_base.handle, d_uids.handle, gv.handle,
                                               ctypes.c_float(0.01), None))
     np.testing.assert_allclose(gv.asnumpy(), ops_port.add_l2_regularization_sparse(base, uids, uvals, 0.01),
                                rtol=RTOL, atol=1e-7)
@@ -269,6 +270,7 @@ def test_operator_interface(hb):
     op.compute([_dev(hb, table), _dev(hb, ids)], out)
     assert np.array_equal(out.asnumpy(), table[ids.astype(np.int64)])
     gnode, _ = op.gradient(None)
+    op.infer_shape([(V, D), (4, 26)])            # propagates embed_shape to the gradient node
     assert gnode.infer_shape([None, None]) == (V, D)
     sl = hb.IndexedSlices()
     gnode.compute([out, _dev(hb, ids)], sl)
