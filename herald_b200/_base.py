@@ -47,3 +47,8 @@ def kernel_launch_count():
 
 def version():
     return _LIB.HBVersion().decode()
+
+
+def set_hot_threshold(rows):
+    """Ids occurring more than `rows` times in a batch take the column-split reduce path."""
+    check_call(_LIB.HBSetHotThreshold(ctypes.c_uint(int(rows))))

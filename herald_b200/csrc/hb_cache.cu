@@ -25,7 +25,7 @@
 #include <mutex>
 
 #include "hb_cache.cuh"
-#include "hb_rows.cuh"
+#include "hb_segment.cuh"
 
 namespace hb {
 namespace {
@@ -1260,24 +1260,19 @@ void run_accumulate(hb_cache *c, size_t n, int batch, const float *dev_grads, co
     flush_begin_kernel<<<1, 1, 0, st>>>(c->view.regs);
     HB_LAUNCHED();
     if (n) {
-        int grid = row_grid(n);
         const u32 *p = c->sorted[batch].perm;
-        if (vec4(c, dev_grads)) {
-            AccumulatePush<4> f{c->view, ws.uniq, c->uslot[batch], c->push_bound,
-                                use_plan ? dev_push_keys : nullptr, (u32)n_push, defer_cleanup};
-            if (use_plan && !dev_push_keys) // empty plan: nothing is pushed
-                f.push_keys = reinterpret_cast<const u64 *>(ws.uniq), f.n_push = 0;
-            segment_rows_kernel<4, AccumulatePush<4>>
-                <<<grid, kRowBlock, 0, st>>>(ws.seg_start, p, ws.num_unique, dev_grads, c->width, f);
-        } else {
-            AccumulatePush<1> f{c->view, ws.uniq, c->uslot[batch], c->push_bound,
-                                use_plan ? dev_push_keys : nullptr, (u32)n_push, defer_cleanup};
-            if (use_plan && !dev_push_keys)
-                f.push_keys = reinterpret_cast<const u64 *>(ws.uniq), f.n_push = 0;
-            segment_rows_kernel<1, AccumulatePush<1>>
-                <<<grid, kRowBlock, 0, st>>>(ws.seg_start, p, ws.num_unique, dev_grads, c->width, f);
+        const u64 *plan = use_plan ? dev_push_keys : nullptr;
+        u32 plan_n = (u32)n_push;
+        if (use_plan && !dev_push_keys) { // empty plan: nothing is pushed
+            plan = ws.uniq;
+            plan_n = 0;
         }
-        HB_LAUNCHED();
+        AccumulatePush<1> f1{c->view, ws.uniq, c->uslot[batch], c->push_bound, plan, plan_n,
+                             defer_cleanup};
+        AccumulatePush<4> f4{c->view, ws.uniq, c->uslot[batch], c->push_bound, plan, plan_n,
+                             defer_cleanup};
+        run_segment_reduce(ws, p, dev_grads, c->width, n, vec4(c, dev_grads), c->hot_threshold, st,
+                           f1, f4);
     }
     if (batch == 0)
         mark(c, 2);
@@ -1504,6 +1499,7 @@ int hb_cache_create(int policy, size_t limit, size_t length, size_t width, int n
     c->device = t->device;
     c->table = t;
     c->key_bits = bits_for(std::max<size_t>(length, t->length));
+    c->hot_threshold = default_hot_threshold();
     HB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     // row store: limit resident lines + slack for the running call's fresh lines and for dirty
     // victims waiting for the next push

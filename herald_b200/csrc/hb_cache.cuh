@@ -180,4 +180,5 @@ struct hb_cache {
     size_t occ_upper = 0;
     size_t pending_upper = 0;
     int key_bits = 64;
+    hb::u32 hot_threshold = 64; // segments longer than this take the column-split path
 };

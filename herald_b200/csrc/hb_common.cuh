@@ -72,6 +72,7 @@ inline int ceil_div(size_t a, size_t b) {
 }
 
 int sm_count();
+u32 default_hot_threshold();
 
 #ifdef __CUDACC__
 // ---- device helpers --------------------------------------------------------

@@ -9,8 +9,7 @@
 #include <map>
 #include <mutex>
 
-#include "hb_rows.cuh"
-#include "hb_sort.cuh"
+#include "hb_segment.cuh"
 
 namespace hb {
 namespace {
@@ -304,14 +303,7 @@ __global__ void emit_unique_f32(const u64 *uniq, const u32 *inverse, const u32 *
 template <class F1, class F4>
 void launch_segments(bool v4, const Segments &sg, const float *vals, size_t D, size_t n,
                      cudaStream_t st, F1 f1, F4 f4) {
-    int grid = row_grid(n);
-    if (v4)
-        segment_rows_kernel<4, F4><<<grid, kRowBlock, 0, st>>>(sg.ws->seg_start, sg.sk.perm,
-                                                               sg.ws->num_unique, vals, D, f4);
-    else
-        segment_rows_kernel<1, F1><<<grid, kRowBlock, 0, st>>>(sg.ws->seg_start, sg.sk.perm,
-                                                               sg.ws->num_unique, vals, D, f1);
-    HB_LAUNCHED();
+    run_segment_reduce(*sg.ws, sg.sk.perm, vals, D, n, v4, default_hot_threshold(), st, f1, f4);
 }
 
 template <class F1, class F4>

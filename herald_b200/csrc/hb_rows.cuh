@@ -117,7 +117,7 @@ template <int VEC, class F>
 __global__ void __launch_bounds__(kRowBlock)
     segment_rows_kernel(const u32 *__restrict__ seg_start, const u32 *__restrict__ perm,
                         const u32 *__restrict__ num_unique, const float *__restrict__ vals,
-                        size_t D, F f) {
+                        size_t D, u32 hot_threshold, F f) {
     using V = RowVec<VEC>;
     const unsigned lane = lane_id();
     const size_t warp_global = (size_t)blockIdx.x * kRowWarps + (threadIdx.x >> 5);
@@ -127,6 +127,8 @@ __global__ void __launch_bounds__(kRowBlock)
     f.kernel_begin();
     for (size_t u = warp_global; u < U; u += nwarps) {
         const u32 s0 = seg_start[u], s1 = seg_start[u + 1];
+        if (s1 - s0 > hot_threshold)
+            continue; // long segments belong to segment_hot_kernel
         typename F::Ctx ctx;
         if (!f.begin(u, s1 - s0, ctx))
             continue;
@@ -147,6 +149,146 @@ __global__ void __launch_bounds__(kRowBlock)
             f.store(ctx, c, acc);
         }
         f.end(ctx);
+    }
+    f.kernel_end();
+}
+
+// ---- long segments (hot ids) -------------------------------------------------------------
+// A Zipf batch has ids that occur thousands of times; one warp walking such a segment would
+// be the critical path of the whole step.  The ADD ORDER is fixed by the parity contract
+// (ascending occurrence), so a segment cannot be split by rows — it is split by COLUMNS: a work
+// item is (hot row, 32-float column chunk); a CTA streams the chunk of every occurrence through
+// shared memory with all 8 warps (256 rows = 32 KB in flight) while warp 0 adds them in order,
+// one column per lane.  Per-row scalars are applied afterwards by segment_hot_finish_kernel,
+// once every chunk of the row has read them.
+constexpr int kHotTileRows = 256;
+constexpr u32 kVeryHot = 1024; // rows above this go first (longest-processing-time-first)
+
+struct HotLists {
+    u32 *very_hot; // [cap] unique indices with count > kVeryHot
+    u32 *hot;      // [cap] unique indices with hot_threshold < count <= kVeryHot
+    u32 *ctrl;     // [0] = #very_hot, [1] = #hot, [2] = work ticket (zeroed with the scan arena)
+};
+
+__device__ __forceinline__ u32 rows_warp_append(u32 *counter, bool pred) {
+    unsigned m = __ballot_sync(FULL, pred);
+    if (!m)
+        return 0;
+    int leader = __ffs(m) - 1;
+    u32 base = 0;
+    if ((int)lane_id() == leader)
+        base = atomicAdd(counter, (u32)__popc(m));
+    base = __shfl_sync(FULL, base, leader);
+    return base + __popc(m & lanemask_lt());
+}
+
+static __global__ void __launch_bounds__(256)
+    build_hot_lists_kernel(const u32 *__restrict__ seg_start, const u32 *__restrict__ num_unique,
+                           u32 hot_threshold, HotLists hl) {
+    const u32 U = *num_unique;
+    const u32 stride = gridDim.x * blockDim.x;
+    const u32 rounds = (U + stride - 1) / stride;
+    for (u32 it = 0; it < rounds; it++) {
+        const u32 u = it * stride + blockIdx.x * blockDim.x + threadIdx.x;
+        u32 cnt = 0;
+        if (u < U)
+            cnt = seg_start[u + 1] - seg_start[u];
+        const bool a = cnt > kVeryHot && cnt > hot_threshold;
+        const bool b = !a && cnt > hot_threshold;
+        u32 pa = rows_warp_append(&hl.ctrl[0], a);
+        if (a)
+            hl.very_hot[pa] = u;
+        u32 pb = rows_warp_append(&hl.ctrl[1], b);
+        if (b)
+            hl.hot[pb] = u;
+    }
+}
+
+template <class F> // F is the VEC = 1 instantiation: load/step/store address single columns
+__global__ void __launch_bounds__(kRowBlock)
+    segment_hot_kernel(const u32 *__restrict__ seg_start, const u32 *__restrict__ perm,
+                       const float *__restrict__ vals, size_t D, HotLists hl, F f) {
+    __shared__ float tile[kHotTileRows][32];
+    __shared__ u32 s_item;
+    constexpr int ROWS_PER_WARP = kHotTileRows / kRowWarps; // 32
+    const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
+    const u32 Q = (u32)((D + 31) / 32);
+    const u32 nA = hl.ctrl[0], nB = hl.ctrl[1];
+    const u32 total = (nA + nB) * Q;
+    f.kernel_begin();
+    while (true) {
+        __syncthreads();
+        if (threadIdx.x == 0)
+            s_item = atomicAdd(&hl.ctrl[2], 1u);
+        __syncthreads();
+        const u32 t = s_item;
+        if (t >= total)
+            break;
+        const u32 h = t / Q, q = t % Q;
+        const u32 u = h < nA ? hl.very_hot[h] : hl.hot[h - nA];
+        const u32 s0 = seg_start[u], s1 = seg_start[u + 1];
+        typename F::Ctx ctx;
+        if (!f.begin(u, s1 - s0, ctx))
+            continue;
+        const size_t col = (size_t)q * 32 + lane;
+        const bool active = col < D;
+        decltype(f.load(ctx, 0)) acc;
+        if (warp == 0 && active)
+            acc = f.load(ctx, col);
+        const u32 ntiles = (s1 - s0 + kHotTileRows - 1) / kHotTileRows;
+        float reg[ROWS_PER_WARP];
+        auto issue = [&](u32 k) {
+            const u32 base = s0 + k * kHotTileRows + warp * ROWS_PER_WARP;
+#pragma unroll
+            for (int j = 0; j < ROWS_PER_WARP; j++) {
+                const u32 p = base + j;
+                reg[j] = (p < s1 && active) ? __ldg(vals + (size_t)perm[p] * D + col) : 0.f;
+            }
+        };
+        issue(0);
+        for (u32 k = 0; k < ntiles; k++) {
+#pragma unroll
+            for (int j = 0; j < ROWS_PER_WARP; j++)
+                tile[warp * ROWS_PER_WARP + j][lane] = reg[j];
+            __syncthreads();
+            if (k + 1 < ntiles)
+                issue(k + 1); // next tile's loads fly while warp 0 adds this one
+            if (warp == 0 && active) {
+                const u32 rows = min((u32)kHotTileRows, s1 - s0 - k * kHotTileRows);
+                u32 r = 0;
+                for (; r + 8 <= rows; r += 8) {
+                    float g[8];
+#pragma unroll
+                    for (int j = 0; j < 8; j++)
+                        g[j] = tile[r + j][lane];
+#pragma unroll
+                    for (int j = 0; j < 8; j++)
+                        acc = f.step(acc, g[j]);
+                }
+                for (; r < rows; r++)
+                    acc = f.step(acc, tile[r][lane]);
+            }
+            __syncthreads();
+        }
+        if (warp == 0 && active)
+            f.store(ctx, col, acc);
+    }
+    f.kernel_end();
+}
+
+// per-row scalars of the hot rows, after every chunk has been processed
+template <class F>
+__global__ void __launch_bounds__(kRowBlock)
+    segment_hot_finish_kernel(const u32 *__restrict__ seg_start, HotLists hl, F f) {
+    const u32 nA = hl.ctrl[0], nB = hl.ctrl[1];
+    const size_t warp_global = (size_t)blockIdx.x * kRowWarps + (threadIdx.x >> 5);
+    const size_t nwarps = (size_t)gridDim.x * kRowWarps;
+    f.kernel_begin();
+    for (size_t h = warp_global; h < nA + nB; h += nwarps) {
+        const u32 u = h < nA ? hl.very_hot[h] : hl.hot[h - nA];
+        typename F::Ctx ctx;
+        if (f.begin(u, seg_start[u + 1] - seg_start[u], ctx))
+            f.end(ctx);
     }
     f.kernel_end();
 }

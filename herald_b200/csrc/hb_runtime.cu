@@ -5,6 +5,8 @@
 #include <cstring>
 #include <mutex>
 
+#include <algorithm>
+
 #include "hb_common.cuh"
 
 namespace hb {
@@ -14,6 +16,18 @@ std::atomic<uint64_t> g_launches{0};
 
 void set_last_error(const std::string &msg) {
     t_last_error = msg;
+}
+
+static std::atomic<u32> g_hot_threshold{0};
+
+u32 default_hot_threshold() {
+    u32 t = g_hot_threshold.load();
+    if (t == 0) {
+        const char *e = getenv("HERALD_HOT_THRESHOLD");
+        t = e ? (u32)std::max(1, atoi(e)) : 64u;
+        g_hot_threshold.store(t);
+    }
+    return t;
 }
 
 int sm_count() {
@@ -56,6 +70,11 @@ const char *HBVersion(void) {
 
 uint64_t HBKernelLaunchCount(void) {
     return g_launches.load();
+}
+
+int HBSetHotThreshold(unsigned rows) {
+    g_hot_threshold.store(rows ? rows : 1u);
+    return 0;
 }
 
 int DLStreamCreate(size_t dev_id, DLStreamHandle *handle) {

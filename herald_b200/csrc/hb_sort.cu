@@ -243,8 +243,10 @@ void KeyWorkspace::reserve(size_t n) {
     dev_alloc(seg_start, c + 1);
     dev_alloc(num_unique, 1);
     ntile_cap = (c + kScanBlock - 1) / kScanBlock + 1;
-    dev_alloc(scan_arena, (size_t)kScanSlots * scan_slot_words());
-    HB_CUDA(cudaMemset(scan_arena, 0, (size_t)kScanSlots * scan_slot_words() * sizeof(u64)));
+    dev_alloc(scan_arena, arena_words());
+    HB_CUDA(cudaMemset(scan_arena, 0, arena_words() * sizeof(u64)));
+    dev_alloc(hot_a, c);
+    dev_alloc(hot_b, c);
     cap = c;
 }
 
@@ -259,12 +261,13 @@ void KeyWorkspace::release() {
     dev_free(seg_start);
     dev_free(num_unique);
     dev_free(scan_arena);
+    dev_free(hot_a);
+    dev_free(hot_b);
     cap = 0;
 }
 
 void KeyWorkspace::reset_scans(cudaStream_t st) {
-    HB_CUDA(cudaMemsetAsync(scan_arena, 0, (size_t)kScanSlots * scan_slot_words() * sizeof(u64),
-                            st));
+    HB_CUDA(cudaMemsetAsync(scan_arena, 0, arena_words() * sizeof(u64), st));
     scan_next = 0;
 }
 

@@ -27,7 +27,10 @@ struct KeyWorkspace {
     u32 *inverse = nullptr;   // [cap]   rank of keys[i] in uniq
     u32 *seg_start = nullptr; // [cap+1] first sorted position of each unique key
     u32 *num_unique = nullptr; // device scalar
-    // scan arena: kScanSlots x (ticket + status[ntile_cap])
+    // hot-segment work lists (see hb_rows.cuh); the control words live behind the scan arena so
+    // that reset_scans() zeroes them with the same memset
+    u32 *hot_a = nullptr, *hot_b = nullptr; // [cap]
+    // scan arena: kScanSlots x (ticket + status[ntile_cap]), then 2 control words
     u64 *scan_arena = nullptr;
     size_t ntile_cap = 0;
     int scan_next = 0;
@@ -36,6 +39,12 @@ struct KeyWorkspace {
     void release();
     size_t scan_slot_words() const {
         return ntile_cap + 1;
+    }
+    size_t arena_words() const {
+        return (size_t)kScanSlots * scan_slot_words() + 2;
+    }
+    u32 *hot_ctrl() const {
+        return reinterpret_cast<u32 *>(scan_arena + (size_t)kScanSlots * scan_slot_words());
     }
     // zero every scan slot (one memset) — call once at the start of an op
     void reset_scans(cudaStream_t st);

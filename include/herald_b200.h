@@ -63,6 +63,10 @@ const char *HBGetLastError(void);
 const char *HBVersion(void);
 /* Number of kernels this library has launched in this process (bench `gpu_launches`). */
 uint64_t HBKernelLaunchCount(void);
+/* Segments (occurrences of one id in a batch) longer than `rows` are reduced by the column-split
+ * hot path; default 64 (or $HERALD_HOT_THRESHOLD).  Applies to op-level calls and to caches
+ * created afterwards.  Results are bit-identical either way; tests lower it for coverage. */
+int HBSetHotThreshold(unsigned rows);
 
 /* ---- runtime plumbing: src/common/c_runtime_api.h:28-77 ------------------- */
 int DLStreamCreate(size_t dev_id, DLStreamHandle *handle);

@@ -73,6 +73,39 @@ def test_wide_rows_and_larger_batches(oracle_impl, policy):
                   max_n=6000, a=1.05)
 
 
+@pytest.mark.parametrize("policy,bound,D", [("lru", 0, 8), ("lfu", 2, 128), ("lru", 10, 40),
+                                            ("lfuopt", 0, 6)])
+@pytest.mark.parametrize("mode", ["plain", "plan", "pushpull"])
+def test_hot_segment_path(oracle_impl, policy, bound, D, mode):
+    """Ids occurring more than 2 times go through the column-split hot path (production
+    threshold: 64); results stay bit-identical to the serial reference."""
+    from herald_b200._base import set_hot_threshold
+    set_hot_threshold(2)
+    try:
+        _run_sequence(oracle_impl, policy, limit=60, bound=bound, V=300, D=D, steps=25, seed=21,
+                      max_n=600, push_keys=mode == "plan", push_pull=mode == "pushpull", a=1.2)
+    finally:
+        set_hot_threshold(64)
+
+
+def test_very_hot_id(oracle_impl):
+    """One id repeated thousands of times (> kVeryHot, several 256-row tiles) among cold ids."""
+    rng = np.random.default_rng(17)
+    V, D = 400, 128
+    h = GpuHarness(oracle_impl, "lru", 100, 0, _rows(rng, V, D))
+    try:
+        for t in range(3):
+            keys = zipf_keys(rng, 6000, V, 1.3)
+            keys[rng.random(6000) < 0.5] = 7      # ~3000 occurrences of id 7
+            keys[rng.random(6000) < 0.1] = 11     # ~600 of id 11
+            h.lookup(keys)
+            h.update(keys, rng.normal(0, 1e-3, (6000, D)).astype(np.float32))
+        h.check_state()
+        h.check_lines()
+    finally:
+        h.close()
+
+
 def test_width_not_multiple_of_four(oracle_impl):
     _run_sequence(oracle_impl, "lru", limit=40, bound=1, V=200, D=6, steps=30, seed=5)
 

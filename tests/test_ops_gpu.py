@@ -82,9 +82,12 @@ def test_unique_inverse_bit_exact(hb):
 
 
 @pytest.mark.parametrize("D", [8, 128])
-def test_sgd_sparse_update_duplicate_ids(hb, D):
+@pytest.mark.parametrize("hot_threshold", [64, 3])
+def test_sgd_sparse_update_duplicate_ids(hb, D, hot_threshold):
     from herald_b200 import gpu_links
+    from herald_b200._base import set_hot_threshold
     from oracle import ops_port
+    set_hot_threshold(hot_threshold)
     rng = np.random.default_rng(4)
     V, n = 60, 500
     param = rng.normal(size=(V, D)).astype(np.float32)
@@ -92,6 +95,7 @@ def test_sgd_sparse_update_duplicate_ids(hb, D):
     g = rng.normal(size=(n, D)).astype(np.float32)
     p = _dev(hb, param)
     gpu_links.sgd_update(p, hb.IndexedSlices(_dev(hb, ids), _dev(hb, g), (V, D)), 0.01)
+    set_hot_threshold(64)
     assert_bits_equal(p.asnumpy(), ops_port.sgd_sparse_update(param, ids, g, 0.01), "sgd sparse")
 
 
