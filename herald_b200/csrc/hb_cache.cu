@@ -265,9 +265,13 @@ __global__ void alloc_kernel(CacheView c, const u64 *uniq, i32 *uslot, const u32
 // sync with the owner shard: kSyncEmbedding (PSFhandle_embedding.cc:30-64) + client closure
 // (hetu_client.cc:19-32): rows whose version is -1 or more than pull_bound behind are re-read.
 // =====================================================================================
-template <int VEC>
+// A warp takes 32 consecutive uniques: the staleness test of all 32 is evaluated lane-parallel
+// (slot, version, owner version), then the stale rows are copied ROWS at a time so that several
+// 512 B row reads are in flight per warp.
+template <int VEC, int ROWS>
 __global__ void __launch_bounds__(kRowBlock)
-    sync_kernel(CacheView c, const u64 *uniq, const i32 *uslot, i64 pull_bound) {
+    sync_kernel(CacheView c, const u64 *__restrict__ uniq, const i32 *__restrict__ uslot,
+                i64 pull_bound) {
     using V = RowVec<VEC>;
     const unsigned lane = lane_id();
     const size_t warp_global = (size_t)blockIdx.x * kRowWarps + (threadIdx.x >> 5);
@@ -279,34 +283,63 @@ __global__ void __launch_bounds__(kRowBlock)
         *cnt = 0;
     __syncthreads();
     u32 pulled = 0;
-    for (size_t i = warp_global; i < U; i += nwarps) {
-        const i32 s = uslot[i];
-        const u64 key = uniq[i];
-        const u64 trow = key - c.row_begin;
-        if (s < 0 || trow >= c.nrows_local)
-            continue;
-        const i64 v = c.slot_version[s];
-        const i64 srv = c.tver[trow];
-        if (!(v == -1 || srv - v > pull_bound))
-            continue;
-        const u8 flags = c.slot_flags[s];
-        const bool addup = flags & F_GRAD;                  // Line::addup (embedding.h:92-96)
-        const bool live_grad = addup && c.slot_updates[s] != 0; // grad store is meaningful
-        const float *src = c.trows + trow * D;
-        float *dst = c.data + (size_t)s * D;
-        const float *g = c.grad + (size_t)s * D;
-        for (size_t k = lane; k < nvec; k += 32) {
-            typename V::T x = V::ld(src + k * VEC);
-            if (addup)
-                x = V::add(x, live_grad ? V::ld(g + k * VEC) : V::zero());
-            V::st(dst + k * VEC, x);
+    for (size_t base = warp_global * 32; base < U; base += nwarps * 32) {
+        const size_t i = base + lane;
+        i32 s = -1;
+        u64 trow = 0;
+        i64 srv = 0;
+        bool need = false, addup = false, live_grad = false;
+        if (i < U) {
+            s = uslot[i];
+            trow = uniq[i] - c.row_begin;
+            if (s >= 0 && trow < c.nrows_local) {
+                const i64 v = c.slot_version[s];
+                srv = c.tver[trow];
+                need = v == -1 || srv - v > pull_bound;
+                if (need) {
+                    addup = c.slot_flags[s] & F_GRAD; // Line::addup (embedding.h:92-96)
+                    live_grad = addup && c.slot_updates[s] != 0; // grad store is meaningful
+                    c.slot_version[s] = srv;
+                }
+            }
         }
-        if (lane == 0) {
-            c.slot_version[s] = srv;
-            pulled++;
+        unsigned m = __ballot_sync(FULL, need);
+        pulled += __popc(m);
+        while (m) {
+            int src[ROWS];
+            i32 rs[ROWS];
+            u64 rt[ROWS];
+            bool ra[ROWS], rg[ROWS];
+#pragma unroll
+            for (int r = 0; r < ROWS; r++) {
+                src[r] = m ? __ffs(m) - 1 : -1;
+                if (m)
+                    m &= m - 1;
+                const int from = src[r] < 0 ? 0 : src[r];
+                rs[r] = __shfl_sync(FULL, s, from);
+                rt[r] = __shfl_sync(FULL, trow, from);
+                ra[r] = __shfl_sync(FULL, addup, from);
+                rg[r] = __shfl_sync(FULL, live_grad, from);
+            }
+            for (size_t k = lane; k < nvec; k += 32) {
+                typename V::T x[ROWS], g[ROWS];
+#pragma unroll
+                for (int r = 0; r < ROWS; r++)
+                    if (src[r] >= 0) {
+                        x[r] = V::ld(c.trows + rt[r] * D + k * VEC);
+                        g[r] = rg[r] ? V::ld(c.grad + (size_t)rs[r] * D + k * VEC) : V::zero();
+                    }
+#pragma unroll
+                for (int r = 0; r < ROWS; r++)
+                    if (src[r] >= 0) {
+                        if (ra[r])
+                            x[r] = V::add(x[r], g[r]);
+                        V::st(c.data + (size_t)rs[r] * D + k * VEC, x[r]);
+                    }
+            }
         }
     }
-    if (pulled)
+    if (lane == 0 && pulled)
         atomicAdd(cnt, pulled);
     __syncthreads();
     if (threadIdx.x == 0 && *cnt)
@@ -698,7 +731,7 @@ template <int VEC>
 struct AccumulatePush {
     using V = RowVec<VEC>;
     struct Acc {
-        typename V::T d, g;
+        typename V::T d, g, t; // cache row, pending gradient, owner row (read ahead for the push)
     };
     struct Ctx {
         i32 s;
@@ -762,22 +795,22 @@ struct AccumulatePush {
         const size_t o = (size_t)x.s * c.width + k * VEC;
         a.d = x.dataless ? V::zero() : V::ld(c.data + o);
         a.g = x.upd0 != 0 ? V::ld(c.grad + o) : V::zero();
+        a.t = (x.pushed && x.local) ? V::ld(c.trows + x.trow * c.width + k * VEC) : V::zero();
         return a;
     }
     __device__ Acc step(const Acc &a, const typename V::T &g) const {
         Acc r; // embedding.h:78-91: grad_ += g; data_ += g  (per occurrence, in order)
         r.g = V::add(a.g, g);
         r.d = V::add(a.d, g);
+        r.t = a.t;
         return r;
     }
     __device__ void store(const Ctx &x, size_t k, const Acc &a) const {
         const size_t o = (size_t)x.s * c.width + k * VEC;
         if (!x.dataless)
             V::st(c.data + o, a.d);
-        if (x.pushed && x.local) { // PSFhandle_embedding.cc:25-26: row += pushed grad
-            float *t = c.trows + x.trow * c.width + k * VEC;
-            V::st(t, V::add(V::ld(t), a.g));
-        }
+        if (x.pushed && x.local) // PSFhandle_embedding.cc:25-26: row += pushed grad
+            V::st(c.trows + x.trow * c.width + k * VEC, V::add(a.t, a.g));
         if (!x.pushed || (defer_cleanup && !x.dataless))
             V::st(c.grad + o, a.g);
     }
@@ -1199,13 +1232,13 @@ bool vec4(const hb_cache *c, const void *user_rows) {
 void run_sync(hb_cache *c, size_t n) {
     if (!n)
         return;
-    int grid = row_grid(n);
+    int grid = row_grid((n + 31) / 32);
     if (c->width % 4 == 0)
-        sync_kernel<4><<<grid, kRowBlock, 0, c->stream>>>(c->view, c->ws[0].uniq, c->uslot[0],
-                                                          c->pull_bound);
+        sync_kernel<4, 4><<<grid, kRowBlock, 0, c->stream>>>(c->view, c->ws[0].uniq, c->uslot[0],
+                                                             c->pull_bound);
     else
-        sync_kernel<1><<<grid, kRowBlock, 0, c->stream>>>(c->view, c->ws[0].uniq, c->uslot[0],
-                                                          c->pull_bound);
+        sync_kernel<1, 4><<<grid, kRowBlock, 0, c->stream>>>(c->view, c->ws[0].uniq, c->uslot[0],
+                                                             c->pull_bound);
     HB_LAUNCHED();
 }
 

@@ -75,8 +75,10 @@ inline int row_grid(size_t rows) {
 }
 
 // ---- gather: dst[n,:] = src[index(n),:] ------------------------------------------------
-// Index is a functor n -> source row (or < 0 to write zeros).  ROWS rows are in flight per warp
-// per iteration: all index loads first, then all row loads, then all stores.
+// Index is a functor n -> source row (or < 0 to write zeros).  A warp takes 32 consecutive
+// destination rows: their source rows are resolved lane-parallel (one coalesced index load
+// instead of 32 broadcast ones), then ROWS rows are in flight per warp per iteration: all row
+// loads first, then all stores.
 template <int VEC, int ROWS, class Index>
 __global__ void __launch_bounds__(kRowBlock)
     gather_rows_kernel(const float *__restrict__ src, float *__restrict__ dst, size_t n, size_t D,
@@ -86,88 +88,65 @@ __global__ void __launch_bounds__(kRowBlock)
     const size_t warp_global = (size_t)blockIdx.x * kRowWarps + (threadIdx.x >> 5);
     const size_t nwarps = (size_t)gridDim.x * kRowWarps;
     const size_t nvec = D / VEC;
-    for (size_t row0 = warp_global * ROWS; row0 < n; row0 += nwarps * ROWS) {
-        long long srow[ROWS];
-#pragma unroll
-        for (int r = 0; r < ROWS; r++)
-            srow[r] = (row0 + r < n) ? index(row0 + r) : -1;
-        for (size_t c = lane; c < nvec; c += 32) {
-            typename V::T v[ROWS];
-#pragma unroll
-            for (int r = 0; r < ROWS; r++)
-                v[r] = srow[r] >= 0 ? V::ld(src + (size_t)srow[r] * D + c * VEC) : V::zero();
+    for (size_t base = warp_global * 32; base < n; base += nwarps * 32) {
+        const long long mine = base + lane < n ? index(base + lane) : -1;
+        const int rows_here = (int)min((size_t)32, n - base);
+#pragma unroll 1
+        for (int r0 = 0; r0 < rows_here; r0 += ROWS) {
+            long long srow[ROWS];
 #pragma unroll
             for (int r = 0; r < ROWS; r++)
-                if (row0 + r < n)
-                    V::st_cs(dst + (row0 + r) * D + c * VEC, v[r]);
+                srow[r] = __shfl_sync(FULL, mine, (r0 + r) & 31);
+            for (size_t c = lane; c < nvec; c += 32) {
+                typename V::T v[ROWS];
+#pragma unroll
+                for (int r = 0; r < ROWS; r++)
+                    v[r] = (r0 + r < rows_here && srow[r] >= 0)
+                               ? V::ld(src + (size_t)srow[r] * D + c * VEC)
+                               : V::zero();
+#pragma unroll
+                for (int r = 0; r < ROWS; r++)
+                    if (r0 + r < rows_here)
+                        V::st_cs(dst + (base + r0 + r) * D + c * VEC, v[r]);
+            }
         }
     }
 }
 
 // ---- segment reduce by unique key, applied to a destination row -----------------------
-// For unique u (one warp):  F::Ctx ctx; if (!f.begin(u, cnt, ctx)) skip;
-//   per 128-bit column chunk c:  acc = f.load(ctx, c);
-//                                for each occurrence p in ascending original index:
-//                                    acc = f.step(acc, vals[perm[p], c]);
-//                                f.store(ctx, c, acc);
-//   f.end(ctx)   (all lanes; per-row scalars are written by lane 0 inside)
-// The adds happen in occurrence order, so the result is deterministic and equal to a serial
-// CPU loop over the batch.
-template <int VEC, class F>
-__global__ void __launch_bounds__(kRowBlock)
-    segment_rows_kernel(const u32 *__restrict__ seg_start, const u32 *__restrict__ perm,
-                        const u32 *__restrict__ num_unique, const float *__restrict__ vals,
-                        size_t D, u32 hot_threshold, F f) {
-    using V = RowVec<VEC>;
-    const unsigned lane = lane_id();
-    const size_t warp_global = (size_t)blockIdx.x * kRowWarps + (threadIdx.x >> 5);
-    const size_t nwarps = (size_t)gridDim.x * kRowWarps;
-    const size_t nvec = D / VEC;
-    const u32 U = *num_unique;
-    f.kernel_begin();
-    for (size_t u = warp_global; u < U; u += nwarps) {
-        const u32 s0 = seg_start[u], s1 = seg_start[u + 1];
-        if (s1 - s0 > hot_threshold)
-            continue; // long segments belong to segment_hot_kernel
-        typename F::Ctx ctx;
-        if (!f.begin(u, s1 - s0, ctx))
-            continue;
-        for (size_t c = lane; c < nvec; c += 32) {
-            auto acc = f.load(ctx, c);
-            u32 p = s0;
-            for (; p + 4 <= s1; p += 4) {
-                typename V::T g[4];
-#pragma unroll
-                for (int k = 0; k < 4; k++)
-                    g[k] = V::ld_nc(vals + (size_t)perm[p + k] * D + c * VEC);
-#pragma unroll
-                for (int k = 0; k < 4; k++)
-                    acc = f.step(acc, g[k]);
-            }
-            for (; p < s1; p++)
-                acc = f.step(acc, V::ld_nc(vals + (size_t)perm[p] * D + c * VEC));
-            f.store(ctx, c, acc);
-        }
-        f.end(ctx);
-    }
-    f.kernel_end();
-}
-
-// ---- long segments (hot ids) -------------------------------------------------------------
-// A Zipf batch has ids that occur thousands of times; one warp walking such a segment would
-// be the critical path of the whole step.  The ADD ORDER is fixed by the parity contract
-// (ascending occurrence), so a segment cannot be split by rows — it is split by COLUMNS: a work
-// item is (hot row, 32-float column chunk); a CTA streams the chunk of every occurrence through
-// shared memory with all 8 warps (256 rows = 32 KB in flight) while warp 0 adds them in order,
-// one column per lane.  Per-row scalars are applied afterwards by segment_hot_finish_kernel,
-// once every chunk of the row has read them.
-constexpr int kHotTileRows = 256;
+// For unique u:  F::Ctx ctx; if (!f.begin(u, cnt, ctx)) skip;
+//   per column chunk c:  acc = f.load(ctx, c);
+//                        for each occurrence p in ascending original index:
+//                            acc = f.step(acc, vals[perm[p], c]);
+//                        f.store(ctx, c, acc);
+//   f.end(ctx)   (all lanes of one warp; per-row scalars are written by lane 0 inside)
+// The adds happen in occurrence order, so the result is deterministic and bit-identical to a
+// serial CPU loop over the batch (Line::accumulate order, src/hetu_cache/include/embedding.h:78-91).
+//
+// One persistent kernel does the whole reduce:
+//   * hot phase — a Zipf batch has ids that occur thousands of times and the add ORDER is fixed
+//     by the parity contract, so such a segment cannot be split by rows; it is split by COLUMNS.
+//     A work item is (hot row, 32-float column chunk).  The CTA streams the chunk of every
+//     occurrence through a kHotStages-deep cp.async ring in shared memory (all 8 warps issue,
+//     128 occurrences x 128 B per stage) while warp 0 adds them in order, one column per lane:
+//     the critical path is the dependent FADD chain itself, not memory latency.  Items are taken
+//     from a ticket, longest rows first; the CTA that finishes the last chunk of a row applies
+//     the row's scalars (f.end).
+//   * cold phase — every warp takes tickets of 32 consecutive uniques and walks them ROWS at a
+//     time: the metadata of all 32 is loaded lane-parallel, then the row / gradient / owner-row
+//     loads of ROWS segments are in flight together (128-bit per lane) before the first add.
+constexpr int kHotTileRows = 128; // occurrences per pipeline stage
+constexpr int kHotStages = 4;     // 4 x 128 x 128 B = 64 KB of dynamic shared memory
+constexpr int kHotSmemBytes = kHotStages * kHotTileRows * 32 * 4;
 constexpr u32 kVeryHot = 1024; // rows above this go first (longest-processing-time-first)
 
 struct HotLists {
     u32 *very_hot; // [cap] unique indices with count > kVeryHot
     u32 *hot;      // [cap] unique indices with hot_threshold < count <= kVeryHot
-    u32 *ctrl;     // [0] = #very_hot, [1] = #hot, [2] = work ticket (zeroed with the scan arena)
+    u32 *done_a;   // [cap] finished chunks per very-hot row (zeroed by build_hot_lists_kernel)
+    u32 *done_b;   // [cap] same for the hot list
+    u32 *ctrl;     // [0] = #very_hot, [1] = #hot, [2] = hot ticket, [3] = cold ticket (zeroed with
+                   // the scan arena)
 };
 
 __device__ __forceinline__ u32 rows_warp_append(u32 *counter, bool pred) {
@@ -196,101 +175,225 @@ static __global__ void __launch_bounds__(256)
         const bool a = cnt > kVeryHot && cnt > hot_threshold;
         const bool b = !a && cnt > hot_threshold;
         u32 pa = rows_warp_append(&hl.ctrl[0], a);
-        if (a)
+        if (a) {
             hl.very_hot[pa] = u;
-        u32 pb = rows_warp_append(&hl.ctrl[1], b);
-        if (b)
-            hl.hot[pb] = u;
-    }
-}
-
-template <class F> // F is the VEC = 1 instantiation: load/step/store address single columns
-__global__ void __launch_bounds__(kRowBlock)
-    segment_hot_kernel(const u32 *__restrict__ seg_start, const u32 *__restrict__ perm,
-                       const float *__restrict__ vals, size_t D, HotLists hl, F f) {
-    __shared__ float tile[kHotTileRows][32];
-    __shared__ u32 s_item;
-    constexpr int ROWS_PER_WARP = kHotTileRows / kRowWarps; // 32
-    const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
-    const u32 Q = (u32)((D + 31) / 32);
-    const u32 nA = hl.ctrl[0], nB = hl.ctrl[1];
-    const u32 total = (nA + nB) * Q;
-    f.kernel_begin();
-    while (true) {
-        __syncthreads();
-        if (threadIdx.x == 0)
-            s_item = atomicAdd(&hl.ctrl[2], 1u);
-        __syncthreads();
-        const u32 t = s_item;
-        if (t >= total)
-            break;
-        const u32 h = t / Q, q = t % Q;
-        const u32 u = h < nA ? hl.very_hot[h] : hl.hot[h - nA];
-        const u32 s0 = seg_start[u], s1 = seg_start[u + 1];
-        typename F::Ctx ctx;
-        if (!f.begin(u, s1 - s0, ctx))
-            continue;
-        const size_t col = (size_t)q * 32 + lane;
-        const bool active = col < D;
-        decltype(f.load(ctx, 0)) acc;
-        if (warp == 0 && active)
-            acc = f.load(ctx, col);
-        const u32 ntiles = (s1 - s0 + kHotTileRows - 1) / kHotTileRows;
-        float reg[ROWS_PER_WARP];
-        auto issue = [&](u32 k) {
-            const u32 base = s0 + k * kHotTileRows + warp * ROWS_PER_WARP;
-#pragma unroll
-            for (int j = 0; j < ROWS_PER_WARP; j++) {
-                const u32 p = base + j;
-                reg[j] = (p < s1 && active) ? __ldg(vals + (size_t)perm[p] * D + col) : 0.f;
-            }
-        };
-        issue(0);
-        for (u32 k = 0; k < ntiles; k++) {
-#pragma unroll
-            for (int j = 0; j < ROWS_PER_WARP; j++)
-                tile[warp * ROWS_PER_WARP + j][lane] = reg[j];
-            __syncthreads();
-            if (k + 1 < ntiles)
-                issue(k + 1); // next tile's loads fly while warp 0 adds this one
-            if (warp == 0 && active) {
-                const u32 rows = min((u32)kHotTileRows, s1 - s0 - k * kHotTileRows);
-                u32 r = 0;
-                for (; r + 8 <= rows; r += 8) {
-                    float g[8];
-#pragma unroll
-                    for (int j = 0; j < 8; j++)
-                        g[j] = tile[r + j][lane];
-#pragma unroll
-                    for (int j = 0; j < 8; j++)
-                        acc = f.step(acc, g[j]);
-                }
-                for (; r < rows; r++)
-                    acc = f.step(acc, tile[r][lane]);
-            }
-            __syncthreads();
+            hl.done_a[pa] = 0;
         }
-        if (warp == 0 && active)
-            f.store(ctx, col, acc);
+        u32 pb = rows_warp_append(&hl.ctrl[1], b);
+        if (b) {
+            hl.hot[pb] = u;
+            hl.done_b[pb] = 0;
+        }
     }
-    f.kernel_end();
 }
 
-// per-row scalars of the hot rows, after every chunk has been processed
-template <class F>
-__global__ void __launch_bounds__(kRowBlock)
-    segment_hot_finish_kernel(const u32 *__restrict__ seg_start, HotLists hl, F f) {
-    const u32 nA = hl.ctrl[0], nB = hl.ctrl[1];
-    const size_t warp_global = (size_t)blockIdx.x * kRowWarps + (threadIdx.x >> 5);
-    const size_t nwarps = (size_t)gridDim.x * kRowWarps;
-    f.kernel_begin();
-    for (size_t h = warp_global; h < nA + nB; h += nwarps) {
-        const u32 u = h < nA ? hl.very_hot[h] : hl.hot[h - nA];
-        typename F::Ctx ctx;
-        if (f.begin(u, seg_start[u + 1] - seg_start[u], ctx))
-            f.end(ctx);
+__device__ __forceinline__ void cp_async_f32(float *smem_dst, const float *gsrc) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() {
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// FV: the functor instantiated for the cold path's vector width VEC; F1: the same functor for
+// VEC = 1 (the hot path addresses single columns).
+template <int VEC, int ROWS, class FV, class F1>
+__global__ void __launch_bounds__(kRowBlock, 2)
+    segment_reduce_kernel(const u32 *__restrict__ seg_start, const u32 *__restrict__ perm,
+                          const u32 *__restrict__ num_unique, const float *__restrict__ vals,
+                          size_t D, u32 hot_threshold, HotLists hl, FV fv, F1 f1) {
+    extern __shared__ __align__(16) float s_ring[]; // [kHotStages][kHotTileRows][32]
+    __shared__ u32 s_item;
+    using V = RowVec<VEC>;
+    const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
+    const u32 U = *num_unique;
+    fv.kernel_begin();
+
+    // ------------------------------- hot phase -------------------------------------------
+    if (hot_threshold != 0xffffffffu) {
+        constexpr int RPW = kHotTileRows / kRowWarps; // rows of a stage issued by one warp: 16
+        const u32 Q = (u32)((D + 31) / 32);
+        const u32 nA = hl.ctrl[0], nB = hl.ctrl[1];
+        const u32 total = (nA + nB) * Q;
+        while (true) {
+            __syncthreads(); // the ring and s_item of the previous item are no longer in use
+            if (threadIdx.x == 0)
+                s_item = atomicAdd(&hl.ctrl[2], 1u);
+            __syncthreads();
+            const u32 t = s_item;
+            if (t >= total)
+                break;
+            const u32 h = t / Q, q = t % Q;
+            const u32 u = h < nA ? hl.very_hot[h] : hl.hot[h - nA];
+            u32 *done = h < nA ? &hl.done_a[h] : &hl.done_b[h - nA];
+            const u32 s0 = seg_start[u], s1 = seg_start[u + 1];
+            const u32 cnt = s1 - s0;
+            typename F1::Ctx ctx;
+            const bool ok = f1.begin(u, cnt, ctx);
+            if (ok) {
+                const size_t col = (size_t)q * 32 + lane;
+                const bool active = col < D;
+                decltype(f1.load(ctx, 0)) acc;
+                if (warp == 0 && active)
+                    acc = f1.load(ctx, col);
+                const u32 ntiles = (cnt + kHotTileRows - 1) / kHotTileRows;
+                // lane j < RPW holds the source row of occurrence (tile, warp * RPW + j)
+                auto load_perm = [&](u32 tile) -> u32 {
+                    const u32 p = s0 + tile * kHotTileRows + warp * RPW + (lane & (RPW - 1));
+                    return (tile < ntiles && p < s1) ? perm[p] : 0xffffffffu;
+                };
+                auto issue = [&](u32 tile, u32 pv) {
+                    float *stage = s_ring + (size_t)(tile % kHotStages) * kHotTileRows * 32;
+#pragma unroll
+                    for (int j = 0; j < RPW; j++) {
+                        const u32 src = __shfl_sync(FULL, pv, j);
+                        if (src != 0xffffffffu && active)
+                            cp_async_f32(stage + (warp * RPW + j) * 32 + lane,
+                                         vals + (size_t)src * D + col);
+                    }
+                    cp_async_commit();
+                };
+#pragma unroll 1
+                for (u32 k = 0; k < kHotStages - 1; k++)
+                    issue(k, load_perm(k));
+                u32 pnext = load_perm(kHotStages - 1);
+                for (u32 k = 0; k < ntiles; k++) {
+                    cp_async_wait<kHotStages - 2>(); // this thread's part of stage k has landed
+                    __syncthreads(); // ... everyone's has; and stage k-1 has been consumed
+                    issue(k + kHotStages - 1, pnext);
+                    pnext = load_perm(k + kHotStages);
+                    if (warp == 0 && active) {
+                        const float *stage = s_ring + (size_t)(k % kHotStages) * kHotTileRows * 32 + lane;
+                        const u32 rows = min((u32)kHotTileRows, cnt - k * kHotTileRows);
+                        u32 r = 0;
+                        for (; r + 16 <= rows; r += 16) {
+                            float g[16];
+#pragma unroll
+                            for (int j = 0; j < 16; j++)
+                                g[j] = stage[(r + j) * 32];
+#pragma unroll
+                            for (int j = 0; j < 16; j++)
+                                acc = f1.step(acc, g[j]);
+                        }
+                        for (; r < rows; r++)
+                            acc = f1.step(acc, stage[r * 32]);
+                    }
+                }
+                cp_async_wait<0>();
+                if (warp == 0 && active)
+                    f1.store(ctx, col, acc);
+            }
+            // the CTA that completes the row's last chunk applies the per-row scalars
+            if (warp == 0) {
+                u32 prev = 0;
+                __syncwarp();
+                if (lane == 0) {
+                    __threadfence();
+                    prev = atomicAdd(done, 1u);
+                }
+                prev = __shfl_sync(FULL, prev, 0);
+                if (prev == Q - 1 && ok) {
+                    __threadfence();
+                    f1.end(ctx);
+                }
+            }
+        }
     }
-    f.kernel_end();
+
+    // ------------------------------- cold phase ------------------------------------------
+    // Ticket t covers the uniques t, t + T, t + 2T, ... (T tickets): ids that are hot tend to be
+    // neighbours in key order, a strided ticket spreads their longer segments over many warps.
+    const size_t nvec = D / VEC;
+    const u32 T = (U + 31) / 32;
+    while (true) {
+        u32 t = 0;
+        if (lane == 0)
+            t = atomicAdd(&hl.ctrl[3], 1u);
+        t = __shfl_sync(FULL, t, 0);
+        if (t >= T)
+            break;
+        // lane-parallel metadata of the 32 uniques of this ticket
+        const u32 my_u = t + lane * T;
+        const bool mine = my_u < U;
+        const u32 my_s0 = mine ? seg_start[my_u] : 0;
+        const u32 my_cnt = mine ? seg_start[my_u + 1] - my_s0 : 0;
+        const bool my_cold = my_cnt > 0 && my_cnt <= hot_threshold;
+        const u32 my_p0 = my_cold ? perm[my_s0] : 0;
+        const int nrows = __popc(__ballot_sync(FULL, mine)); // valid lanes are 0 .. nrows-1
+#pragma unroll 1
+        for (int g0 = 0; g0 < nrows; g0 += ROWS) {
+            typename FV::Ctx ctx[ROWS];
+            u32 s0[ROWS], cnt[ROWS], p0[ROWS];
+            bool ok[ROWS];
+#pragma unroll
+            for (int r = 0; r < ROWS; r++) {
+                const int from = (g0 + r) & 31;
+                s0[r] = __shfl_sync(FULL, my_s0, from);
+                cnt[r] = __shfl_sync(FULL, my_cnt, from);
+                p0[r] = __shfl_sync(FULL, my_p0, from);
+                ok[r] = g0 + r < nrows && __shfl_sync(FULL, my_cold, from);
+            }
+#pragma unroll
+            for (int r = 0; r < ROWS; r++)
+                if (ok[r])
+                    ok[r] = fv.begin(t + (size_t)(g0 + r) * T, cnt[r], ctx[r]);
+            // warp-uniform column loop (lanes beyond the row width idle): the shuffles below
+            // need every lane
+            for (size_t c0 = 0; c0 < nvec; c0 += 32) {
+                const size_t c = c0 + lane;
+                const bool cv = c < nvec;
+                decltype(fv.load(ctx[0], 0)) acc[ROWS];
+                typename V::T g[ROWS];
+#pragma unroll
+                for (int r = 0; r < ROWS; r++)
+                    if (ok[r] && cv) {
+                        acc[r] = fv.load(ctx[r], c);
+                        g[r] = V::ld_nc(vals + (size_t)p0[r] * D + c * VEC);
+                    }
+#pragma unroll
+                for (int r = 0; r < ROWS; r++)
+                    if (ok[r] && cv)
+                        acc[r] = fv.step(acc[r], g[r]);
+                // further occurrences (few rows have any): 32 at a time, their source rows
+                // fetched lane-parallel, four gradient rows in flight
+#pragma unroll
+                for (int r = 0; r < ROWS; r++) {
+                    if (!ok[r] || cnt[r] < 2)
+                        continue;
+                    for (u32 b = 1; b < cnt[r]; b += 32) {
+                        const u32 nb = min(32u, cnt[r] - b);
+                        const u32 pl = lane < nb ? perm[s0[r] + b + lane] : 0;
+                        for (u32 j = 0; j < nb; j += 4) {
+                            typename V::T gg[4];
+#pragma unroll
+                            for (int k = 0; k < 4; k++) {
+                                const u32 pi = __shfl_sync(FULL, pl, (j + k) & 31);
+                                if (j + k < nb && cv)
+                                    gg[k] = V::ld_nc(vals + (size_t)pi * D + c * VEC);
+                            }
+#pragma unroll
+                            for (int k = 0; k < 4; k++)
+                                if (j + k < nb && cv)
+                                    acc[r] = fv.step(acc[r], gg[k]);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int r = 0; r < ROWS; r++)
+                    if (ok[r] && cv)
+                        fv.store(ctx[r], c, acc[r]);
+            }
+#pragma unroll
+            for (int r = 0; r < ROWS; r++)
+                if (ok[r])
+                    fv.end(ctx[r]);
+        }
+    }
+    fv.kernel_end();
 }
 
 // ---- one warp per listed row: f.begin(r); f.apply(r, c) per column chunk; f.end(r) -------------

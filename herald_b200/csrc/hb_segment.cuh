@@ -17,13 +17,43 @@ u32 default_hot_threshold();
 
 // f1 / f4: the same functor instantiated for VEC = 1 and VEC = 4; v4 selects the 128-bit cold
 // path.  `n` = number of values (upper bound of any segment length).
+template <class K>
+int persistent_grid(K kernel, size_t smem) {
+    int per_sm = 0;
+    HB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    HB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kRowBlock, smem));
+    return sm_count() * std::max(per_sm, 1);
+}
+
+// segments a warp keeps in flight in the cold phase (2 or 4; $HERALD_SEG_ROWS for tuning)
+inline int seg_rows() {
+    static const int rows = [] {
+        const char *e = getenv("HERALD_SEG_ROWS");
+        int r = e ? atoi(e) : 4;
+        return r == 2 ? 2 : 4;
+    }();
+    return rows;
+}
+
+template <int VEC, int ROWS, class FV, class F1>
+void launch_segment_reduce(KeyWorkspace &ws, const u32 *perm, const float *vals, size_t D, size_t n,
+                           bool hot, u32 thr, const HotLists &hl, cudaStream_t st, FV fv, F1 f1) {
+    auto k = segment_reduce_kernel<VEC, ROWS, FV, F1>;
+    static const int full = persistent_grid(k, kHotSmemBytes);
+    const size_t chunks = (n + 31) / 32; // upper bound of the cold tickets
+    int grid = (int)std::max<size_t>(1, std::min<size_t>(full, (chunks + kRowWarps - 1) / kRowWarps));
+    k<<<hot ? full : grid, kRowBlock, kHotSmemBytes, st>>>(ws.seg_start, perm, ws.num_unique, vals, D,
+                                                           thr, hl, fv, f1);
+    HB_LAUNCHED();
+}
+
 template <class F1, class F4>
 void run_segment_reduce(KeyWorkspace &ws, const u32 *perm, const float *vals, size_t D, size_t n,
                         bool v4, u32 hot_threshold, cudaStream_t st, F1 f1, F4 f4) {
     if (n == 0)
         return;
     const bool hot = n > hot_threshold;
-    HotLists hl{ws.hot_a, ws.hot_b, ws.hot_ctrl()};
+    HotLists hl{ws.hot_a, ws.hot_b, ws.hot_done_a, ws.hot_done_b, ws.hot_ctrl()};
     if (hot) {
         int g = (int)std::min<size_t>((n + 255) / 256, (size_t)sm_count() * 4);
         build_hot_lists_kernel<<<std::max(g, 1), 256, 0, st>>>(ws.seg_start, ws.num_unique,
@@ -31,21 +61,15 @@ void run_segment_reduce(KeyWorkspace &ws, const u32 *perm, const float *vals, si
         HB_LAUNCHED();
     }
     const u32 thr = hot ? hot_threshold : 0xffffffffu;
-    int grid = row_grid(n);
-    if (v4)
-        segment_rows_kernel<4, F4><<<grid, kRowBlock, 0, st>>>(ws.seg_start, perm, ws.num_unique,
-                                                               vals, D, thr, f4);
+    const bool r4 = seg_rows() == 4;
+    if (v4 && r4)
+        launch_segment_reduce<4, 4>(ws, perm, vals, D, n, hot, thr, hl, st, f4, f1);
+    else if (v4)
+        launch_segment_reduce<4, 2>(ws, perm, vals, D, n, hot, thr, hl, st, f4, f1);
+    else if (r4)
+        launch_segment_reduce<1, 4>(ws, perm, vals, D, n, hot, thr, hl, st, f1, f1);
     else
-        segment_rows_kernel<1, F1><<<grid, kRowBlock, 0, st>>>(ws.seg_start, perm, ws.num_unique,
-                                                               vals, D, thr, f1);
-    HB_LAUNCHED();
-    if (hot) {
-        segment_hot_kernel<F1><<<sm_count() * 4, kRowBlock, 0, st>>>(ws.seg_start, perm, vals, D, hl,
-                                                                     f1);
-        HB_LAUNCHED();
-        segment_hot_finish_kernel<F1><<<32, kRowBlock, 0, st>>>(ws.seg_start, hl, f1);
-        HB_LAUNCHED();
-    }
+        launch_segment_reduce<1, 2>(ws, perm, vals, D, n, hot, thr, hl, st, f1, f1);
 }
 
 } // namespace hb

@@ -1,11 +1,12 @@
 // Stable LSD radix sort + sorted-unique (see hb_sort.cuh for what it replaces).
 //
 // Sort: 9-bit digits (3 passes for ids < 2^27, i.e. the 33.7M-row Criteo table and the 1e8-row
-// sweep).  Per pass: tile histogram -> one-block scan of the [digit][tile] matrix -> stable
-// scatter.  Ranking inside a tile is warp-cooperative: __match_any_sync groups the lanes of a
+// sweep).  One kernel counts the digits of every pass; then one kernel per pass ranks a tile,
+// finds its digit offsets by chained look-back over the earlier tiles and scatters (stable:
+// "onesweep").  Ranking inside a tile is warp-cooperative: __match_any_sync groups the lanes of a
 // warp that hold the same digit, the lowest lane of each group bumps the warp's digit counter in
 // shared memory, so there are no shared-memory atomics and hot (Zipf) keys do not serialise.
-// HBM traffic per pass: 2 reads + 1 write of 12 B/key; at N = 212,992 everything is L2-resident.
+// HBM traffic per pass: 1 read + 1 write of 12 B/key; at N = 212,992 everything is L2-resident.
 #include <algorithm>
 
 #include "hb_sort.cuh"
@@ -14,8 +15,8 @@ namespace hb {
 
 namespace {
 
-constexpr int RB = 9;
-constexpr int RADIX = 1 << RB;
+constexpr int RB = kSortRadixBits;
+constexpr int RADIX = kSortRadix;
 constexpr int SORT_THREADS = 256;
 constexpr int SORT_WARPS = SORT_THREADS / 32;
 constexpr int SORT_ITEMS = 8;
@@ -63,33 +64,72 @@ __device__ __forceinline__ void rank_tile(const void *kin, size_t n, int shift, 
     __syncthreads();
 }
 
+// Digit histograms of EVERY pass in one read of the keys (the totals do not depend on the order
+// the keys are in).  totals[p][d] must be zero on entry (they live in the scan arena).
 template <int KIND>
 __global__ void __launch_bounds__(SORT_THREADS)
-    sort_hist_kernel(const void *kin, size_t n, int shift, u32 *blk_hist, int nblk) {
+    sort_hist_all_kernel(const void *kin, size_t n, int passes, u32 *totals) {
+    __shared__ u32 sh[kMaxSortPasses * RADIX];
+    for (int b = threadIdx.x; b < passes * RADIX; b += SORT_THREADS)
+        sh[b] = 0;
+    __syncthreads();
+    const size_t stride = (size_t)gridDim.x * SORT_THREADS;
+    for (size_t e = (size_t)blockIdx.x * SORT_THREADS + threadIdx.x; e < n; e += stride) {
+        const u64 key = load_key<KIND>(kin, e);
+        for (int p = 0; p < passes; p++)
+            atomicAdd(&sh[p * RADIX + ((u32)(key >> (p * RB)) & (RADIX - 1))], 1u);
+    }
+    __syncthreads();
+    for (int b = threadIdx.x; b < passes * RADIX; b += SORT_THREADS)
+        if (sh[b])
+            atomicAdd(&totals[b], sh[b]);
+}
+
+// status word of one (tile, digit): epoch << 34 | flag << 32 | count.  flag 1 = the tile's own
+// count, 2 = inclusive prefix over tiles 0..tile.  A word whose epoch is not the running pass's
+// counts as "not written yet", so the status array is never cleared.
+__device__ __forceinline__ u64 pack_status(u32 epoch, u32 flag, u32 value) {
+    return ((u64)epoch << 34) | ((u64)flag << 32) | value;
+}
+
+// One pass of the stable LSD radix sort in a single kernel: rank inside the tile, chained
+// look-back over the earlier tiles per digit, scatter.  Tiles are numbered by an atomic ticket,
+// so a tile only ever waits for tiles that are already running.
+template <int KIND, bool FIRST>
+__global__ void __launch_bounds__(SORT_THREADS)
+    sort_pass_kernel(const void *kin, const u32 *vin, u64 *kout, u32 *vout, size_t n, int shift,
+                     const u32 *__restrict__ totals, u64 *status, u32 *ticket, u32 epoch) {
     __shared__ u32 s_cnt[SORT_WARPS][RADIX];
+    __shared__ u32 s_off[RADIX];
+    __shared__ u32 s_wsum[SORT_WARPS];
     u64 key[SORT_ITEMS];
     u32 rank[SORT_ITEMS];
     bool valid[SORT_ITEMS];
-    rank_tile<KIND>(kin, n, shift, (size_t)blockIdx.x * SORT_TILE, s_cnt, key, rank, valid);
-    for (int b = threadIdx.x; b < RADIX; b += SORT_THREADS) {
-        u32 sum = 0;
-#pragma unroll
-        for (int w = 0; w < SORT_WARPS; w++)
-            sum += s_cnt[w][b];
-        blk_hist[(size_t)b * nblk + blockIdx.x] = sum;
-    }
-}
-
-// In-place exclusive scan of `total` counters by one block.
-__global__ void __launch_bounds__(1024) sort_scan_kernel(u32 *data, size_t total) {
-    __shared__ u32 s_warp[32];
+    const u32 tile = take_ticket(ticket);
+    const size_t tile_base = (size_t)tile * SORT_TILE;
+    rank_tile<KIND>(kin, n, shift, tile_base, s_cnt, key, rank, valid);
     const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
-    size_t chunk = (total + 1023) / 1024;
-    size_t lo = (size_t)threadIdx.x * chunk, hi = min(lo + chunk, total);
-    u32 sum = 0;
-    for (size_t i = lo; i < hi; i++)
-        sum += data[i];
-    u32 incl = sum;
+    constexpr int DPT = RADIX / SORT_THREADS; // consecutive digits per thread
+    u32 cnt[DPT], tot[DPT];
+    u32 tsum = 0;
+#pragma unroll
+    for (int k = 0; k < DPT; k++) {
+        const int b = threadIdx.x * DPT + k;
+        u32 run = 0;
+#pragma unroll
+        for (int w = 0; w < SORT_WARPS; w++) { // exclusive prefix over the tile's warps
+            u32 t = s_cnt[w][b];
+            s_cnt[w][b] = run;
+            run += t;
+        }
+        cnt[k] = run;
+        *reinterpret_cast<volatile u64 *>(&status[(size_t)tile * RADIX + b]) =
+            pack_status(epoch, tile == 0 ? 2u : 1u, run);
+        tot[k] = totals[b];
+        tsum += tot[k];
+    }
+    // exclusive scan of the digit totals over the block -> first output position of each digit
+    u32 incl = tsum;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
         u32 t = __shfl_up_sync(FULL, incl, d);
@@ -97,56 +137,42 @@ __global__ void __launch_bounds__(1024) sort_scan_kernel(u32 *data, size_t total
             incl += t;
     }
     if (lane == 31)
-        s_warp[warp] = incl;
+        s_wsum[warp] = incl;
     __syncthreads();
-    if (warp == 0) {
-        u32 w = s_warp[lane], wi = w;
+    u32 base = incl - tsum;
+    for (unsigned w = 0; w < warp; w++)
+        base += s_wsum[w];
+    // look back over the earlier tiles
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            u32 t = __shfl_up_sync(FULL, wi, d);
-            if (lane >= (unsigned)d)
-                wi += t;
+    for (int k = 0; k < DPT; k++) {
+        const int b = threadIdx.x * DPT + k;
+        u32 excl = 0;
+        if (tile > 0) {
+            int look = (int)tile - 1;
+            while (true) {
+                u64 s;
+                do {
+                    s = *reinterpret_cast<volatile u64 *>(&status[(size_t)look * RADIX + b]);
+                } while ((u32)(s >> 34) != epoch || ((s >> 32) & 3u) == 0);
+                excl += (u32)s;
+                if (((s >> 32) & 3u) == 2u)
+                    break;
+                look--;
+            }
+            *reinterpret_cast<volatile u64 *>(&status[(size_t)tile * RADIX + b]) =
+                pack_status(epoch, 2u, excl + cnt[k]);
         }
-        s_warp[lane] = wi - w;
+        s_off[b] = base + excl;
+        base += tot[k];
     }
     __syncthreads();
-    u32 run = s_warp[warp] + incl - sum;
-    for (size_t i = lo; i < hi; i++) {
-        u32 v = data[i];
-        data[i] = run;
-        run += v;
-    }
-}
-
-template <int KIND, bool FIRST>
-__global__ void __launch_bounds__(SORT_THREADS)
-    sort_scatter_kernel(const void *kin, const u32 *vin, u64 *kout, u32 *vout, size_t n, int shift,
-                        const u32 *offsets, int nblk) {
-    __shared__ u32 s_cnt[SORT_WARPS][RADIX];
-    u64 key[SORT_ITEMS];
-    u32 rank[SORT_ITEMS];
-    bool valid[SORT_ITEMS];
-    const size_t tile_base = (size_t)blockIdx.x * SORT_TILE;
-    rank_tile<KIND>(kin, n, shift, tile_base, s_cnt, key, rank, valid);
-    // per digit: global offset of this tile, then exclusive prefix over the tile's warps
-    for (int b = threadIdx.x; b < RADIX; b += SORT_THREADS) {
-        u32 run = offsets[(size_t)b * nblk + blockIdx.x];
-#pragma unroll
-        for (int w = 0; w < SORT_WARPS; w++) {
-            u32 t = s_cnt[w][b];
-            s_cnt[w][b] = run;
-            run += t;
-        }
-    }
-    __syncthreads();
-    const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
     const size_t warp_base = tile_base + (size_t)warp * (SORT_ITEMS * 32);
 #pragma unroll
     for (int r = 0; r < SORT_ITEMS; r++) {
         if (valid[r]) {
             size_t e = warp_base + r * 32 + lane;
             u32 d = (u32)(key[r] >> shift) & (RADIX - 1);
-            u32 pos = s_cnt[warp][d] + rank[r];
+            u32 pos = s_off[d] + s_cnt[warp][d] + rank[r];
             kout[pos] = key[r];
             vout[pos] = FIRST ? (u32)e : vin[e];
         }
@@ -237,7 +263,8 @@ void KeyWorkspace::reserve(size_t n) {
         dev_alloc(vals[i], c);
     }
     nblk_cap = (c + SORT_TILE - 1) / SORT_TILE;
-    dev_alloc(blk_hist, (size_t)RADIX * nblk_cap);
+    dev_alloc(sort_status, (size_t)RADIX * nblk_cap);
+    HB_CUDA(cudaMemset(sort_status, 0, (size_t)RADIX * nblk_cap * sizeof(u64)));
     dev_alloc(uniq, c);
     dev_alloc(inverse, c);
     dev_alloc(seg_start, c + 1);
@@ -247,6 +274,8 @@ void KeyWorkspace::reserve(size_t n) {
     HB_CUDA(cudaMemset(scan_arena, 0, arena_words() * sizeof(u64)));
     dev_alloc(hot_a, c);
     dev_alloc(hot_b, c);
+    dev_alloc(hot_done_a, c);
+    dev_alloc(hot_done_b, c);
     cap = c;
 }
 
@@ -255,7 +284,7 @@ void KeyWorkspace::release() {
         dev_free(keys[i]);
         dev_free(vals[i]);
     }
-    dev_free(blk_hist);
+    dev_free(sort_status);
     dev_free(uniq);
     dev_free(inverse);
     dev_free(seg_start);
@@ -263,6 +292,8 @@ void KeyWorkspace::release() {
     dev_free(scan_arena);
     dev_free(hot_a);
     dev_free(hot_b);
+    dev_free(hot_done_a);
+    dev_free(hot_done_b);
     cap = 0;
 }
 
@@ -285,8 +316,15 @@ SortedKeys radix_sort_keys(KeyWorkspace &ws, const void *keys_in, int key_kind, 
                            int key_bits, cudaStream_t st) {
     HB_CHECK(n <= ws.cap, "sort workspace too small");
     HB_CHECK(n < (1ull << 32), "too many keys");
-    int passes = std::max(1, (key_bits + RB - 1) / RB);
+    int passes = std::min(kMaxSortPasses, std::max(1, (key_bits + RB - 1) / RB));
     int nblk = ceil_div(n, SORT_TILE);
+    u32 *totals = ws.sort_totals();
+    int hgrid = std::min(nblk, sm_count() * 4);
+    if (key_kind == HB_KEYS_F32)
+        sort_hist_all_kernel<HB_KEYS_F32><<<hgrid, SORT_THREADS, 0, st>>>(keys_in, n, passes, totals);
+    else
+        sort_hist_all_kernel<HB_KEYS_U64><<<hgrid, SORT_THREADS, 0, st>>>(keys_in, n, passes, totals);
+    HB_LAUNCHED();
     const void *kin = keys_in;
     const u32 *vin = nullptr;
     int out = 0;
@@ -294,24 +332,18 @@ SortedKeys radix_sort_keys(KeyWorkspace &ws, const void *keys_in, int key_kind, 
         int shift = p * RB;
         bool first = p == 0;
         bool f32 = first && key_kind == HB_KEYS_F32;
+        u32 epoch = ws.next_sort_epoch();
+        const u32 *tp = totals + (size_t)p * RADIX;
+        u32 *ticket = ws.sort_tickets() + p;
         if (f32)
-            sort_hist_kernel<HB_KEYS_F32><<<nblk, SORT_THREADS, 0, st>>>(kin, n, shift,
-                                                                         ws.blk_hist, nblk);
-        else
-            sort_hist_kernel<HB_KEYS_U64><<<nblk, SORT_THREADS, 0, st>>>(kin, n, shift,
-                                                                         ws.blk_hist, nblk);
-        HB_LAUNCHED();
-        sort_scan_kernel<<<1, 1024, 0, st>>>(ws.blk_hist, (size_t)RADIX * nblk);
-        HB_LAUNCHED();
-        if (f32)
-            sort_scatter_kernel<HB_KEYS_F32, true><<<nblk, SORT_THREADS, 0, st>>>(
-                kin, vin, ws.keys[out], ws.vals[out], n, shift, ws.blk_hist, nblk);
+            sort_pass_kernel<HB_KEYS_F32, true><<<nblk, SORT_THREADS, 0, st>>>(
+                kin, vin, ws.keys[out], ws.vals[out], n, shift, tp, ws.sort_status, ticket, epoch);
         else if (first)
-            sort_scatter_kernel<HB_KEYS_U64, true><<<nblk, SORT_THREADS, 0, st>>>(
-                kin, vin, ws.keys[out], ws.vals[out], n, shift, ws.blk_hist, nblk);
+            sort_pass_kernel<HB_KEYS_U64, true><<<nblk, SORT_THREADS, 0, st>>>(
+                kin, vin, ws.keys[out], ws.vals[out], n, shift, tp, ws.sort_status, ticket, epoch);
         else
-            sort_scatter_kernel<HB_KEYS_U64, false><<<nblk, SORT_THREADS, 0, st>>>(
-                kin, vin, ws.keys[out], ws.vals[out], n, shift, ws.blk_hist, nblk);
+            sort_pass_kernel<HB_KEYS_U64, false><<<nblk, SORT_THREADS, 0, st>>>(
+                kin, vin, ws.keys[out], ws.vals[out], n, shift, tp, ws.sort_status, ticket, epoch);
         HB_LAUNCHED();
         kin = ws.keys[out];
         vin = ws.vals[out];

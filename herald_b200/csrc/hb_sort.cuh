@@ -14,14 +14,18 @@ namespace hb {
 
 constexpr int kScanSlots = 12;  // independent grid-scan states per workspace
 constexpr int kScanBlock = 256; // threads per scan tile
+constexpr int kSortRadixBits = 9;
+constexpr int kSortRadix = 1 << kSortRadixBits;
+constexpr int kMaxSortPasses = 8; // 64-bit keys / 9 bits, rounded up
 
 // Per-call scratch, sized for `cap` keys.  All device memory.
 struct KeyWorkspace {
     size_t cap = 0;
     u64 *keys[2] = {nullptr, nullptr}; // ping-pong sort buffers (keys)
     u32 *vals[2] = {nullptr, nullptr}; // ping-pong sort buffers (original index)
-    u32 *blk_hist = nullptr;           // [RADIX][nblk] digit counts / offsets
+    u64 *sort_status = nullptr;        // [nblk][RADIX] look-back status words (epoch-tagged)
     size_t nblk_cap = 0;
+    u32 sort_epoch = 0;                // one epoch per sort pass ever run on this workspace
     // results of unique_from_sorted
     u64 *uniq = nullptr;      // [cap]   ascending unique keys
     u32 *inverse = nullptr;   // [cap]   rank of keys[i] in uniq
@@ -30,7 +34,9 @@ struct KeyWorkspace {
     // hot-segment work lists (see hb_rows.cuh); the control words live behind the scan arena so
     // that reset_scans() zeroes them with the same memset
     u32 *hot_a = nullptr, *hot_b = nullptr; // [cap]
-    // scan arena: kScanSlots x (ticket + status[ntile_cap]), then 2 control words
+    u32 *hot_done_a = nullptr, *hot_done_b = nullptr; // [cap] finished chunks per hot row
+    // scan arena: kScanSlots x (ticket + status[ntile_cap]), then 2 control words (hot lists),
+    // then the sort's digit totals [kMaxSortPasses][RADIX] and its per-pass tile tickets
     u64 *scan_arena = nullptr;
     size_t ntile_cap = 0;
     int scan_next = 0;
@@ -41,10 +47,23 @@ struct KeyWorkspace {
         return ntile_cap + 1;
     }
     size_t arena_words() const {
-        return (size_t)kScanSlots * scan_slot_words() + 2;
+        return (size_t)kScanSlots * scan_slot_words() + 2 + (kMaxSortPasses * kSortRadix) / 2 +
+               kMaxSortPasses / 2;
     }
-    u32 *hot_ctrl() const {
+    u32 *hot_ctrl() const { // 4 x u32
         return reinterpret_cast<u32 *>(scan_arena + (size_t)kScanSlots * scan_slot_words());
+    }
+    u32 *sort_totals() const {
+        return hot_ctrl() + 4;
+    }
+    u32 *sort_tickets() const {
+        return sort_totals() + kMaxSortPasses * kSortRadix;
+    }
+    u32 next_sort_epoch() {
+        sort_epoch = (sort_epoch + 1) & 0x3fffffffu;
+        if (sort_epoch == 0)
+            sort_epoch = 1;
+        return sort_epoch;
     }
     // zero every scan slot (one memset) — call once at the start of an op
     void reset_scans(cudaStream_t st);
