@@ -733,10 +733,12 @@ struct AccumulatePush {
     struct Acc {
         typename V::T d, g, t; // cache row, pending gradient, owner row (read ahead for the push)
     };
-    struct Ctx {
-        i32 s;
+    struct Ctx { // everything end() needs is read by begin(): end() only stores
         u64 trow;
+        i64 version, tver;
+        i32 s;
         i32 upd0, upd;
+        u8 flags;
         bool dataless, pushed, local;
     };
     CacheView c;
@@ -782,12 +784,15 @@ struct AccumulatePush {
         x.trow = key - c.row_begin;
         x.local = x.trow < c.nrows_local;
         x.upd0 = c.slot_updates[x.s];
+        x.flags = c.slot_flags[x.s];
+        x.version = c.slot_version[x.s];
         x.upd = x.upd0 + (i32)cnt;
-        x.dataless = c.slot_flags[x.s] & F_DATALESS;
+        x.dataless = x.flags & F_DATALESS;
         if (push_keys)
             x.pushed = !x.dataless && in_plan(key); // cache.cc:296
         else
             x.pushed = (i64)x.upd > push_bound || x.dataless; // cache.cc:157
+        x.tver = (x.pushed && x.local) ? c.tver[x.trow] : 0;
         return true;
     }
     __device__ Acc load(const Ctx &x, size_t k) const {
@@ -814,13 +819,12 @@ struct AccumulatePush {
         if (!x.pushed || (defer_cleanup && !x.dataless))
             V::st(c.grad + o, a.g);
     }
-    __device__ void end(const Ctx &x) const {
-        if (lane_id() != 0)
-            return;
-        c.slot_flags[x.s] |= F_GRAD;
+    __device__ void end(const Ctx &x) const { // one thread per row
+        if (!(x.flags & F_GRAD))
+            c.slot_flags[x.s] = x.flags | F_GRAD;
         if (x.pushed) {
             if (x.local)
-                c.tver[x.trow] += x.upd; // PSFhandle_embedding.cc:24
+                c.tver[x.trow] = x.tver + x.upd; // PSFhandle_embedding.cc:24
             atomicAdd(block_counter(), 1u);
         }
         if (defer_cleanup) {
@@ -828,10 +832,10 @@ struct AccumulatePush {
             return;
         }
         if (push_keys) { // cache.cc:308-314: every touched line, every call
-            c.slot_version[x.s] += x.upd;
+            c.slot_version[x.s] = x.version + x.upd;
             c.slot_updates[x.s] = x.pushed ? 0 : x.upd;
         } else if (x.pushed && !x.dataless) { // cache.cc:171-177
-            c.slot_version[x.s] += x.upd;
+            c.slot_version[x.s] = x.version + x.upd;
             c.slot_updates[x.s] = 0;
         } else {
             c.slot_updates[x.s] = x.upd;
@@ -1203,10 +1207,13 @@ void resolve_batch(hb_cache *c, const void *dev_keys, int kind, size_t n, int ba
     cudaStream_t st = c->stream;
     ws.reset_scans(st);
     SortedKeys sk{nullptr, nullptr};
+    const u32 *same = check_same_keys(ws, dev_keys, kind, n, st);
     if (n)
-        sk = radix_sort_keys(ws, dev_keys, kind, n, c->key_bits, st);
+        sk = radix_sort_keys(ws, dev_keys, kind, n, c->key_bits, st, same);
     c->sorted[batch] = sk;
-    unique_from_sorted(ws, sk, n, st);
+    unique_from_sorted(ws, sk, n, st, same);
+    ws.sorted_valid = n > 0;
+    ws.sorted_n = n;
     if (marks)
         mark(c, 0);
     u32 ntiles = (u32)std::max(1, ceil_div(n, kScanBlock));
@@ -1937,6 +1944,7 @@ int hb_cache_touch(hb_cache *c, uint64_t key, int *found, int64_t *version, floa
     // a batched lookup of one key without the insert/sync half: CacheBase::lookup via python
     begin_call(c);
     ws.reset_scans(st);
+    ws.sorted_valid = false;
     single_key_kernel<<<1, 1, 0, st>>>(ws.uniq, ws.num_unique, key);
     HB_LAUNCHED();
     u64 *clk = clk_of(c);
@@ -1984,6 +1992,7 @@ int hb_cache_insert(hb_cache *c, uint64_t key, int64_t version, const float *dat
         KeyWorkspace &ws = c->ws[0];
         begin_call(c);
         ws.reset_scans(st);
+        ws.sorted_valid = false;
         single_key_kernel<<<1, 1, 0, st>>>(ws.uniq, ws.num_unique, key);
         HB_LAUNCHED();
         u64 *clk = clk_of(c);

@@ -119,7 +119,9 @@ __global__ void __launch_bounds__(kRowBlock)
 //                        for each occurrence p in ascending original index:
 //                            acc = f.step(acc, vals[perm[p], c]);
 //                        f.store(ctx, c, acc);
-//   f.end(ctx)   (all lanes of one warp; per-row scalars are written by lane 0 inside)
+//   f.end(ctx)   (ONE thread per row: writes the per-row scalars from values begin() read)
+// begin() and end() contain no warp-collective operation: the cold phase calls them with a
+// different row in every lane.
 // The adds happen in occurrence order, so the result is deterministic and bit-identical to a
 // serial CPU loop over the batch (Line::accumulate order, src/hetu_cache/include/embedding.h:78-91).
 //
@@ -139,6 +141,22 @@ constexpr int kHotTileRows = 128; // occurrences per pipeline stage
 constexpr int kHotStages = 4;     // 4 x 128 x 128 B = 64 KB of dynamic shared memory
 constexpr int kHotSmemBytes = kHotStages * kHotTileRows * 32 * 4;
 constexpr u32 kVeryHot = 1024; // rows above this go first (longest-processing-time-first)
+
+// broadcast a trivially copyable struct from lane `src` (32 bits at a time)
+template <class T>
+__device__ __forceinline__ T shfl_pod(const T &v, int src) {
+    static_assert(sizeof(T) % 4 == 0, "pad the context to a multiple of 4 bytes");
+    union U {
+        T t;
+        u32 w[sizeof(T) / 4];
+        __device__ U() {}
+    } in, out;
+    in.t = v;
+#pragma unroll
+    for (size_t i = 0; i < sizeof(T) / 4; i++)
+        out.w[i] = __shfl_sync(FULL, in.w[i], src);
+    return out.t;
+}
 
 struct HotLists {
     u32 *very_hot; // [cap] unique indices with count > kVeryHot
@@ -191,6 +209,10 @@ __device__ __forceinline__ void cp_async_f32(float *smem_dst, const float *gsrc)
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc) : "memory");
 }
+__device__ __forceinline__ void cp_async_16(float *smem_dst, const float *gsrc) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() {
     asm volatile("cp.async.commit_group;" ::: "memory");
 }
@@ -209,6 +231,7 @@ __global__ void __launch_bounds__(kRowBlock, 2)
     extern __shared__ __align__(16) float s_ring[]; // [kHotStages][kHotTileRows][32]
     __shared__ u32 s_item;
     using V = RowVec<VEC>;
+    constexpr bool WIDE = VEC == 4; // rows are 16 B aligned and D % 4 == 0
     const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
     const u32 U = *num_unique;
     fv.kernel_begin();
@@ -241,31 +264,49 @@ __global__ void __launch_bounds__(kRowBlock, 2)
                 if (warp == 0 && active)
                     acc = f1.load(ctx, col);
                 const u32 ntiles = (cnt + kHotTileRows - 1) / kHotTileRows;
-                // lane j < RPW holds the source row of occurrence (tile, warp * RPW + j)
-                auto load_perm = [&](u32 tile) -> u32 {
-                    const u32 p = s0 + tile * kHotTileRows + warp * RPW + (lane & (RPW - 1));
-                    return (tile < ntiles && p < s1) ? perm[p] : 0xffffffffu;
+                // Stage layout [kHotTileRows][32 floats].  WIDE (rows 16 B aligned): a thread
+                // copies 16 B, eight threads cover one occurrence, a warp instruction four of them
+                // (LDGSTS costs ~8 cycles per warp instruction whatever its width, so 16 B
+                // copies are what keeps the ring ahead of the adder); otherwise 4 B per thread,
+                // one occurrence per warp instruction.
+                constexpr int CPT = WIDE ? kHotTileRows / 32 : RPW; // copies per thread per stage
+                const u32 my_row = WIDE ? (threadIdx.x >> 3) : warp * RPW; // first row it copies
+                const u32 my_off = WIDE ? (threadIdx.x & 7) * 4 : lane;    // float offset in row
+                const bool cp_active = (size_t)q * 32 + my_off < D;
+                const float *my_src = vals + (size_t)q * 32 + my_off;
+                u32 pv[CPT];
+                auto load_perm = [&](u32 tile) {
+#pragma unroll
+                    for (int j = 0; j < CPT; j++) {
+                        const u32 p = s0 + tile * kHotTileRows + my_row + (WIDE ? 32 * j : j);
+                        pv[j] = (tile < ntiles && p < s1) ? perm[p] : 0xffffffffu;
+                    }
                 };
-                auto issue = [&](u32 tile, u32 pv) {
+                auto issue = [&](u32 tile) {
                     float *stage = s_ring + (size_t)(tile % kHotStages) * kHotTileRows * 32;
 #pragma unroll
-                    for (int j = 0; j < RPW; j++) {
-                        const u32 src = __shfl_sync(FULL, pv, j);
-                        if (src != 0xffffffffu && active)
-                            cp_async_f32(stage + (warp * RPW + j) * 32 + lane,
-                                         vals + (size_t)src * D + col);
+                    for (int j = 0; j < CPT; j++) {
+                        const u32 row = my_row + (WIDE ? 32 * j : j);
+                        if (pv[j] != 0xffffffffu && cp_active) {
+                            if (WIDE)
+                                cp_async_16(stage + row * 32 + my_off, my_src + (size_t)pv[j] * D);
+                            else
+                                cp_async_f32(stage + row * 32 + my_off, my_src + (size_t)pv[j] * D);
+                        }
                     }
                     cp_async_commit();
                 };
 #pragma unroll 1
-                for (u32 k = 0; k < kHotStages - 1; k++)
-                    issue(k, load_perm(k));
-                u32 pnext = load_perm(kHotStages - 1);
+                for (u32 k = 0; k < kHotStages - 1; k++) {
+                    load_perm(k);
+                    issue(k);
+                }
+                load_perm(kHotStages - 1);
                 for (u32 k = 0; k < ntiles; k++) {
                     cp_async_wait<kHotStages - 2>(); // this thread's part of stage k has landed
                     __syncthreads(); // ... everyone's has; and stage k-1 has been consumed
-                    issue(k + kHotStages - 1, pnext);
-                    pnext = load_perm(k + kHotStages);
+                    issue(k + kHotStages - 1);
+                    load_perm(k + kHotStages);
                     if (warp == 0 && active) {
                         const float *stage = s_ring + (size_t)(k % kHotStages) * kHotTileRows * 32 + lane;
                         const u32 rows = min((u32)kHotTileRows, cnt - k * kHotTileRows);
@@ -296,7 +337,7 @@ __global__ void __launch_bounds__(kRowBlock, 2)
                     prev = atomicAdd(done, 1u);
                 }
                 prev = __shfl_sync(FULL, prev, 0);
-                if (prev == Q - 1 && ok) {
+                if (prev == Q - 1 && ok && lane == 0) {
                     __threadfence();
                     f1.end(ctx);
                 }
@@ -324,6 +365,9 @@ __global__ void __launch_bounds__(kRowBlock, 2)
         const bool my_cold = my_cnt > 0 && my_cnt <= hot_threshold;
         const u32 my_p0 = my_cold ? perm[my_s0] : 0;
         const int nrows = __popc(__ballot_sync(FULL, mine)); // valid lanes are 0 .. nrows-1
+        // every lane opens its own row: the dependent scalar loads of 32 rows overlap
+        typename FV::Ctx my_ctx;
+        const bool my_ok = my_cold && fv.begin(my_u, my_cnt, my_ctx);
 #pragma unroll 1
         for (int g0 = 0; g0 < nrows; g0 += ROWS) {
             typename FV::Ctx ctx[ROWS];
@@ -335,12 +379,9 @@ __global__ void __launch_bounds__(kRowBlock, 2)
                 s0[r] = __shfl_sync(FULL, my_s0, from);
                 cnt[r] = __shfl_sync(FULL, my_cnt, from);
                 p0[r] = __shfl_sync(FULL, my_p0, from);
-                ok[r] = g0 + r < nrows && __shfl_sync(FULL, my_cold, from);
+                ok[r] = g0 + r < nrows && __shfl_sync(FULL, my_ok, from);
+                ctx[r] = shfl_pod(my_ctx, from);
             }
-#pragma unroll
-            for (int r = 0; r < ROWS; r++)
-                if (ok[r])
-                    ok[r] = fv.begin(t + (size_t)(g0 + r) * T, cnt[r], ctx[r]);
             // warp-uniform column loop (lanes beyond the row width idle): the shuffles below
             // need every lane
             for (size_t c0 = 0; c0 < nvec; c0 += 32) {
@@ -387,11 +428,9 @@ __global__ void __launch_bounds__(kRowBlock, 2)
                     if (ok[r] && cv)
                         fv.store(ctx[r], c, acc[r]);
             }
-#pragma unroll
-            for (int r = 0; r < ROWS; r++)
-                if (ok[r])
-                    fv.end(ctx[r]);
         }
+        if (my_ok)
+            fv.end(my_ctx);
     }
     fv.kernel_end();
 }

@@ -19,8 +19,8 @@ constexpr int RB = kSortRadixBits;
 constexpr int RADIX = kSortRadix;
 constexpr int SORT_THREADS = 256;
 constexpr int SORT_WARPS = SORT_THREADS / 32;
-constexpr int SORT_ITEMS = 8;
-constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS; // 2048 keys per block
+constexpr int SORT_ITEMS = 16;
+constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS; // 4096 keys per block
 
 template <int KIND>
 __device__ __forceinline__ u64 load_key(const void *in, size_t e) {
@@ -68,8 +68,10 @@ __device__ __forceinline__ void rank_tile(const void *kin, size_t n, int shift, 
 // the keys are in).  totals[p][d] must be zero on entry (they live in the scan arena).
 template <int KIND>
 __global__ void __launch_bounds__(SORT_THREADS)
-    sort_hist_all_kernel(const void *kin, size_t n, int passes, u32 *totals) {
+    sort_hist_all_kernel(const void *kin, size_t n, int passes, u32 *totals, const u32 *mismatch) {
     __shared__ u32 sh[kMaxSortPasses * RADIX];
+    if (mismatch && *mismatch == 0)
+        return; // same keys as the batch this workspace already holds sorted
     for (int b = threadIdx.x; b < passes * RADIX; b += SORT_THREADS)
         sh[b] = 0;
     __syncthreads();
@@ -98,8 +100,11 @@ __device__ __forceinline__ u64 pack_status(u32 epoch, u32 flag, u32 value) {
 template <int KIND, bool FIRST>
 __global__ void __launch_bounds__(SORT_THREADS)
     sort_pass_kernel(const void *kin, const u32 *vin, u64 *kout, u32 *vout, size_t n, int shift,
-                     const u32 *__restrict__ totals, u64 *status, u32 *ticket, u32 epoch) {
+                     const u32 *__restrict__ totals, u64 *status, u32 *ticket, u32 epoch,
+                     const u32 *mismatch) {
     __shared__ u32 s_cnt[SORT_WARPS][RADIX];
+    if (mismatch && *mismatch == 0)
+        return;
     __shared__ u32 s_off[RADIX];
     __shared__ u32 s_wsum[SORT_WARPS];
     u64 key[SORT_ITEMS];
@@ -148,16 +153,28 @@ __global__ void __launch_bounds__(SORT_THREADS)
         const int b = threadIdx.x * DPT + k;
         u32 excl = 0;
         if (tile > 0) {
+            // four predecessors per round trip; stop at the nearest one that holds a prefix
             int look = (int)tile - 1;
-            while (true) {
-                u64 s;
-                do {
-                    s = *reinterpret_cast<volatile u64 *>(&status[(size_t)look * RADIX + b]);
-                } while ((u32)(s >> 34) != epoch || ((s >> 32) & 3u) == 0);
-                excl += (u32)s;
-                if (((s >> 32) & 3u) == 2u)
-                    break;
-                look--;
+            bool done = false;
+            while (!done) {
+                u64 sv[4];
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const int idx = look - i;
+                    sv[i] = idx >= 0 ? *reinterpret_cast<volatile u64 *>(&status[(size_t)idx * RADIX + b])
+                                     : pack_status(epoch, 2u, 0);
+                }
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const int idx = look - i;
+                    while ((u32)(sv[i] >> 34) != epoch || ((sv[i] >> 32) & 3u) == 0)
+                        sv[i] = *reinterpret_cast<volatile u64 *>(&status[(size_t)idx * RADIX + b]);
+                    if (!done) {
+                        excl += (u32)sv[i];
+                        done = ((sv[i] >> 32) & 3u) == 2u;
+                    }
+                }
+                look -= 4;
             }
             *reinterpret_cast<volatile u64 *>(&status[(size_t)tile * RADIX + b]) =
                 pack_status(epoch, 2u, excl + cnt[k]);
@@ -185,7 +202,9 @@ constexpr int UNIQ_TILE = kScanBlock * UNIQ_ITEMS;
 
 __global__ void __launch_bounds__(kScanBlock)
     unique_kernel(const u64 *sk, const u32 *perm, size_t n, u64 *uniq, u32 *inverse,
-                  u32 *seg_start, u32 *num_unique, ScanState st, u32 ntiles) {
+                  u32 *seg_start, u32 *num_unique, ScanState st, u32 ntiles, const u32 *mismatch) {
+    if (mismatch && *mismatch == 0)
+        return;
     const u32 tile = take_ticket(st.ticket);
     const size_t base = (size_t)tile * UNIQ_TILE + (size_t)threadIdx.x * UNIQ_ITEMS;
     u64 k[UNIQ_ITEMS];
@@ -226,6 +245,25 @@ __global__ void __launch_bounds__(kScanBlock)
     }
 }
 
+// Does the new batch hold the same key sequence as the one this workspace has sorted?  Exact:
+// key(new[i]) == uniq[inverse[i]] for every i.  *mismatch (zeroed with the scan arena) counts
+// the positions that differ.
+template <int KIND>
+__global__ void __launch_bounds__(256)
+    same_keys_kernel(const void *kin, size_t n, const u64 *__restrict__ uniq,
+                     const u32 *__restrict__ inverse, const u32 *__restrict__ num_unique,
+                     u32 *mismatch) {
+    const u32 U = *num_unique;
+    bool bad = false;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (size_t)gridDim.x * blockDim.x) {
+        const u32 r = inverse[i];
+        bad |= r >= U || uniq[r] != load_key<KIND>(kin, i);
+    }
+    if (__any_sync(FULL, bad) && lane_id() == 0)
+        atomicAdd(mismatch, 1u);
+}
+
 __global__ void set_zero_unique(u32 *num_unique, u32 *seg_start) {
     *num_unique = 0;
     seg_start[0] = 0;
@@ -243,6 +281,22 @@ void dev_free(T *&p) {
 }
 
 } // namespace
+
+const u32 *check_same_keys(KeyWorkspace &ws, const void *keys_in, int key_kind, size_t n,
+                           cudaStream_t st) {
+    if (!ws.sorted_valid || n == 0 || n != ws.sorted_n)
+        return nullptr;
+    u32 *mismatch = ws.reuse_mismatch();
+    int grid = std::min(ceil_div(n, 256 * 4), sm_count() * 4);
+    if (key_kind == HB_KEYS_F32)
+        same_keys_kernel<HB_KEYS_F32><<<grid, 256, 0, st>>>(keys_in, n, ws.uniq, ws.inverse,
+                                                           ws.num_unique, mismatch);
+    else
+        same_keys_kernel<HB_KEYS_U64><<<grid, 256, 0, st>>>(keys_in, n, ws.uniq, ws.inverse,
+                                                           ws.num_unique, mismatch);
+    HB_LAUNCHED();
+    return mismatch;
+}
 
 int bits_for(u64 max_key_exclusive) {
     int bits = 1;
@@ -272,6 +326,7 @@ void KeyWorkspace::reserve(size_t n) {
     ntile_cap = (c + kScanBlock - 1) / kScanBlock + 1;
     dev_alloc(scan_arena, arena_words());
     HB_CUDA(cudaMemset(scan_arena, 0, arena_words() * sizeof(u64)));
+    sorted_valid = false;
     dev_alloc(hot_a, c);
     dev_alloc(hot_b, c);
     dev_alloc(hot_done_a, c);
@@ -313,7 +368,7 @@ ScanState KeyWorkspace::next_scan() {
 }
 
 SortedKeys radix_sort_keys(KeyWorkspace &ws, const void *keys_in, int key_kind, size_t n,
-                           int key_bits, cudaStream_t st) {
+                           int key_bits, cudaStream_t st, const u32 *mismatch) {
     HB_CHECK(n <= ws.cap, "sort workspace too small");
     HB_CHECK(n < (1ull << 32), "too many keys");
     int passes = std::min(kMaxSortPasses, std::max(1, (key_bits + RB - 1) / RB));
@@ -321,9 +376,9 @@ SortedKeys radix_sort_keys(KeyWorkspace &ws, const void *keys_in, int key_kind, 
     u32 *totals = ws.sort_totals();
     int hgrid = std::min(nblk, sm_count() * 4);
     if (key_kind == HB_KEYS_F32)
-        sort_hist_all_kernel<HB_KEYS_F32><<<hgrid, SORT_THREADS, 0, st>>>(keys_in, n, passes, totals);
+        sort_hist_all_kernel<HB_KEYS_F32><<<hgrid, SORT_THREADS, 0, st>>>(keys_in, n, passes, totals, mismatch);
     else
-        sort_hist_all_kernel<HB_KEYS_U64><<<hgrid, SORT_THREADS, 0, st>>>(keys_in, n, passes, totals);
+        sort_hist_all_kernel<HB_KEYS_U64><<<hgrid, SORT_THREADS, 0, st>>>(keys_in, n, passes, totals, mismatch);
     HB_LAUNCHED();
     const void *kin = keys_in;
     const u32 *vin = nullptr;
@@ -337,13 +392,16 @@ SortedKeys radix_sort_keys(KeyWorkspace &ws, const void *keys_in, int key_kind, 
         u32 *ticket = ws.sort_tickets() + p;
         if (f32)
             sort_pass_kernel<HB_KEYS_F32, true><<<nblk, SORT_THREADS, 0, st>>>(
-                kin, vin, ws.keys[out], ws.vals[out], n, shift, tp, ws.sort_status, ticket, epoch);
+                kin, vin, ws.keys[out], ws.vals[out], n, shift, tp, ws.sort_status, ticket, epoch,
+                mismatch);
         else if (first)
             sort_pass_kernel<HB_KEYS_U64, true><<<nblk, SORT_THREADS, 0, st>>>(
-                kin, vin, ws.keys[out], ws.vals[out], n, shift, tp, ws.sort_status, ticket, epoch);
+                kin, vin, ws.keys[out], ws.vals[out], n, shift, tp, ws.sort_status, ticket, epoch,
+                mismatch);
         else
             sort_pass_kernel<HB_KEYS_U64, false><<<nblk, SORT_THREADS, 0, st>>>(
-                kin, vin, ws.keys[out], ws.vals[out], n, shift, tp, ws.sort_status, ticket, epoch);
+                kin, vin, ws.keys[out], ws.vals[out], n, shift, tp, ws.sort_status, ticket, epoch,
+                mismatch);
         HB_LAUNCHED();
         kin = ws.keys[out];
         vin = ws.vals[out];
@@ -355,7 +413,8 @@ SortedKeys radix_sort_keys(KeyWorkspace &ws, const void *keys_in, int key_kind, 
     return sk;
 }
 
-void unique_from_sorted(KeyWorkspace &ws, const SortedKeys &sk, size_t n, cudaStream_t st) {
+void unique_from_sorted(KeyWorkspace &ws, const SortedKeys &sk, size_t n, cudaStream_t st,
+                        const u32 *mismatch) {
     if (n == 0) {
         set_zero_unique<<<1, 1, 0, st>>>(ws.num_unique, ws.seg_start);
         HB_LAUNCHED();
@@ -364,7 +423,7 @@ void unique_from_sorted(KeyWorkspace &ws, const SortedKeys &sk, size_t n, cudaSt
     u32 ntiles = (u32)ceil_div(n, UNIQ_TILE);
     unique_kernel<<<ntiles, kScanBlock, 0, st>>>(sk.keys, sk.perm, n, ws.uniq, ws.inverse,
                                                  ws.seg_start, ws.num_unique, ws.next_scan(),
-                                                 ntiles);
+                                                 ntiles, mismatch);
     HB_LAUNCHED();
 }
 

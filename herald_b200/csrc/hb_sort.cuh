@@ -48,7 +48,7 @@ struct KeyWorkspace {
     }
     size_t arena_words() const {
         return (size_t)kScanSlots * scan_slot_words() + 2 + (kMaxSortPasses * kSortRadix) / 2 +
-               kMaxSortPasses / 2;
+               kMaxSortPasses / 2 + 1;
     }
     u32 *hot_ctrl() const { // 4 x u32
         return reinterpret_cast<u32 *>(scan_arena + (size_t)kScanSlots * scan_slot_words());
@@ -59,6 +59,12 @@ struct KeyWorkspace {
     u32 *sort_tickets() const {
         return sort_totals() + kMaxSortPasses * kSortRadix;
     }
+    u32 *reuse_mismatch() const {
+        return sort_tickets() + kMaxSortPasses;
+    }
+    // host-side record of what uniq / inverse / seg_start / the sorted buffers currently hold
+    bool sorted_valid = false;
+    size_t sorted_n = 0;
     u32 next_sort_epoch() {
         sort_epoch = (sort_epoch + 1) & 0x3fffffffu;
         if (sort_epoch == 0)
@@ -77,11 +83,21 @@ struct SortedKeys {
 
 // keys_in: n keys of `key_kind` (HB_KEYS_U64 / HB_KEYS_F32) in device memory.
 // key_bits: keys are < 2^key_bits (fewer bits = fewer passes).
+// `mismatch` (from check_same_keys, may be null): the kernels do nothing when *mismatch == 0,
+// i.e. when the workspace already holds this very batch sorted.
 SortedKeys radix_sort_keys(KeyWorkspace &ws, const void *keys_in, int key_kind, size_t n,
-                           int key_bits, cudaStream_t st);
+                           int key_bits, cudaStream_t st, const u32 *mismatch = nullptr);
+
+// Hetu's BSP loop updates the batch it looked up one call earlier (python/hetu/gpu_ops/
+// ParameterServerCommunicate.py:48-52), so the second sort of a batch can be skipped.  Enqueues
+// an exact device-side comparison of the new keys with the batch the workspace holds and returns
+// the device counter the sort kernels test; null when there is nothing to compare with.
+const u32 *check_same_keys(KeyWorkspace &ws, const void *keys_in, int key_kind, size_t n,
+                           cudaStream_t st);
 
 // Fills ws.uniq / ws.inverse / ws.seg_start / ws.num_unique from a sorted sequence.
-void unique_from_sorted(KeyWorkspace &ws, const SortedKeys &sk, size_t n, cudaStream_t st);
+void unique_from_sorted(KeyWorkspace &ws, const SortedKeys &sk, size_t n, cudaStream_t st,
+                        const u32 *mismatch = nullptr);
 
 int bits_for(u64 max_key_exclusive);
 
