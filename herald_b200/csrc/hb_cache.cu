@@ -122,12 +122,14 @@ __device__ __forceinline__ u64 make_prio(u32 use, u64 stamp) {
 // =====================================================================================
 // clk[0..3]: the replacement clock as a chain — stage s of a call reads clk[s] and writes
 // clk[s+1], so no kernel reads a word that another block of the same kernel writes.
-__global__ void op_begin_kernel(CacheRegs *r, u64 *clk) {
+// flush != 0: the call pushes, so it also flushes the dirty victims collected so far (evict_)
+__global__ void op_begin_kernel(CacheRegs *r, u64 *clk, int flush) {
     r->clock0 = r->clock;
     clk[0] = r->clock;
     clk[1] = clk[2] = clk[3] = r->clock;
     r->U = r->M = r->alloc_base = 0;
-    r->pulled = r->pushed = r->flushed = 0;
+    r->pulled = r->pushed = 0;
+    r->flushed = flush ? r->pending : 0;
     r->E = r->k_old = r->n_drop = r->need_min = r->nv = r->nc = 0;
     r->U2 = r->M2 = r->alloc_base2 = 0;
 }
@@ -227,6 +229,7 @@ __global__ void __launch_bounds__(kScanBlock)
         }
         alloc_base = top - M;
         r->free_top = alloc_base;
+        r->slot_hw = max(r->slot_hw, c.capacity - alloc_base); // the stack hands out 0, 1, 2, ...
         if (batch == 0) {
             r->U = U;
             r->M = M;
@@ -403,7 +406,8 @@ __global__ void __launch_bounds__(256) sel_hist_kernel(CacheView c) {
     const u64 floor = r->floor;
     const u32 shift = r->sel_shift;
     const u64 cls = (u64)class_use_of(c.policy);
-    for (size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x; s < c.capacity;
+    const size_t hw = r->slot_hw;
+    for (size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x; s < hw;
          s += (size_t)gridDim.x * blockDim.x) {
         const u64 p = c.slot_prio[s];
         if (p != PRIO_NONE && (p >> kStampBits) == cls) {
@@ -510,12 +514,13 @@ __global__ void __launch_bounds__(256) sel_collect_kernel(CacheView c) {
     const u32 shift = r->sel_shift;
     const u64 cls = (u64)class_use_of(c.policy);
     const size_t stride = (size_t)gridDim.x * blockDim.x;
-    const size_t rounds = (c.capacity + stride - 1) / stride;
+    const size_t hw = r->slot_hw;
+    const size_t rounds = (hw + stride - 1) / stride;
     for (size_t it = 0; it < rounds; it++) {
         const size_t s = it * stride + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
         bool victim = false, cand = false;
         u64 p = 0;
-        if (s < c.capacity) {
+        if (s < hw) {
             p = c.slot_prio[s];
             if (p != PRIO_NONE && (p >> kStampBits) == cls) {
                 u64 bin = min(((p & kStampMask) - floor) >> shift, (u64)(kSelBins - 1));
@@ -644,7 +649,7 @@ __global__ void min_use_kernel(CacheView c) {
     if (!r->need_min)
         return;
     u32 best = 0xffffffffu;
-    for (size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x; s < c.capacity;
+    for (size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x; s < r->slot_hw;
          s += (size_t)gridDim.x * blockDim.x)
         if (c.slot_state[s] == S_CACHED)
             best = min(best, c.slot_use[s]);
@@ -659,7 +664,7 @@ __global__ void min_prio_kernel(CacheView c) {
         return;
     const u32 mu = r->min_use;
     u64 best = ~0ull;
-    for (size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x; s < c.capacity;
+    for (size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x; s < r->slot_hw;
          s += (size_t)gridDim.x * blockDim.x)
         if (c.slot_state[s] == S_CACHED && c.slot_use[s] == mu)
             best = min(best, c.slot_prio[s] & kStampMask);
@@ -674,7 +679,7 @@ __global__ void min_pick_kernel(CacheView c) {
         return;
     const u32 mu = r->min_use;
     const u64 mp = r->min_prio;
-    for (size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x; s < c.capacity;
+    for (size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x; s < r->slot_hw;
          s += (size_t)gridDim.x * blockDim.x)
         if (c.slot_state[s] == S_CACHED && c.slot_use[s] == mu &&
             (c.slot_prio[s] & kStampMask) == mp)
@@ -876,16 +881,13 @@ struct FlushPending {
     }
 };
 
-__global__ void flush_begin_kernel(CacheRegs *r) {
-    r->flushed = r->pending;
-}
-__global__ void flush_end_kernel(CacheRegs *r) {
-    r->pending = 0;
-}
 
 // dataless lines are dropped after the push (never inserted)
-__global__ void free_transient_kernel(CacheView c, const i32 *uslot, const u32 *miss_list, int batch) {
+__global__ void free_transient_kernel(CacheView c, const i32 *uslot, const u32 *miss_list, int batch,
+                                      int flushed) {
     CacheRegs *r = c.regs;
+    if (flushed && blockIdx.x == 0 && threadIdx.x == 0)
+        r->pending = 0; // the pending victims have just been pushed
     const u32 M = batch == 0 ? r->M : r->M2;
     for (u32 j = blockIdx.x * blockDim.x + threadIdx.x; j < M; j += gridDim.x * blockDim.x) {
         const u32 s = (u32)uslot[miss_list[j]];
@@ -1181,11 +1183,11 @@ void mark(hb_cache *c, int k) {
     c->phase_mask[idx] |= 1u << k;
 }
 
-void begin_call(hb_cache *c) {
+void begin_call(hb_cache *c, bool flush = false) {
     int idx = (int)(c->calls % hb_cache::kRing);
     c->phase_mask[idx] = 0;
     HB_CUDA(cudaEventRecord(c->ev_begin[idx], c->stream));
-    op_begin_kernel<<<1, 1, 0, c->stream>>>(c->view.regs, clk_of(c));
+    op_begin_kernel<<<1, 1, 0, c->stream>>>(c->view.regs, clk_of(c), flush ? 1 : 0);
     HB_LAUNCHED();
 }
 
@@ -1297,8 +1299,6 @@ void run_accumulate(hb_cache *c, size_t n, int batch, const float *dev_grads, co
                     size_t n_push, bool use_plan, bool defer_cleanup = false) {
     cudaStream_t st = c->stream;
     KeyWorkspace &ws = c->ws[batch];
-    flush_begin_kernel<<<1, 1, 0, st>>>(c->view.regs);
-    HB_LAUNCHED();
     if (n) {
         const u32 *p = c->sorted[batch].perm;
         const u64 *plan = use_plan ? dev_push_keys : nullptr;
@@ -1331,14 +1331,10 @@ void run_accumulate(hb_cache *c, size_t n, int batch, const float *dev_grads, co
         }
         HB_LAUNCHED();
     }
-    flush_end_kernel<<<1, 1, 0, st>>>(c->view.regs);
-    HB_LAUNCHED();
     c->pending_upper = 0;
-    if (n) {
-        free_transient_kernel<<<lin_grid(n), 256, 0, st>>>(c->view, c->uslot[batch],
-                                                           c->miss_list[batch], batch);
-        HB_LAUNCHED();
-    }
+    free_transient_kernel<<<lin_grid(n), 256, 0, st>>>(c->view, c->uslot[batch], c->miss_list[batch],
+                                                       batch, 1);
+    HB_LAUNCHED();
 }
 
 const u64 *stage_push_keys(hb_cache *c, const void *push_keys, int kind, size_t n_push) {
@@ -1383,7 +1379,7 @@ void do_update(hb_cache *c, const void *keys, int kind, size_t n, const float *g
         dgrads = stage;
     }
     const u64 *dpush = use_plan ? stage_push_keys(c, push_keys, push_kind, n_push) : nullptr;
-    begin_call(c);
+    begin_call(c, /*flush=*/true);
     resolve_batch(c, dkeys, kind, n, 0, /*dataless=*/true, 0);
     run_accumulate(c, n, 0, dgrads, dpush, n_push, use_plan);
     end_call(c, 1, 1, n, false);
@@ -1752,7 +1748,7 @@ int hb_cache_push_pull(hb_cache *c, const void *pull_keys, int pull_kind, size_t
                                 cudaMemcpyHostToDevice, st));
         dgrads = stage;
     }
-    begin_call(c);
+    begin_call(c, /*flush=*/true);
     // cache.cc:360-391: pull-side lookup, then push-side lookup + accumulate
     resolve_batch(c, dpull, pull_kind, n_pull, 0, /*dataless=*/false, 0, false);
     resolve_batch(c, dpush, push_kind, n_push, 1, /*dataless=*/true, 1, false);
@@ -1956,7 +1952,7 @@ int hb_cache_touch(hb_cache *c, uint64_t key, int *found, int64_t *version, floa
     // allocates nothing)
     alloc_kernel<<<1, 32, 0, st>>>(c->view, ws.uniq, c->uslot[0], c->miss_list[0], 0, 0);
     HB_LAUNCHED();
-    free_transient_kernel<<<1, 32, 0, st>>>(c->view, c->uslot[0], c->miss_list[0], 0);
+    free_transient_kernel<<<1, 32, 0, st>>>(c->view, c->uslot[0], c->miss_list[0], 0, 0);
     HB_LAUNCHED();
     end_call(c, 1, 0, 1, false);
     HB_CUDA(cudaStreamSynchronize(st));

@@ -72,6 +72,8 @@ struct CacheRegs {
     u32 pending;     // dirty victims awaiting a push
     u32 ht_occupied; // non-EMPTY index entries (live + tombstones)
     u32 error;
+    u32 slot_hw;     // slots [0, slot_hw) have been handed out at least once (scan bound)
+    u32 pad0;
     u64 clock; // replacement clock: one tick per policy touch / insert
     u64 floor; // lower bound of the stamps of the policy's victim class
     // per call (zeroed by op_begin)

@@ -3,7 +3,7 @@
 // Sort: 9-bit digits (3 passes for ids < 2^27, i.e. the 33.7M-row Criteo table and the 1e8-row
 // sweep).  One kernel counts the digits of every pass; then one kernel per pass ranks a tile,
 // finds its digit offsets by chained look-back over the earlier tiles and scatters (stable:
-// "onesweep").  Ranking inside a tile is warp-cooperative: __match_any_sync groups the lanes of a
+// "onesweep").  Ranking inside a tile is warp-cooperative: nine ballots group the lanes of a
 // warp that hold the same digit, the lowest lane of each group bumps the warp's digit counter in
 // shared memory, so there are no shared-memory atomics and hot (Zipf) keys do not serialise.
 // HBM traffic per pass: 1 read + 1 write of 12 B/key; at N = 212,992 everything is L2-resident.
@@ -19,8 +19,8 @@ constexpr int RB = kSortRadixBits;
 constexpr int RADIX = kSortRadix;
 constexpr int SORT_THREADS = 256;
 constexpr int SORT_WARPS = SORT_THREADS / 32;
-constexpr int SORT_ITEMS = 16;
-constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS; // 4096 keys per block
+constexpr int SORT_ITEMS = 8;
+constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS; // 2048 keys per block
 
 template <int KIND>
 __device__ __forceinline__ u64 load_key(const void *in, size_t e) {
@@ -32,27 +32,25 @@ __device__ __forceinline__ u64 load_key(const void *in, size_t e) {
 // Each warp walks its SORT_ITEMS*32 consecutive keys in order, 32 at a time.  On return
 // s_cnt[w][d] = number of keys with digit d in warp w's span, rank[r] = how many keys with the
 // same digit precede this one inside the warp's span (stable).
-template <int KIND>
-__device__ __forceinline__ void rank_tile(const void *kin, size_t n, int shift, size_t tile_base,
-                                          u32 (*s_cnt)[RADIX], u64 (&key)[SORT_ITEMS],
-                                          u32 (&rank)[SORT_ITEMS], bool (&valid)[SORT_ITEMS]) {
-    const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
+__device__ __forceinline__ void rank_tile(int shift, u32 (*s_cnt)[RADIX], const u64 (&key)[SORT_ITEMS],
+                                          u32 (&rank)[SORT_ITEMS], const bool (&valid)[SORT_ITEMS]) {
+    const unsigned warp = threadIdx.x >> 5;
     for (int b = threadIdx.x; b < SORT_WARPS * RADIX; b += SORT_THREADS)
         (&s_cnt[0][0])[b] = 0;
     __syncthreads();
-    const size_t warp_base = tile_base + (size_t)warp * (SORT_ITEMS * 32);
-#pragma unroll
-    for (int r = 0; r < SORT_ITEMS; r++) {
-        size_t e = warp_base + r * 32 + lane;
-        valid[r] = e < n;
-        key[r] = valid[r] ? load_key<KIND>(kin, e) : 0;
-    }
 #pragma unroll
     for (int r = 0; r < SORT_ITEMS; r++) {
         unsigned vm = __ballot_sync(FULL, valid[r]);
         if (valid[r]) {
             u32 d = (u32)(key[r] >> shift) & (RADIX - 1);
-            unsigned peers = __match_any_sync(vm, d);
+            // lanes holding the same digit: RB ballots
+            unsigned peers = vm;
+#pragma unroll
+            for (int bit = 0; bit < RB; bit++) {
+                const bool one = (d >> bit) & 1u;
+                const unsigned bal = __ballot_sync(vm, one);
+                peers &= one ? bal : ~bal;
+            }
             u32 base = s_cnt[warp][d];
             __syncwarp(vm);
             if ((peers & lanemask_lt()) == 0) // lowest lane of the group
@@ -97,7 +95,10 @@ __device__ __forceinline__ u64 pack_status(u32 epoch, u32 flag, u32 value) {
 // One pass of the stable LSD radix sort in a single kernel: rank inside the tile, chained
 // look-back over the earlier tiles per digit, scatter.  Tiles are numbered by an atomic ticket,
 // so a tile only ever waits for tiles that are already running.
-template <int KIND, bool FIRST>
+// FIRST: keys come from the caller's array (KIND) and the payload is the position.  PIN / POUT:
+// the input / output of the pass is one packed word per key, key << 32 | original index (used
+// when the keys fit 32 bits: one scattered store per key instead of two).
+template <int KIND, bool FIRST, bool PIN, bool POUT>
 __global__ void __launch_bounds__(SORT_THREADS)
     sort_pass_kernel(const void *kin, const u32 *vin, u64 *kout, u32 *vout, size_t n, int shift,
                      const u32 *__restrict__ totals, u64 *status, u32 *ticket, u32 epoch,
@@ -112,8 +113,29 @@ __global__ void __launch_bounds__(SORT_THREADS)
     bool valid[SORT_ITEMS];
     const u32 tile = take_ticket(ticket);
     const size_t tile_base = (size_t)tile * SORT_TILE;
-    rank_tile<KIND>(kin, n, shift, tile_base, s_cnt, key, rank, valid);
     const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
+    const size_t warp_base = tile_base + (size_t)warp * (SORT_ITEMS * 32);
+    u32 idx[SORT_ITEMS];
+#pragma unroll
+    for (int r = 0; r < SORT_ITEMS; r++) {
+        const size_t e = warp_base + r * 32 + lane;
+        valid[r] = e < n;
+        key[r] = 0;
+        idx[r] = (u32)e;
+        if (valid[r]) {
+            if (FIRST) {
+                key[r] = load_key<KIND>(kin, e);
+            } else if (PIN) {
+                const u64 w = reinterpret_cast<const u64 *>(kin)[e];
+                key[r] = w >> 32;
+                idx[r] = (u32)w;
+            } else {
+                key[r] = reinterpret_cast<const u64 *>(kin)[e];
+                idx[r] = vin[e];
+            }
+        }
+    }
+    rank_tile(shift, s_cnt, key, rank, valid);
     constexpr int DPT = RADIX / SORT_THREADS; // consecutive digits per thread
     u32 cnt[DPT], tot[DPT];
     u32 tsum = 0;
@@ -153,28 +175,30 @@ __global__ void __launch_bounds__(SORT_THREADS)
         const int b = threadIdx.x * DPT + k;
         u32 excl = 0;
         if (tile > 0) {
-            // four predecessors per round trip; stop at the nearest one that holds a prefix
+            // kLook predecessors per round trip (independent loads); stop at the nearest one
+            // that already holds a prefix
+            constexpr int kLook = 16;
             int look = (int)tile - 1;
             bool done = false;
             while (!done) {
-                u64 sv[4];
+                u64 sv[kLook];
 #pragma unroll
-                for (int i = 0; i < 4; i++) {
+                for (int i = 0; i < kLook; i++) {
                     const int idx = look - i;
                     sv[i] = idx >= 0 ? *reinterpret_cast<volatile u64 *>(&status[(size_t)idx * RADIX + b])
                                      : pack_status(epoch, 2u, 0);
                 }
 #pragma unroll
-                for (int i = 0; i < 4; i++) {
+                for (int i = 0; i < kLook; i++) {
                     const int idx = look - i;
-                    while ((u32)(sv[i] >> 34) != epoch || ((sv[i] >> 32) & 3u) == 0)
-                        sv[i] = *reinterpret_cast<volatile u64 *>(&status[(size_t)idx * RADIX + b]);
                     if (!done) {
+                        while ((u32)(sv[i] >> 34) != epoch || ((sv[i] >> 32) & 3u) == 0)
+                            sv[i] = *reinterpret_cast<volatile u64 *>(&status[(size_t)idx * RADIX + b]);
                         excl += (u32)sv[i];
                         done = ((sv[i] >> 32) & 3u) == 2u;
                     }
                 }
-                look -= 4;
+                look -= kLook;
             }
             *reinterpret_cast<volatile u64 *>(&status[(size_t)tile * RADIX + b]) =
                 pack_status(epoch, 2u, excl + cnt[k]);
@@ -183,15 +207,17 @@ __global__ void __launch_bounds__(SORT_THREADS)
         base += tot[k];
     }
     __syncthreads();
-    const size_t warp_base = tile_base + (size_t)warp * (SORT_ITEMS * 32);
 #pragma unroll
     for (int r = 0; r < SORT_ITEMS; r++) {
         if (valid[r]) {
-            size_t e = warp_base + r * 32 + lane;
             u32 d = (u32)(key[r] >> shift) & (RADIX - 1);
             u32 pos = s_off[d] + s_cnt[warp][d] + rank[r];
-            kout[pos] = key[r];
-            vout[pos] = FIRST ? (u32)e : vin[e];
+            if (POUT) {
+                kout[pos] = (key[r] << 32) | idx[r];
+            } else {
+                kout[pos] = key[r];
+                vout[pos] = idx[r];
+            }
         }
     }
 }
@@ -374,7 +400,7 @@ SortedKeys radix_sort_keys(KeyWorkspace &ws, const void *keys_in, int key_kind, 
     int passes = std::min(kMaxSortPasses, std::max(1, (key_bits + RB - 1) / RB));
     int nblk = ceil_div(n, SORT_TILE);
     u32 *totals = ws.sort_totals();
-    int hgrid = std::min(nblk, sm_count() * 4);
+    int hgrid = std::max(1, std::min(ceil_div(n, 1024), sm_count() * 2));
     if (key_kind == HB_KEYS_F32)
         sort_hist_all_kernel<HB_KEYS_F32><<<hgrid, SORT_THREADS, 0, st>>>(keys_in, n, passes, totals, mismatch);
     else
@@ -390,18 +416,27 @@ SortedKeys radix_sort_keys(KeyWorkspace &ws, const void *keys_in, int key_kind, 
         u32 epoch = ws.next_sort_epoch();
         const u32 *tp = totals + (size_t)p * RADIX;
         u32 *ticket = ws.sort_tickets() + p;
-        if (f32)
-            sort_pass_kernel<HB_KEYS_F32, true><<<nblk, SORT_THREADS, 0, st>>>(
-                kin, vin, ws.keys[out], ws.vals[out], n, shift, tp, ws.sort_status, ticket, epoch,
-                mismatch);
+        // keys below 2^32 travel packed with their index between the passes
+        const bool packed = key_bits <= 32 && passes > 1;
+        const bool pin = packed && !first, pout = packed && p + 1 < passes;
+#define HB_SORT_PASS(KIND, F, PI, PO)                                                             \
+    sort_pass_kernel<KIND, F, PI, PO><<<nblk, SORT_THREADS, 0, st>>>(                            \
+        kin, vin, ws.keys[out], ws.vals[out], n, shift, tp, ws.sort_status, ticket, epoch, mismatch)
+        if (f32 && pout)
+            HB_SORT_PASS(HB_KEYS_F32, true, false, true);
+        else if (f32)
+            HB_SORT_PASS(HB_KEYS_F32, true, false, false);
+        else if (first && pout)
+            HB_SORT_PASS(HB_KEYS_U64, true, false, true);
         else if (first)
-            sort_pass_kernel<HB_KEYS_U64, true><<<nblk, SORT_THREADS, 0, st>>>(
-                kin, vin, ws.keys[out], ws.vals[out], n, shift, tp, ws.sort_status, ticket, epoch,
-                mismatch);
+            HB_SORT_PASS(HB_KEYS_U64, true, false, false);
+        else if (pin && pout)
+            HB_SORT_PASS(HB_KEYS_U64, false, true, true);
+        else if (pin)
+            HB_SORT_PASS(HB_KEYS_U64, false, true, false);
         else
-            sort_pass_kernel<HB_KEYS_U64, false><<<nblk, SORT_THREADS, 0, st>>>(
-                kin, vin, ws.keys[out], ws.vals[out], n, shift, tp, ws.sort_status, ticket, epoch,
-                mismatch);
+            HB_SORT_PASS(HB_KEYS_U64, false, false, false);
+#undef HB_SORT_PASS
         HB_LAUNCHED();
         kin = ws.keys[out];
         vin = ws.vals[out];

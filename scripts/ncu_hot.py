@@ -27,7 +27,7 @@ i_src, i_s, i_ex = hdr.index('Source'), hdr.index('# Samples'), hdr.index('Instr
 stalls = [(j, h) for j, h in enumerate(hdr) if h.startswith('stall_') and 'Not Issued' not in h]
 seen, order = set(), []
 for r in rows[2:]:
-    if r[0] in seen or r[0] == 'Address':
+    if len(r) <= max(i_s, i_ex) or r[0] in seen or r[0] == 'Address':
         continue
     seen.add(r[0])
     try:
