@@ -252,12 +252,13 @@ def herald_main(args, rank, world, local_rank):
     if world > 1:
         import torch.distributed as dist                       # rendezvous + barrier only (gloo)
         dist.init_process_group("gloo", rank=rank, world_size=world)
-        idbuf = (ctypes.c_char * 128)()
-        if rank == 0:
-            check_call(_LIB.hb_comm_unique_id(idbuf))
-        obj = [bytes(idbuf.raw)]
-        dist.broadcast_object_list(obj, src=0)
-        check_call(_LIB.hb_comm_init(obj[0], rank, world, local_rank))
+
+        def exchange(b):
+            obj = [b]
+            dist.broadcast_object_list(obj, src=0)
+            return obj[0]
+
+        ps.group_init(rank, world, local_rank, exchange)
 
     dev = hb.gpu(local_rank)
     B, D, V = args.batch, args.dim, args.vocab
@@ -413,7 +414,7 @@ def herald_main(args, rank, world, local_rank):
     del cst
     comm.ClearTensor(0)
     if dist is not None:
-        check_call(_LIB.hb_comm_finalize())
+        ps.group_finalize()
         dist.destroy_process_group()
 
 

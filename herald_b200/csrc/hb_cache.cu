@@ -292,12 +292,20 @@ __global__ void __launch_bounds__(kRowBlock)
         u64 trow = 0;
         i64 srv = 0;
         bool need = false, addup = false, live_grad = false;
+        int owner = 0;
         if (i < U) {
             s = uslot[i];
-            trow = uniq[i] - c.row_begin;
-            if (s >= 0 && trow < c.nrows_local) {
+            bool have;
+            if (c.pv.world > 1) { // the owner's shard is read in place over NVLink
+                owner = owner_of(c.pv, uniq[i], trow);
+                have = uniq[i] < c.table_len;
+            } else {
+                trow = uniq[i] - c.row_begin;
+                have = trow < c.nrows_local;
+            }
+            if (s >= 0 && have) {
                 const i64 v = c.slot_version[s];
-                srv = c.tver[trow];
+                srv = c.pv.ver[owner][trow];
                 need = v == -1 || srv - v > pull_bound;
                 if (need) {
                     addup = c.slot_flags[s] & F_GRAD; // Line::addup (embedding.h:92-96)
@@ -312,6 +320,7 @@ __global__ void __launch_bounds__(kRowBlock)
             int src[ROWS];
             i32 rs[ROWS];
             u64 rt[ROWS];
+            const float *rbase[ROWS];
             bool ra[ROWS], rg[ROWS];
 #pragma unroll
             for (int r = 0; r < ROWS; r++) {
@@ -321,6 +330,7 @@ __global__ void __launch_bounds__(kRowBlock)
                 const int from = src[r] < 0 ? 0 : src[r];
                 rs[r] = __shfl_sync(FULL, s, from);
                 rt[r] = __shfl_sync(FULL, trow, from);
+                rbase[r] = c.pv.rows[__shfl_sync(FULL, owner, from)];
                 ra[r] = __shfl_sync(FULL, addup, from);
                 rg[r] = __shfl_sync(FULL, live_grad, from);
             }
@@ -329,7 +339,7 @@ __global__ void __launch_bounds__(kRowBlock)
 #pragma unroll
                 for (int r = 0; r < ROWS; r++)
                     if (src[r] >= 0) {
-                        x[r] = V::ld(c.trows + rt[r] * D + k * VEC);
+                        x[r] = V::ld(rbase[r] + rt[r] * D + k * VEC);
                         g[r] = rg[r] ? V::ld(c.grad + (size_t)rs[r] * D + k * VEC) : V::zero();
                     }
 #pragma unroll
@@ -743,8 +753,10 @@ struct AccumulatePush {
         i64 version, tver;
         i32 s;
         i32 upd0, upd;
-        u8 flags;
+        u32 mpos; // multi-GPU: slot in the owner's mailbox (batch section)
+        u8 flags, owner;
         bool dataless, pushed, local;
+        u8 pad[3];
     };
     CacheView c;
     const u64 *uniq;
@@ -781,13 +793,35 @@ struct AccumulatePush {
         }
         return lo < n_push && push_keys[lo] == key;
     }
+    __device__ MailboxSection outbox(int owner) const {
+        return mailbox_section(c.pv.out[owner], 0, c.pv.cap, c.width);
+    }
     __device__ bool begin(size_t u, u32 cnt, Ctx &x) const {
         x.s = uslot[u];
-        if (x.s < 0)
-            return false;
         const u64 key = uniq[u];
-        x.trow = key - c.row_begin;
-        x.local = x.trow < c.nrows_local;
+        x.owner = 0;
+        x.mpos = 0;
+        if (c.pv.world > 1) { // every line goes through the owner's mailbox, the local ones too:
+                              // the owner applies all sources in rank order
+            if (key >= c.table_len)
+                return false;
+            x.owner = (u8)owner_of(c.pv, key, x.trow);
+            x.mpos = (u32)u - c.pv.lo[x.owner];
+            x.local = false;
+            if (x.mpos >= c.pv.cap) {
+                atomicMax(&c.regs->error, (u32)E_MAILBOX);
+                return false;
+            }
+            if (x.s < 0) { // no line (the call already failed): the slot must still read "not pushed"
+                outbox(x.owner).upd[x.mpos] = 0;
+                return false;
+            }
+        } else {
+            if (x.s < 0)
+                return false;
+            x.trow = key - c.row_begin;
+            x.local = x.trow < c.nrows_local;
+        }
         x.upd0 = c.slot_updates[x.s];
         x.flags = c.slot_flags[x.s];
         x.version = c.slot_version[x.s];
@@ -821,12 +855,19 @@ struct AccumulatePush {
             V::st(c.data + o, a.d);
         if (x.pushed && x.local) // PSFhandle_embedding.cc:25-26: row += pushed grad
             V::st(c.trows + x.trow * c.width + k * VEC, V::add(a.t, a.g));
+        else if (x.pushed && c.pv.world > 1) // deposit the pushed gradient at the owner (NVLink store)
+            V::st(outbox(x.owner).grad + (size_t)x.mpos * c.width + k * VEC, a.g);
         if (!x.pushed || (defer_cleanup && !x.dataless))
             V::st(c.grad + o, a.g);
     }
     __device__ void end(const Ctx &x) const { // one thread per row
         if (!(x.flags & F_GRAD))
             c.slot_flags[x.s] = x.flags | F_GRAD;
+        if (c.pv.world > 1) {
+            const MailboxSection m = outbox(x.owner);
+            m.key[x.mpos] = x.trow;
+            m.upd[x.mpos] = x.pushed ? x.upd : 0; // 0 = slot not pushed this call
+        }
         if (x.pushed) {
             if (x.local)
                 c.tver[x.trow] = x.tver + x.upd; // PSFhandle_embedding.cc:24
@@ -881,6 +922,145 @@ struct FlushPending {
     }
 };
 
+
+// ---- multi-GPU exchange -----------------------------------------------------------------
+// lo[o] = first unique index whose key belongs to owner o: the sorted uniques split into
+// contiguous per-owner slices exactly as PSAgent splits them with lower_bound (PSAgent.h:541-559)
+__global__ void owner_bounds_kernel(CacheView c, const u64 *__restrict__ uniq,
+                                    const u32 *__restrict__ num_unique) {
+    const int o = threadIdx.x;
+    if (o > c.pv.world)
+        return;
+    const u32 U = *num_unique;
+    u32 lo = 0, hi = U;
+    {
+        // the last bound stops at the table length: keys beyond it (a failed call) have no owner
+        const u64 target = o == c.pv.world ? c.table_len : shard_begin(c.pv, o);
+        while (lo < hi) {
+            const u32 mid = (lo + hi) >> 1;
+            if (uniq[mid] < target)
+                lo = mid + 1;
+            else
+                hi = mid;
+        }
+    }
+    c.pv.lo[o] = lo;
+    if (o < c.pv.world)
+        c.pv.fl_count[o] = 0;
+}
+
+// Dirty victims go to their owner's "flush" section (one warp per line).
+template <int VEC>
+__global__ void __launch_bounds__(kRowBlock) flush_remote_kernel(CacheView c) {
+    using V = RowVec<VEC>;
+    const unsigned lane = lane_id();
+    const size_t warp_global = (size_t)blockIdx.x * kRowWarps + (threadIdx.x >> 5);
+    const size_t nwarps = (size_t)gridDim.x * kRowWarps;
+    const u32 count = c.regs->flushed;
+    const size_t D = c.width, nvec = D / VEC;
+    for (size_t e = warp_global; e < count; e += nwarps) {
+        const u32 s = c.pending_list[e];
+        i32 upd = c.slot_updates[s];
+        u64 trow;
+        int owner = 0;
+        if (c.slot_key[s] < c.table_len)
+            owner = owner_of(c.pv, c.slot_key[s], trow);
+        else
+            upd = 0;
+        // updates == 0: a line push_pull evicted right after pushing it; nothing to send
+        u32 pos = 0;
+        if (lane == 0 && upd != 0)
+            pos = atomicAdd(&c.pv.fl_count[owner], 1u);
+        pos = __shfl_sync(FULL, pos, 0);
+        if (upd != 0) {
+            if (pos < c.pv.cap) {
+                const MailboxSection m = mailbox_section(c.pv.out[owner], 1, c.pv.cap, D);
+                for (size_t k = lane; k < nvec; k += 32)
+                    V::st(m.grad + (size_t)pos * D + k * VEC, V::ld(c.grad + (size_t)s * D + k * VEC));
+                if (lane == 0) {
+                    m.key[pos] = trow;
+                    m.upd[pos] = upd;
+                }
+            } else if (lane == 0) {
+                atomicMax(&c.regs->error, (u32)E_MAILBOX);
+            }
+        }
+        if (lane == 0) {
+            c.slot_updates[s] = 0;
+            c.slot_state[s] = S_FREE;
+            c.free_stack[atomicAdd(&c.regs->free_top, 1u)] = s;
+        }
+    }
+}
+
+// Tell every owner how many slots of its two sections this rank filled.
+__global__ void publish_counts_kernel(CacheView c) {
+    const int o = threadIdx.x;
+    if (o >= c.pv.world)
+        return;
+    u32 *hdr = reinterpret_cast<u32 *>(c.pv.out[o]);
+    hdr[0] = c.pv.lo[o + 1] - c.pv.lo[o];
+    hdr[1] = min(c.pv.fl_count[o], c.pv.cap);
+}
+
+// Owner side (PSFhandle_embedding.cc:5-28): row += pushed grad; ver += updates, one section of
+// one source rank per launch — the launches walk the sources in rank order, so the order of the
+// adds on a row does not depend on timing.  A warp takes 32 slots, tests them lane-parallel and
+// applies the pushed ones ROWS at a time.
+template <int VEC, int ROWS>
+__global__ void __launch_bounds__(kRowBlock) apply_mailbox_kernel(CacheView c, int src, int section) {
+    using V = RowVec<VEC>;
+    const unsigned lane = lane_id();
+    const size_t warp_global = (size_t)blockIdx.x * kRowWarps + (threadIdx.x >> 5);
+    const size_t nwarps = (size_t)gridDim.x * kRowWarps;
+    const size_t D = c.width, nvec = D / VEC;
+    char *region = c.pv.in + (size_t)src * c.pv.region_bytes;
+    const u32 count = min(reinterpret_cast<const u32 *>(region)[section], c.pv.cap);
+    const MailboxSection mb = mailbox_section(region, section, c.pv.cap, D);
+    for (size_t base = warp_global * 32; base < count; base += nwarps * 32) {
+        const size_t i = base + lane;
+        i32 upd = 0;
+        u64 trow = 0;
+        if (i < count) {
+            upd = mb.upd[i];
+            trow = mb.key[i];
+            if (upd != 0 && trow < c.nrows_local)
+                c.tver[trow] += upd;
+            else
+                upd = 0;
+        }
+        unsigned m = __ballot_sync(FULL, upd != 0);
+        while (m) {
+            int from[ROWS];
+            u64 rt[ROWS];
+#pragma unroll
+            for (int r = 0; r < ROWS; r++) {
+                from[r] = m ? __ffs(m) - 1 : -1;
+                if (m)
+                    m &= m - 1;
+                rt[r] = __shfl_sync(FULL, trow, from[r] < 0 ? 0 : from[r]);
+            }
+            for (size_t k = lane; k < nvec; k += 32) {
+                typename V::T t[ROWS], g[ROWS];
+#pragma unroll
+                for (int r = 0; r < ROWS; r++)
+                    if (from[r] >= 0) {
+                        t[r] = V::ld(c.trows + rt[r] * D + k * VEC);
+                        g[r] = V::ld(mb.grad + (base + from[r]) * D + k * VEC);
+                    }
+#pragma unroll
+                for (int r = 0; r < ROWS; r++)
+                    if (from[r] >= 0)
+                        V::st(c.trows + rt[r] * D + k * VEC, V::add(t[r], g[r]));
+            }
+        }
+    }
+}
+
+__global__ void barrier_error_kernel(CacheRegs *r, const u32 *barrier_err) {
+    if (*barrier_err)
+        atomicMax(&r->error, (u32)E_BARRIER);
+}
 
 // dataless lines are dropped after the push (never inserted)
 __global__ void free_transient_kernel(CacheView c, const i32 *uslot, const u32 *miss_list, int batch,
@@ -1098,6 +1278,29 @@ struct Guard { // select the cache's device for the duration of a call
     }
 };
 
+// (Re)allocate this rank's mailboxes for `rows` slots per section and map every owner's.
+// Collective: every rank calls it with the same `rows`, in the same order.
+void setup_mailbox(hb_cache *c, size_t rows) {
+    PeerView &pv = c->view.pv;
+    if (c->mailbox) {
+        HB_CUDA(cudaDeviceSynchronize());
+        HB_CHECK(hb_comm_barrier() == 0, "barrier failed");
+        ipc_unshare(reinterpret_cast<void **>(c->peer_mailbox));
+        cudaFree(c->mailbox);
+        c->mailbox = nullptr;
+    }
+    pv.cap = (u32)rows;
+    pv.region_bytes = mailbox_region_bytes(rows, c->width);
+    HB_CUDA(cudaMalloc((void **)&c->mailbox, pv.region_bytes * pv.world));
+    HB_CUDA(cudaMemset(c->mailbox, 0, pv.region_bytes * pv.world));
+    c->mailbox_cap = rows;
+    ipc_share(c->mailbox, reinterpret_cast<void **>(c->peer_mailbox));
+    pv.in = c->mailbox;
+    for (int o = 0; o < pv.world; o++)
+        pv.out[o] = c->peer_mailbox[o] + (size_t)pv.rank * pv.region_bytes;
+    HB_CHECK(hb_comm_barrier() == 0, "barrier failed"); // every mailbox is zeroed and mapped
+}
+
 u64 *clk_of(hb_cache *c) {
     // four u64 right behind the perf record in the same device allocation
     return reinterpret_cast<u64 *>(reinterpret_cast<char *>(c->dev_record) + 64);
@@ -1294,11 +1497,39 @@ void run_insert(hb_cache *c, size_t n, int clk_stage) {
     HB_LAUNCHED();
 }
 
+// Multi-GPU: the pushes of this call sit in the owners' mailboxes.  Publish the slot counts,
+// meet the other ranks, apply what this rank received as an owner (sources in rank order: the
+// result does not depend on arrival order), meet again so that no rank reads a shard that is
+// still being updated.  All on the cache's stream, nothing synchronises with the host.
+void exchange_pushes(hb_cache *c) {
+    cudaStream_t st = c->stream;
+    const int world = c->view.pv.world;
+    publish_counts_kernel<<<1, 32, 0, st>>>(c->view);
+    HB_LAUNCHED();
+    device_barrier(st);
+    const int grid = sm_count() * 4;
+    for (int src = 0; src < world; src++)
+        for (int section = 0; section < 2; section++) {
+            if (c->width % 4 == 0)
+                apply_mailbox_kernel<4, 4><<<grid, kRowBlock, 0, st>>>(c->view, src, section);
+            else
+                apply_mailbox_kernel<1, 4><<<grid, kRowBlock, 0, st>>>(c->view, src, section);
+            HB_LAUNCHED();
+        }
+    device_barrier(st);
+    barrier_error_kernel<<<1, 1, 0, st>>>(c->view.regs, g_comm.barrier_err);
+    HB_LAUNCHED();
+}
+
 // accumulate + push of batch `batch`, then flush of pending victims, then drop dataless lines
 void run_accumulate(hb_cache *c, size_t n, int batch, const float *dev_grads, const u64 *dev_push_keys,
                     size_t n_push, bool use_plan, bool defer_cleanup = false) {
     cudaStream_t st = c->stream;
     KeyWorkspace &ws = c->ws[batch];
+    if (c->view.pv.world > 1) {
+        owner_bounds_kernel<<<1, 32, 0, st>>>(c->view, ws.uniq, ws.num_unique);
+        HB_LAUNCHED();
+    }
     if (n) {
         const u32 *p = c->sorted[batch].perm;
         const u64 *plan = use_plan ? dev_push_keys : nullptr;
@@ -1318,7 +1549,17 @@ void run_accumulate(hb_cache *c, size_t n, int batch, const float *dev_grads, co
         mark(c, 2);
     // pending victims (count is device-side; bound the grid with the host's upper bound)
     size_t pend = std::min<size_t>(c->pending_upper, c->view.capacity);
-    if (pend) {
+    if (c->view.pv.world > 1) {
+        if (pend) {
+            int grid = row_grid(pend);
+            if (c->width % 4 == 0)
+                flush_remote_kernel<4><<<grid, kRowBlock, 0, st>>>(c->view);
+            else
+                flush_remote_kernel<1><<<grid, kRowBlock, 0, st>>>(c->view);
+            HB_LAUNCHED();
+        }
+        exchange_pushes(c);
+    } else if (pend) {
         int grid = row_grid(pend);
         if (c->width % 4 == 0) {
             FlushPending<4> f{c->view, 0};
@@ -1416,6 +1657,10 @@ int hb_table_create(int node_id, size_t length, size_t width, int device, hb_tab
     dmalloc(t->ver, t->nrows);
     HB_CUDA(cudaMemset(t->rows, 0, std::max<size_t>(t->nrows * width, 1) * sizeof(float)));
     HB_CUDA(cudaMemset(t->ver, 0, std::max<size_t>(t->nrows, 1) * sizeof(i64)));
+    t->rank = rank;
+    t->world = world;
+    ipc_share(t->rows, reinterpret_cast<void **>(t->peer_rows));
+    ipc_share(t->ver, reinterpret_cast<void **>(t->peer_ver));
     g_tables[node_id] = t;
     if (out)
         *out = t;
@@ -1438,6 +1683,11 @@ int hb_table_destroy(hb_table *t) {
         g_tables.erase(t->node_id);
         Guard g(t->device);
         HB_CUDA(cudaDeviceSynchronize());
+        if (t->world > 1) {
+            hb_comm_barrier(); // every rank is done with every shard
+            ipc_unshare(reinterpret_cast<void **>(t->peer_rows));
+            ipc_unshare(reinterpret_cast<void **>(t->peer_ver));
+        }
         dfree(t->rows);
         dfree(t->ver);
         delete t;
@@ -1573,6 +1823,30 @@ int hb_cache_create(int policy, size_t limit, size_t length, size_t width, int n
     v.row_begin = t->row_begin;
     v.nrows_local = t->nrows;
     v.table_len = t->length;
+    PeerView &pv = v.pv;
+    std::memset(&pv, 0, sizeof(pv));
+    pv.world = t->world;
+    pv.rank = t->rank;
+    pv.per = t->length / t->world;
+    pv.rem = t->length % t->world;
+    for (int r = 0; r < kMaxWorld; r++) {
+        pv.rows[r] = t->peer_rows[r];
+        pv.ver[r] = t->peer_ver[r];
+    }
+    if (t->world == 1) {
+        pv.rows[0] = t->rows;
+        pv.ver[0] = t->ver;
+    }
+    dmalloc(pv.lo, kMaxWorld + 1);
+    dmalloc(pv.fl_count, kMaxWorld);
+    HB_CUDA(cudaMemset(pv.lo, 0, (kMaxWorld + 1) * sizeof(u32)));
+    HB_CUDA(cudaMemset(pv.fl_count, 0, kMaxWorld * sizeof(u32)));
+    if (t->world > 1) {
+        size_t rows = 1 << 18;
+        if (const char *e = getenv("HERALD_MAILBOX_ROWS"))
+            rows = std::max<size_t>(1024, strtoull(e, nullptr, 10));
+        setup_mailbox(c, rows);
+    }
     HB_CUDA(cudaMemset(v.ht, 0xff, hs * sizeof(HtEntry)));
     CacheRegs regs;
     std::memset(&regs, 0, sizeof(regs));
@@ -1624,6 +1898,13 @@ int hb_cache_destroy(hb_cache *c) {
         dfree(v.cand_slot);
         dfree(v.sel_hist);
         dfree(v.regs);
+        dfree(v.pv.lo);
+        dfree(v.pv.fl_count);
+        if (c->mailbox) {
+            hb_comm_barrier(); // nobody still writes into this rank's mailboxes
+            ipc_unshare(reinterpret_cast<void **>(c->peer_mailbox));
+            cudaFree(c->mailbox);
+        }
         for (int b = 0; b < 2; b++) {
             c->ws[b].release();
             dfree(c->uslot[b]);
@@ -1678,6 +1959,10 @@ int hb_cache_reserve(hb_cache *c, size_t max_keys) {
     HB_API_BEGIN();
     Guard g(c->device);
     ensure_batch(c, max_keys);
+    if (c->view.pv.world > 1 && max_keys > c->mailbox_cap) {
+        HB_CUDA(cudaStreamSynchronize(c->stream));
+        setup_mailbox(c, max_keys); // collective
+    }
     HB_API_END();
 }
 
@@ -1825,8 +2110,10 @@ int hb_cache_wait(hb_cache *c, hb_perf *perf) {
         if (r.error) {
             static const char *names[] = {"", "row store slack exhausted (too many transient/pending lines)",
                                           "cache index full", "key outside the table",
-                                          "pending-eviction list overflow"};
-            throw Error(std::string("device-side cache failure: ") + names[std::min<u32>(r.error, 4)]);
+                                          "pending-eviction list overflow",
+                                          "owner mailbox too small (hb_cache_reserve / HERALD_MAILBOX_ROWS)",
+                                          "a peer did not reach the exchange barrier"};
+            throw Error(std::string("device-side cache failure: ") + names[std::min<u32>(r.error, 6)]);
         }
     } else if (perf) {
         std::memset(perf, 0, sizeof(*perf));

@@ -8,6 +8,7 @@
 
 #include <vector>
 
+#include "hb_comm.cuh"
 #include "hb_common.cuh"
 #include "hb_sort.cuh"
 
@@ -18,6 +19,10 @@ struct hb_table {
     size_t row_begin = 0, nrows = 0; // rows owned by this rank
     float *rows = nullptr;           // [nrows, width]
     hb::i64 *ver = nullptr;          // [nrows]  (ps-lite/include/ps/server/param.h:124)
+    // every rank's shard mapped into this process (CUDA IPC over NVLink); [rank] = own shard
+    float *peer_rows[hb::kMaxWorld] = {};
+    hb::i64 *peer_ver[hb::kMaxWorld] = {};
+    int rank = 0, world = 1;
 };
 
 namespace hb {
@@ -60,8 +65,56 @@ enum : u32 {
     E_NO_FREE_SLOT = 1,  // transient + pending lines exceeded the slack of the row store
     E_INDEX_FULL = 2,    // open-addressing index could not place a key
     E_KEY_RANGE = 3,     // key >= table length
-    E_EVICT_OVERFLOW = 4 // pending-eviction list overflow
+    E_EVICT_OVERFLOW = 4, // pending-eviction list overflow
+    E_MAILBOX = 5,        // more pushed lines for one owner than its mailbox holds
+    E_BARRIER = 6         // a peer did not reach the exchange barrier
 };
+
+// ---- multi-GPU: owner shards and push mailboxes of the whole group, mapped over NVLink ----
+// Rank w's cache reads missing / stale rows straight out of the owner's shard (sync) and
+// deposits the lines it pushes into a mailbox inside the owner's memory; after a barrier the
+// owner applies the mailboxes in source-rank order (deterministic), see DESIGN.md section 6.
+// A mailbox region (one per source rank, inside each owner) holds two sections, "batch" (the
+// lines of the update call, one slot per unique key of the owner's range, upd == 0 = not
+// pushed) and "flush" (dirty victims), each {key[cap] (row inside the shard), upd[cap],
+// grad[cap, D]}, behind a 16-byte header {cnt_batch, cnt_flush}.
+struct PeerView {
+    int world, rank;
+    u64 per, rem;                 // AveragePartitioner: len / G rows each, the first len % G one more
+    const float *rows[kMaxWorld]; // owner shards (rows[rank] is local)
+    const i64 *ver[kMaxWorld];
+    char *out[kMaxWorld]; // this rank's region inside owner o
+    char *in;             // this rank's mailboxes as an owner: world regions, indexed by source
+    size_t region_bytes;
+    u32 cap;       // slots per section
+    u32 *lo;       // [world + 1] first unique index of each owner's key range (per call)
+    u32 *fl_count; // [world] flush slots taken per owner (per call)
+};
+
+struct MailboxSection {
+    u64 *key;
+    i32 *upd;
+    float *grad;
+};
+
+__host__ __device__ inline size_t align16(size_t x) {
+    return (x + 15) & ~(size_t)15;
+}
+__host__ __device__ inline size_t mailbox_section_bytes(size_t cap, size_t D) {
+    return align16(cap * 8) + align16(cap * 4) + align16(cap * D * 4);
+}
+__host__ __device__ inline size_t mailbox_region_bytes(size_t cap, size_t D) {
+    return 16 + 2 * mailbox_section_bytes(cap, D);
+}
+__host__ __device__ inline MailboxSection mailbox_section(char *region, int section, size_t cap,
+                                                          size_t D) {
+    char *p = region + 16 + (size_t)section * mailbox_section_bytes(cap, D);
+    MailboxSection m;
+    m.key = reinterpret_cast<u64 *>(p);
+    m.upd = reinterpret_cast<i32 *>(p + align16(cap * 8));
+    m.grad = reinterpret_cast<float *>(p + align16(cap * 8) + align16(cap * 4));
+    return m;
+}
 
 // Mutable scalars of one cache, resident in device memory (one cache line or two).
 struct CacheRegs {
@@ -131,7 +184,27 @@ struct CacheView {
     float *trows;
     i64 *tver;
     u64 row_begin, nrows_local, table_len;
+    PeerView pv; // pv.world == 1: single GPU, trows / tver are the whole table
 };
+
+#ifdef __CUDACC__
+// owner of a key and its row inside the owner's shard (ps-lite/include/ps/partitioner.h:46-57)
+__device__ __forceinline__ int owner_of(const PeerView &pv, u64 key, u64 &trow) {
+    const u64 cut = pv.rem * (pv.per + 1);
+    if (key < cut) {
+        const u64 o = key / (pv.per + 1);
+        trow = key - o * (pv.per + 1);
+        return (int)o;
+    }
+    const u64 o = pv.per ? (key - cut) / pv.per : 0;
+    trow = key - cut - o * pv.per;
+    return (int)(pv.rem + o);
+}
+__device__ __forceinline__ u64 shard_begin(const PeerView &pv, int o) {
+    const u64 uo = (u64)o;
+    return uo < pv.rem ? uo * (pv.per + 1) : pv.rem * (pv.per + 1) + (uo - pv.rem) * pv.per;
+}
+#endif
 
 // counters copied to pinned host memory at the end of every call
 struct PerfRecord {
@@ -183,4 +256,8 @@ struct hb_cache {
     size_t pending_upper = 0;
     int key_bits = 64;
     hb::u32 hot_threshold = 64; // segments longer than this take the column-split path
+    // multi-GPU
+    char *mailbox = nullptr;              // this rank's regions as an owner
+    char *peer_mailbox[hb::kMaxWorld] = {}; // every owner's regions, mapped
+    size_t mailbox_cap = 0;
 };

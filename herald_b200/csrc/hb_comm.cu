@@ -73,6 +73,80 @@ NcclApi &nccl() {
     return g_comm.api;
 }
 
+void ipc_share(void *local, void **peers) {
+    const int world = g_comm.world, rank = g_comm.rank;
+    for (int r = 0; r < kMaxWorld; r++)
+        peers[r] = nullptr;
+    peers[rank] = local;
+    if (world == 1)
+        return;
+    HB_CHECK(g_comm.comm, "group not initialised");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    cudaIpcMemHandle_t mine;
+    HB_CUDA(cudaIpcGetMemHandle(&mine, local));
+    char *dev = nullptr;
+    HB_CUDA(cudaMalloc((void **)&dev, 64 * (size_t)(world + 1)));
+    HB_CUDA(cudaMemcpy(dev, &mine, 64, cudaMemcpyHostToDevice));
+    nccl_check(nccl().AllGather(dev, dev + 64, 64, kNcclInt8, g_comm.comm, g_comm.stream),
+               "ncclAllGather(ipc handles)");
+    HB_CUDA(cudaStreamSynchronize(g_comm.stream));
+    std::vector<cudaIpcMemHandle_t> all(world);
+    HB_CUDA(cudaMemcpy(all.data(), dev + 64, 64 * (size_t)world, cudaMemcpyDeviceToHost));
+    cudaFree(dev);
+    for (int r = 0; r < world; r++) {
+        if (r == rank)
+            continue;
+        HB_CUDA(cudaIpcOpenMemHandle(&peers[r], all[r], cudaIpcMemLazyEnablePeerAccess));
+    }
+}
+
+void ipc_unshare(void **peers) {
+    for (int r = 0; r < kMaxWorld; r++) {
+        if (peers[r] && r != g_comm.rank)
+            cudaIpcCloseMemHandle(peers[r]);
+        peers[r] = nullptr;
+    }
+}
+
+namespace {
+struct PeerFlags {
+    u64 *peer[kMaxWorld];
+    u64 *local;
+};
+
+__global__ void peer_barrier_kernel(PeerFlags pf, int rank, int world, u64 epoch, u32 *err) {
+    const int r = threadIdx.x;
+    if (r >= world)
+        return;
+    __threadfence_system(); // everything this GPU wrote to peer memory before the barrier
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(pf.peer[r] + rank), "l"(epoch) : "memory");
+    const long long t0 = clock64();
+    u64 seen = 0;
+    while (true) {
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(pf.local + r) : "memory");
+        if (seen >= epoch)
+            break;
+        if (clock64() - t0 > 60000000000ll) { // ~30 s: a peer is gone; fail the call, do not hang
+            *err = 1;
+            break;
+        }
+    }
+}
+} // namespace
+
+void device_barrier(cudaStream_t st) {
+    if (g_comm.world == 1)
+        return;
+    PeerFlags pf;
+    for (int r = 0; r < kMaxWorld; r++)
+        pf.peer[r] = g_comm.peer_flags[r];
+    pf.local = g_comm.flags;
+    g_comm.epoch++;
+    peer_barrier_kernel<<<1, 32, 0, st>>>(pf, g_comm.rank, g_comm.world, g_comm.epoch,
+                                          g_comm.barrier_err);
+    HB_LAUNCHED();
+}
+
 } // namespace hb
 
 using namespace hb;
@@ -102,6 +176,12 @@ int hb_comm_init(const void *id128, int rank, int world, int device) {
         HB_CUDA(cudaStreamCreateWithFlags(&g_comm.stream, cudaStreamNonBlocking));
         HB_CUDA(cudaMalloc((void **)&g_comm.scratch, 256));
         HB_CUDA(cudaMemset(g_comm.scratch, 0, 256));
+        HB_CHECK(world <= kMaxWorld, "at most 8 ranks (one NVSwitch domain)");
+        HB_CUDA(cudaMalloc((void **)&g_comm.flags, 256));
+        HB_CUDA(cudaMemset(g_comm.flags, 0, 256));
+        g_comm.barrier_err = reinterpret_cast<u32 *>(g_comm.flags + 16);
+        g_comm.epoch = 0;
+        ipc_share(g_comm.flags, reinterpret_cast<void **>(g_comm.peer_flags));
     }
     HB_API_END();
 }
@@ -129,7 +209,11 @@ int hb_comm_barrier(void) {
 int hb_comm_finalize(void) {
     HB_API_BEGIN();
     if (g_comm.comm) {
-        cudaStreamSynchronize(g_comm.stream);
+        cudaDeviceSynchronize();
+        hb_comm_barrier(); // nobody still reads or writes a peer's memory
+        ipc_unshare(reinterpret_cast<void **>(g_comm.peer_flags));
+        cudaFree(g_comm.flags);
+        g_comm.flags = nullptr;
         nccl().CommDestroy(g_comm.comm);
         g_comm.comm = nullptr;
         cudaStreamDestroy(g_comm.stream);

@@ -111,6 +111,27 @@ class WorkerCommunicate(object):
         pass
 
 
+_LIB.hb_comm_unique_id.argtypes = [ctypes.c_char_p]
+_LIB.hb_comm_init.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+
+
+def group_init(rank, world, device, exchange):
+    """Bring up the multi-GPU group (one process per GPU of one NVSwitch box).  `exchange(b)`
+    broadcasts rank 0's 128 bytes to every rank — any rendezvous the launcher has: the bench and
+    the tests use torch.distributed (gloo) for it; nothing else of torch is involved.  Tables and
+    caches created afterwards are sharded / exchange over NVLink; their create / reserve /
+    update / destroy calls are collective (same order on every rank)."""
+    idbuf = ctypes.create_string_buffer(128)
+    if rank == 0:
+        check_call(_LIB.hb_comm_unique_id(idbuf))
+    uid = exchange(bytes(idbuf.raw))
+    check_call(_LIB.hb_comm_init(uid, int(rank), int(world), int(device)))
+
+
+def group_finalize():
+    check_call(_LIB.hb_comm_finalize())
+
+
 _comm = None
 
 
