@@ -394,6 +394,7 @@ __global__ void __launch_bounds__(256)
     r->need_min = 0;
     r->nv = 0;
     r->nc = 0;
+    r->sel_done = 0;
     r->min_use = 0xffffffffu;
     r->min_prio = ~0ull;
     const u64 now = *clk_in;
@@ -403,32 +404,6 @@ __global__ void __launch_bounds__(256)
     const u64 span = now > r->floor ? now - r->floor : 1; // stamp offsets 0 .. span-1
     const int bits = span > 1 ? 64 - __clzll((long long)(span - 1)) : 0;
     r->sel_shift = bits > kSelBits ? (u32)(bits - kSelBits) : 0;
-}
-
-__global__ void __launch_bounds__(256) sel_hist_kernel(CacheView c) {
-    const CacheRegs *r = c.regs;
-    if (r->E == 0)
-        return;
-    __shared__ u32 sh[kSelBins];
-    for (int b = threadIdx.x; b < kSelBins; b += blockDim.x)
-        sh[b] = 0;
-    __syncthreads();
-    const u64 floor = r->floor;
-    const u32 shift = r->sel_shift;
-    const u64 cls = (u64)class_use_of(c.policy);
-    const size_t hw = r->slot_hw;
-    for (size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x; s < hw;
-         s += (size_t)gridDim.x * blockDim.x) {
-        const u64 p = c.slot_prio[s];
-        if (p != PRIO_NONE && (p >> kStampBits) == cls) {
-            u64 bin = ((p & kStampMask) - floor) >> shift;
-            atomicAdd(&sh[min(bin, (u64)(kSelBins - 1))], 1u);
-        }
-    }
-    __syncthreads();
-    for (int b = threadIdx.x; b < kSelBins; b += blockDim.x)
-        if (sh[b])
-            atomicAdd(&c.sel_hist[b], sh[b]);
 }
 
 // Block-wide: exclusive prefix of sh[0..kSelBins) in place; returns total.  blockDim.x == 256.
@@ -462,23 +437,51 @@ __device__ __forceinline__ u32 block_scan_bins(u32 *sh) {
     return total;
 }
 
-__global__ void __launch_bounds__(256) sel_collect_kernel(CacheView c) {
+// Level-one histogram of the victim class over [floor, now).  The block that adds its bins last
+// scans the finished histogram ONCE and leaves the selection plan in the registers: threshold bin,
+// victims to take inside it, and the closed-form corner cases of DESIGN.md 4.3.
+__global__ void __launch_bounds__(256) sel_hist_kernel(CacheView c) {
     CacheRegs *r = c.regs;
     const u32 E = r->E;
     if (E == 0)
         return;
     __shared__ u32 sh[kSelBins];
-    __shared__ u32 s_bin, s_kold;
+    __shared__ u32 s_bin;
+    __shared__ bool s_last;
     for (int b = threadIdx.x; b < kSelBins; b += blockDim.x)
-        sh[b] = c.sel_hist[b];
+        sh[b] = 0;
+    __syncthreads();
+    const u64 floor = r->floor;
+    const u32 shift = r->sel_shift;
+    const u64 cls = (u64)class_use_of(c.policy);
+    const size_t hw = r->slot_hw;
+    for (size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x; s < hw;
+         s += (size_t)gridDim.x * blockDim.x) {
+        const u64 p = c.slot_prio[s];
+        if (p != PRIO_NONE && (p >> kStampBits) == cls) {
+            u64 bin = ((p & kStampMask) - floor) >> shift;
+            atomicAdd(&sh[min(bin, (u64)(kSelBins - 1))], 1u);
+        }
+    }
+    __syncthreads();
+    for (int b = threadIdx.x; b < kSelBins; b += blockDim.x)
+        if (sh[b])
+            atomicAdd(&c.sel_hist[b], sh[b]);
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0)
+        s_last = atomicAdd(&r->sel_done, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!s_last)
+        return;
+    __threadfence();
+    for (int b = threadIdx.x; b < kSelBins; b += blockDim.x)
+        sh[b] = __ldcg(&c.sel_hist[b]);
+    if (threadIdx.x == 0)
+        s_bin = 0;
     __syncthreads();
     const u32 class_count = block_scan_bins(sh); // sh = exclusive prefix
     const u32 k_old = min(E, class_count);
-    if (threadIdx.x == 0) {
-        s_kold = k_old;
-        s_bin = 0;
-    }
-    __syncthreads();
     // threshold bin: the last bin whose exclusive prefix is < k_old (k_old > 0)
     if (k_old > 0) {
         for (int b = threadIdx.x; b < kSelBins; b += blockDim.x) {
@@ -489,8 +492,8 @@ __global__ void __launch_bounds__(256) sel_collect_kernel(CacheView c) {
         }
     }
     __syncthreads();
-    const u32 bstar = s_bin;
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
+    if (threadIdx.x == 0) {
+        const u32 bstar = s_bin;
         const u32 M = r->M, size_old = r->size;
         const u32 extra = E - k_old;
         u32 n_drop = 0, need_min = 0;
@@ -518,34 +521,75 @@ __global__ void __launch_bounds__(256) sel_collect_kernel(CacheView c) {
         r->sel_bin = bstar;
         r->sel_rem = k_old > 0 ? k_old - sh[bstar] : 0;
     }
-    if (k_old == 0)
+}
+
+// Second sweep over the slot priorities: everything below the threshold bin is a victim, the
+// threshold bin's lines become candidates for sel_refine_kernel.  Both lists are gathered in
+// shared memory and appended with ONE global atomic per block and flush (the victims of a
+// steady-state batch are a few per cent of the slots, so a per-warp append would put tens of
+// thousands of atomics on one address).
+constexpr int kCollectCap = 1024;
+
+__global__ void __launch_bounds__(256) sel_collect_kernel(CacheView c) {
+    CacheRegs *r = c.regs;
+    if (r->E == 0 || r->k_old == 0)
         return;
+    __shared__ u32 s_vic[kCollectCap];
+    __shared__ u32 s_cslot[kCollectCap];
+    __shared__ u64 s_cprio[kCollectCap];
+    __shared__ u32 s_nv, s_nc, s_vbase, s_cbase;
+    if (threadIdx.x == 0) {
+        s_nv = 0;
+        s_nc = 0;
+    }
+    __syncthreads();
+    const u32 bstar = r->sel_bin;
     const u64 floor = r->floor;
     const u32 shift = r->sel_shift;
     const u64 cls = (u64)class_use_of(c.policy);
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     const size_t hw = r->slot_hw;
     const size_t rounds = (hw + stride - 1) / stride;
-    for (size_t it = 0; it < rounds; it++) {
-        const size_t s = it * stride + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-        bool victim = false, cand = false;
-        u64 p = 0;
-        if (s < hw) {
-            p = c.slot_prio[s];
-            if (p != PRIO_NONE && (p >> kStampBits) == cls) {
-                u64 bin = min(((p & kStampMask) - floor) >> shift, (u64)(kSelBins - 1));
-                victim = bin < bstar;
-                cand = bin == bstar;
+    for (size_t it = 0; it <= rounds; it++) {
+        if (it < rounds) {
+            const size_t s = it * stride + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+            if (s < hw) {
+                const u64 p = c.slot_prio[s];
+                if (p != PRIO_NONE && (p >> kStampBits) == cls) {
+                    const u64 bin = min(((p & kStampMask) - floor) >> shift, (u64)(kSelBins - 1));
+                    if (bin < bstar) {
+                        s_vic[atomicAdd(&s_nv, 1u)] = (u32)s;
+                    } else if (bin == bstar) {
+                        const u32 k = atomicAdd(&s_nc, 1u);
+                        s_cprio[k] = p & kStampMask;
+                        s_cslot[k] = (u32)s;
+                    }
+                }
             }
         }
-        u32 vpos = warp_append(&r->nv, victim);
-        if (victim)
-            c.victims[vpos] = (u32)s;
-        u32 cpos = warp_append(&r->nc, cand);
-        if (cand) {
-            c.cand_prio[cpos] = p & kStampMask;
-            c.cand_slot[cpos] = (u32)s;
+        __syncthreads();
+        // block-uniform: flush when the next round could overflow a list, and after the last round
+        const u32 nv = s_nv, nc = s_nc;
+        const bool last = it == rounds;
+        if (last || nv + 256 > kCollectCap || nc + 256 > kCollectCap) {
+            if (threadIdx.x == 0) {
+                s_vbase = nv ? atomicAdd(&r->nv, nv) : 0;
+                s_cbase = nc ? atomicAdd(&r->nc, nc) : 0;
+            }
+            __syncthreads();
+            for (u32 k = threadIdx.x; k < nv; k += blockDim.x)
+                c.victims[s_vbase + k] = s_vic[k];
+            for (u32 k = threadIdx.x; k < nc; k += blockDim.x) {
+                c.cand_prio[s_cbase + k] = s_cprio[k];
+                c.cand_slot[s_cbase + k] = s_cslot[k];
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                s_nv = 0;
+                s_nc = 0;
+            }
         }
+        __syncthreads();
     }
 }
 

@@ -151,7 +151,8 @@ struct CacheRegs {
     u64 min_prio;
     u64 ins_clock0; // stamps of inserted lines start here
     // second batch of a push_pull call
-    u32 U2, M2, alloc_base2, pad2;
+    u32 U2, M2, alloc_base2;
+    u32 sel_done; // blocks of sel_hist_kernel that have added their bins (zeroed by plan_insert)
 };
 
 // Everything a kernel needs to address the cache (passed by value).

@@ -272,6 +272,110 @@ struct ScatterRows {
     }
 };
 
+
+// ---- Lamb (src/ops/OptimizersSparse.cu:538-721) ------------------------------------------
+// The reference gathers the indexed rows, takes their L2 norm with cuDNN, writes the Adam
+// direction, takes its norm, then applies the trust ratio.  Here: one warp per listed row
+// computes the direction, updates m / v and leaves the row's two sums of squares (fixed lane
+// order); one block folds the per-row sums in a fixed order (run-to-run identical, unlike a
+// cuDNN tree whose shape depends on the library version); one warp per row applies the step.
+__global__ void __launch_bounds__(kRowBlock)
+    lamb_direction_kernel(const float *__restrict__ ids, const float *__restrict__ grads,
+                          const float *__restrict__ param, float *__restrict__ m,
+                          float *__restrict__ v, float *__restrict__ update,
+                          float *__restrict__ row_sq, size_t n, size_t D, AdamScalars s) {
+    const unsigned lane = lane_id();
+    const size_t warp_global = (size_t)blockIdx.x * kRowWarps + (threadIdx.x >> 5);
+    const size_t nwarps = (size_t)gridDim.x * kRowWarps;
+    for (size_t r = warp_global; r < n; r += nwarps) {
+        const size_t row = (size_t)(int)ids[r];
+        float sp = 0.f, su = 0.f;
+        for (size_t c = lane; c < D; c += 32) {
+            const size_t o = row * D + c;
+            const float g = grads[r * D + c], p = param[o];
+            float cur_m = s.beta1 * m[o] + (1 - s.beta1) * g; // :566-573
+            float cur_v = s.beta2 * v[o] + (1 - s.beta2) * g * g;
+            m[o] = cur_m;
+            v[o] = cur_v;
+            cur_m /= (1 - s.beta1t);
+            cur_v /= (1 - s.beta2t);
+            const float u = cur_m / (sqrtf(cur_v) + s.eps);
+            update[r * D + c] = u;
+            sp += p * p;
+            su += u * u;
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            sp += __shfl_xor_sync(FULL, sp, d);
+            su += __shfl_xor_sync(FULL, su, d);
+        }
+        if (lane == 0) {
+            row_sq[2 * r] = sp;
+            row_sq[2 * r + 1] = su;
+        }
+    }
+}
+
+// norms[0] = ||param[ids]||_2, norms[1] = ||update||_2 (CUDNN_REDUCE_TENSOR_NORM2, :667-699)
+__global__ void __launch_bounds__(1024) lamb_norms_kernel(const float *__restrict__ row_sq, size_t n,
+                                                          float *norms) {
+    __shared__ double sh[2][1024];
+    double sp = 0.0, su = 0.0;
+    for (size_t r = threadIdx.x; r < n; r += 1024) {
+        sp += row_sq[2 * r];
+        su += row_sq[2 * r + 1];
+    }
+    sh[0][threadIdx.x] = sp;
+    sh[1][threadIdx.x] = su;
+    __syncthreads();
+    for (int d = 512; d > 0; d >>= 1) {
+        if ((int)threadIdx.x < d) {
+            sh[0][threadIdx.x] += sh[0][threadIdx.x + d];
+            sh[1][threadIdx.x] += sh[1][threadIdx.x + d];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        norms[0] = (float)sqrt(sh[0][0]);
+        norms[1] = (float)sqrt(sh[1][0]);
+    }
+}
+
+__global__ void __launch_bounds__(kRowBlock)
+    lamb_step_kernel(const float *__restrict__ ids, const float *__restrict__ update,
+                     float *__restrict__ param, const float *__restrict__ norms, size_t n, size_t D,
+                     float lr, float weight_decay) {
+    const unsigned lane = lane_id();
+    const size_t warp_global = (size_t)blockIdx.x * kRowWarps + (threadIdx.x >> 5);
+    const size_t nwarps = (size_t)gridDim.x * kRowWarps;
+    const float n0 = norms[0], n1 = norms[1];
+    for (size_t r = warp_global; r < n; r += nwarps) {
+        const size_t row = (size_t)(int)ids[r];
+        for (size_t c = lane; c < D; c += 32) {
+            const size_t o = row * D + c;
+            const float p = param[o]; // :592
+            param[o] = p - lr * (n0 / n1) * (update[r * D + c] + weight_decay * p);
+        }
+    }
+}
+
+// per-stream float scratch for ops that need an intermediate of the gradient's size
+std::map<cudaStream_t, std::pair<float *, size_t>> g_scratch;
+float *float_scratch(cudaStream_t st, size_t count) {
+    std::lock_guard<std::mutex> lock(g_ws_mtx);
+    auto &e = g_scratch[st];
+    if (count > e.second) {
+        HB_CUDA(cudaStreamSynchronize(st));
+        if (e.first)
+            cudaFree(e.first);
+        e.first = nullptr;
+        size_t cap = std::max<size_t>(count, 1 << 16);
+        HB_CUDA(cudaMalloc((void **)&e.first, cap * sizeof(float)));
+        e.second = cap;
+    }
+    return e.first;
+}
+
 __global__ void momentum_second_phase(float *param, float *veloc, float momentum, bool nesterov,
                                       size_t size) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -502,6 +606,36 @@ int AdamWOptimizerSparseUpdate(DLArrayHandle param, const DLArrayHandle grad_ind
                                DLStreamHandle stream_handle) {
     AdamScalars s{lr, beta1, beta2, beta1t, beta2t, eps, weight_decay, true};
     return adam_rows(param, grad_indices, grad_values, expavg, expavgsq, s, stream_handle);
+}
+
+int LambOptimizerSparseUpdate(DLArrayHandle param, const DLArrayHandle grad_indices,
+                              const DLArrayHandle grad_values, DLArrayHandle expavg,
+                              DLArrayHandle expavgsq, float lr, float beta1, float beta2,
+                              float beta1t, float beta2t, float eps, float weight_decay,
+                              DLStreamHandle stream_handle) {
+    HB_API_BEGIN();
+    cudaStream_t st = stream_of(stream_handle);
+    size_t D = (size_t)param->shape[1], n = numel(grad_indices);
+    HB_CHECK(numel(grad_values) == n * D, "grad_values shape must be indices.shape + [width]");
+    if (n) {
+        AdamScalars s{lr, beta1, beta2, beta1t, beta2t, eps, weight_decay, true};
+        const float *ids = (const float *)grad_indices->data;
+        float *p = (float *)param->data;
+        // scratch: update [n, D], per-row sums [n, 2], norms [2]
+        float *scratch = float_scratch(st, n * D + 2 * n + 2);
+        float *update = scratch, *row_sq = scratch + n * D, *norms = row_sq + 2 * n;
+        int grid = row_grid(n);
+        lamb_direction_kernel<<<grid, kRowBlock, 0, st>>>(ids, (const float *)grad_values->data, p,
+                                                          (float *)expavg->data,
+                                                          (float *)expavgsq->data, update, row_sq, n,
+                                                          D, s);
+        HB_LAUNCHED();
+        lamb_norms_kernel<<<1, 1024, 0, st>>>(row_sq, n, norms);
+        HB_LAUNCHED();
+        lamb_step_kernel<<<grid, kRowBlock, 0, st>>>(ids, update, p, norms, n, D, lr, weight_decay);
+        HB_LAUNCHED();
+    }
+    HB_API_END();
 }
 
 int HBUniqueIndexedSlices(const DLArrayHandle ids, DLArrayHandle unique_ids, DLArrayHandle inverse,

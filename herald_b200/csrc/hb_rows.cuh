@@ -138,9 +138,27 @@ __global__ void __launch_bounds__(kRowBlock)
 //     time: the metadata of all 32 is loaded lane-parallel, then the row / gradient / owner-row
 //     loads of ROWS segments are in flight together (128-bit per lane) before the first add.
 constexpr int kHotTileRows = 128; // occurrences per pipeline stage
-constexpr int kHotStages = 4;     // 4 x 128 x 128 B = 64 KB of dynamic shared memory
-constexpr int kHotSmemBytes = kHotStages * kHotTileRows * 32 * 4;
+constexpr int kHotStagesDefault = 6; // 6 x 128 x 128 B = 96 KB of dynamic shared memory (x 2 CTAs/SM)
+constexpr int kHotStagesMax = 12;
+constexpr int kHotStageBytes = kHotTileRows * 32 * 4;
 constexpr u32 kVeryHot = 1024; // rows above this go first (longest-processing-time-first)
+
+// ring depth of the hot phase ($HERALD_HOT_STAGES, 3 .. 12): the bytes a CTA keeps in flight are
+// (stages - 1) x 16 KB, which is what hides HBM latency under the dependent add chain
+int hot_stages();
+
+// optional per-CTA timeline of the last segment_reduce launch (diagnostics, HBSegTraceEnable):
+// [0] = grid, [1] = hot items; then 4 words per CTA {start, hot phase end, end, items taken};
+// then 3 words per hot item {start, end, occurrences} for the first kTraceItems items
+constexpr u32 kTraceCtas = 2048, kTraceItems = 1024;
+constexpr size_t kTraceWords = 2 + 4 * (size_t)kTraceCtas + 3 * (size_t)kTraceItems;
+u64 *seg_trace_buffer(); // null unless enabled
+
+__device__ __forceinline__ u64 global_timer_ns() {
+    u64 t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 
 // broadcast a trivially copyable struct from lane `src` (32 bits at a time)
 template <class T>
@@ -165,6 +183,8 @@ struct HotLists {
     u32 *done_b;   // [cap] same for the hot list
     u32 *ctrl;     // [0] = #very_hot, [1] = #hot, [2] = hot ticket, [3] = cold ticket (zeroed with
                    // the scan arena)
+    u64 *trace;    // diagnostics timeline or null
+    int stages;    // ring depth of the hot phase
 };
 
 __device__ __forceinline__ u32 rows_warp_append(u32 *counter, bool pred) {
@@ -228,8 +248,16 @@ __global__ void __launch_bounds__(kRowBlock, 2)
     segment_reduce_kernel(const u32 *__restrict__ seg_start, const u32 *__restrict__ perm,
                           const u32 *__restrict__ num_unique, const float *__restrict__ vals,
                           size_t D, u32 hot_threshold, HotLists hl, FV fv, F1 f1) {
-    extern __shared__ __align__(16) float s_ring[]; // [kHotStages][kHotTileRows][32]
+    extern __shared__ __align__(16) float s_ring[]; // [stages][kHotTileRows][32]
     __shared__ u32 s_item;
+    const u32 S = (u32)hl.stages;
+    u64 *const trace = hl.trace;
+    u32 items_taken = 0;
+    if (trace && threadIdx.x == 0 && blockIdx.x < kTraceCtas) {
+        trace[2 + 4 * blockIdx.x] = global_timer_ns();
+        if (blockIdx.x == 0)
+            trace[0] = gridDim.x;
+    }
     using V = RowVec<VEC>;
     constexpr bool WIDE = VEC == 4; // rows are 16 B aligned and D % 4 == 0
     const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
@@ -250,6 +278,9 @@ __global__ void __launch_bounds__(kRowBlock, 2)
             const u32 t = s_item;
             if (t >= total)
                 break;
+            items_taken++;
+            if (trace && threadIdx.x == 0 && t < kTraceItems)
+                trace[2 + 4 * (size_t)kTraceCtas + 3 * t] = global_timer_ns();
             const u32 h = t / Q, q = t % Q;
             const u32 u = h < nA ? hl.very_hot[h] : hl.hot[h - nA];
             u32 *done = h < nA ? &hl.done_a[h] : &hl.done_b[h - nA];
@@ -282,8 +313,11 @@ __global__ void __launch_bounds__(kRowBlock, 2)
                         pv[j] = (tile < ntiles && p < s1) ? perm[p] : 0xffffffffu;
                     }
                 };
+                u32 issue_slot = 0; // tile % S of the next tile to issue, kept without a division
                 auto issue = [&](u32 tile) {
-                    float *stage = s_ring + (size_t)(tile % kHotStages) * kHotTileRows * 32;
+                    float *stage = s_ring + (size_t)issue_slot * kHotTileRows * 32;
+                    issue_slot = issue_slot + 1 == S ? 0 : issue_slot + 1;
+                    (void)tile;
 #pragma unroll
                     for (int j = 0; j < CPT; j++) {
                         const u32 row = my_row + (WIDE ? 32 * j : j);
@@ -297,32 +331,59 @@ __global__ void __launch_bounds__(kRowBlock, 2)
                     cp_async_commit();
                 };
 #pragma unroll 1
-                for (u32 k = 0; k < kHotStages - 1; k++) {
+                for (u32 k = 0; k < S - 1; k++) {
                     load_perm(k);
                     issue(k);
                 }
-                load_perm(kHotStages - 1);
+                load_perm(S - 1);
+                u32 read_slot = 0;
                 for (u32 k = 0; k < ntiles; k++) {
-                    cp_async_wait<kHotStages - 2>(); // this thread's part of stage k has landed
-                    __syncthreads(); // ... everyone's has; and stage k-1 has been consumed
-                    issue(k + kHotStages - 1);
-                    load_perm(k + kHotStages);
-                    if (warp == 0 && active) {
-                        const float *stage = s_ring + (size_t)(k % kHotStages) * kHotTileRows * 32 + lane;
-                        const u32 rows = min((u32)kHotTileRows, cnt - k * kHotTileRows);
-                        u32 r = 0;
-                        for (; r + 16 <= rows; r += 16) {
-                            float g[16];
-#pragma unroll
-                            for (int j = 0; j < 16; j++)
-                                g[j] = stage[(r + j) * 32];
-#pragma unroll
-                            for (int j = 0; j < 16; j++)
-                                acc = f1.step(acc, g[j]);
-                        }
-                        for (; r < rows; r++)
-                            acc = f1.step(acc, stage[r * 32]);
+                    // groups are committed one per tile, in order: at most S - 2 newer than tile k
+                    // may still be pending (wait_group takes an immediate, so the depth is switched)
+                    switch (S) {
+                    case 3: cp_async_wait<1>(); break;
+                    case 4: cp_async_wait<2>(); break;
+                    case 5: cp_async_wait<3>(); break;
+                    case 6: cp_async_wait<4>(); break;
+                    case 7: cp_async_wait<5>(); break;
+                    case 8: cp_async_wait<6>(); break;
+                    case 9: cp_async_wait<7>(); break;
+                    case 10: cp_async_wait<8>(); break;
+                    case 11: cp_async_wait<9>(); break;
+                    default: cp_async_wait<10>(); break;
                     }
+                    __syncthreads(); // ... everyone's has; and stage k-1 has been consumed
+                    issue(k + S - 1);
+                    load_perm(k + S);
+                    if (warp == 0 && active) {
+                        const float *stage = s_ring + (size_t)read_slot * kHotTileRows * 32 + lane;
+                        const u32 rows = min((u32)kHotTileRows, cnt - k * kHotTileRows);
+                        if (rows == kHotTileRows) {
+                            // full tile: completely unrolled, so the shared-memory loads run ahead
+                            // of the dependent adds as far as the register file allows
+                            float g[kHotTileRows];
+#pragma unroll
+                            for (int j = 0; j < kHotTileRows; j++)
+                                g[j] = stage[j * 32];
+#pragma unroll
+                            for (int j = 0; j < kHotTileRows; j++)
+                                acc = f1.step(acc, g[j]);
+                        } else {
+                            u32 r = 0;
+                            for (; r + 16 <= rows; r += 16) {
+                                float g[16];
+#pragma unroll
+                                for (int j = 0; j < 16; j++)
+                                    g[j] = stage[(r + j) * 32];
+#pragma unroll
+                                for (int j = 0; j < 16; j++)
+                                    acc = f1.step(acc, g[j]);
+                            }
+                            for (; r < rows; r++)
+                                acc = f1.step(acc, stage[r * 32]);
+                        }
+                    }
+                    read_slot = read_slot + 1 == S ? 0 : read_slot + 1;
                 }
                 cp_async_wait<0>();
                 if (warp == 0 && active)
@@ -342,7 +403,17 @@ __global__ void __launch_bounds__(kRowBlock, 2)
                     f1.end(ctx);
                 }
             }
+            if (trace && threadIdx.x == 0 && t < kTraceItems) {
+                trace[2 + 4 * (size_t)kTraceCtas + 3 * t + 1] = global_timer_ns();
+                trace[2 + 4 * (size_t)kTraceCtas + 3 * t + 2] = cnt;
+            }
         }
+        if (trace && threadIdx.x == 0 && blockIdx.x == 0)
+            trace[1] = total;
+    }
+    if (trace && threadIdx.x == 0 && blockIdx.x < kTraceCtas) {
+        trace[2 + 4 * blockIdx.x + 1] = global_timer_ns();
+        trace[2 + 4 * blockIdx.x + 3] = items_taken;
     }
 
     // ------------------------------- cold phase ------------------------------------------
@@ -431,6 +502,11 @@ __global__ void __launch_bounds__(kRowBlock, 2)
         }
         if (my_ok)
             fv.end(my_ctx);
+    }
+    if (trace && blockIdx.x < kTraceCtas) {
+        __syncthreads();
+        if (threadIdx.x == 0)
+            trace[2 + 4 * blockIdx.x + 2] = global_timer_ns();
     }
     fv.kernel_end();
 }

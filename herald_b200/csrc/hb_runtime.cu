@@ -7,7 +7,7 @@
 
 #include <algorithm>
 
-#include "hb_common.cuh"
+#include "hb_rows.cuh"
 
 namespace hb {
 
@@ -28,6 +28,21 @@ u32 default_hot_threshold() {
         g_hot_threshold.store(t);
     }
     return t;
+}
+
+int hot_stages() {
+    static const int stages = [] {
+        const char *e = getenv("HERALD_HOT_STAGES");
+        int v = e ? atoi(e) : kHotStagesDefault;
+        return std::min(std::max(v, 3), kHotStagesMax);
+    }();
+    return stages;
+}
+
+static std::atomic<u64 *> g_seg_trace{nullptr};
+
+u64 *seg_trace_buffer() {
+    return g_seg_trace.load(std::memory_order_relaxed);
 }
 
 int sm_count() {
@@ -70,6 +85,31 @@ const char *HBVersion(void) {
 
 uint64_t HBKernelLaunchCount(void) {
     return g_launches.load();
+}
+
+int HBSegTraceEnable(int on) {
+    HB_API_BEGIN();
+    u64 *cur = g_seg_trace.load();
+    if (on && !cur) {
+        u64 *buf = nullptr;
+        HB_CUDA(cudaMalloc((void **)&buf, kTraceWords * sizeof(u64)));
+        HB_CUDA(cudaMemset(buf, 0, kTraceWords * sizeof(u64)));
+        g_seg_trace.store(buf);
+    } else if (!on && cur) {
+        g_seg_trace.store(nullptr);
+        HB_CUDA(cudaDeviceSynchronize());
+        cudaFree(cur);
+    }
+    HB_API_END();
+}
+
+int HBSegTraceRead(unsigned long long *out, size_t words) {
+    HB_API_BEGIN();
+    u64 *cur = g_seg_trace.load();
+    HB_CHECK(cur != nullptr, "segment trace is not enabled");
+    HB_CUDA(cudaDeviceSynchronize());
+    HB_CUDA(cudaMemcpy(out, cur, std::min(words, kTraceWords) * sizeof(u64), cudaMemcpyDeviceToHost));
+    HB_API_END();
 }
 
 int HBSetHotThreshold(unsigned rows) {

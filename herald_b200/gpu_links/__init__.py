@@ -116,3 +116,18 @@ def adamw_update(param, grad, expavg, expavgsq, lr, beta1, beta2, beta1t, beta2t
         ctypes.c_float(lr), ctypes.c_float(beta1), ctypes.c_float(beta2), ctypes.c_float(beta1t),
         ctypes.c_float(beta2t), ctypes.c_float(eps), ctypes.c_float(weight_decay), _s(stream)))
     g.free_deduplicate()
+
+
+def lamb_update(param, grad, expavg, expavgsq, lr, beta1, beta2, beta1t, beta2t, eps,
+                weight_decay, stream=None):
+    """python/hetu/gpu_links/OptimizerLink.py:102-116 (sparse branch)."""
+    if not isinstance(grad, _nd.IndexedSlices):
+        raise NotImplementedError("dense optimizer updates are outside the embedding hot path")
+    grad.deduplicate(stream)
+    g = _sparse(grad)
+    check_call(_LIB.LambOptimizerSparseUpdate(
+        param.handle, g.indices.handle, g.values.handle, expavg.handle, expavgsq.handle,
+        ctypes.c_float(lr), ctypes.c_float(beta1), ctypes.c_float(beta2), ctypes.c_float(beta1t),
+        ctypes.c_float(beta2t), ctypes.c_float(eps), ctypes.c_float(weight_decay), _s(stream)))
+    g.free_deduplicate()
+    g.free_dense()

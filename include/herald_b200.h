@@ -67,6 +67,11 @@ uint64_t HBKernelLaunchCount(void);
  * hot path; default 64 (or $HERALD_HOT_THRESHOLD).  Applies to op-level calls and to caches
  * created afterwards.  Results are bit-identical either way; tests lower it for coverage. */
 int HBSetHotThreshold(unsigned rows);
+/* Diagnostics: per-CTA / per-hot-row timeline (globaltimer ns) of the most recent segment-reduce
+ * launch.  Layout: [0] grid, [1] hot items, 4 words per CTA {start, hot phase end, end, items},
+ * then 3 words per hot item {start, end, occurrences}.  Off by default (no cost when off). */
+int HBSegTraceEnable(int on);
+int HBSegTraceRead(unsigned long long *out, size_t words);
 
 /* ---- runtime plumbing: src/common/c_runtime_api.h:28-77 ------------------- */
 int DLStreamCreate(size_t dev_id, DLStreamHandle *handle);
@@ -125,6 +130,13 @@ int AdamOptimizerSparseUpdate(DLArrayHandle param, const DLArrayHandle grad_indi
                               DLStreamHandle stream_handle);
 /* c_runtime_api.h:681-686; src/ops/OptimizersSparse.cu:457-522 (ids unique) */
 int AdamWOptimizerSparseUpdate(DLArrayHandle param, const DLArrayHandle grad_indices,
+                               const DLArrayHandle grad_values, DLArrayHandle expavg,
+                               DLArrayHandle expavgsq, float lr, float beta1, float beta2,
+                               float beta1t, float beta2t, float eps, float weight_decay,
+                               DLStreamHandle stream_handle);
+/* c_runtime_api.h:692-698, src/ops/OptimizersSparse.cu:596-721: Adam direction scaled by the trust
+ * ratio ||param[ids]|| / ||update|| (norms over the listed rows only); ids must be unique. */
+int LambOptimizerSparseUpdate(DLArrayHandle param, const DLArrayHandle grad_indices,
                                const DLArrayHandle grad_values, DLArrayHandle expavg,
                                DLArrayHandle expavgsq, float lr, float beta1, float beta2,
                                float beta1t, float beta2t, float eps, float weight_decay,

@@ -99,6 +99,34 @@ def adamw_sparse_update(param, ids, grads, m, v, lr, beta1, beta2, beta1t, beta2
     return param, m, v
 
 
+def lamb_sparse_update(param, ids, grads, m, v, lr, beta1, beta2, beta1t, beta2t, eps,
+                       weight_decay):
+    """src/ops/OptimizersSparse.cu:538-721 — ids must already be unique.  The two norms are taken
+    over the listed rows only (get_indexed_params :521-536, cuDNN NORM2 :667-699); they are
+    accumulated in float64 here (cuDNN's reduction order is not specified)."""
+    param, m, v = (np.array(x, np.float32) for x in (param, m, v))
+    width = param.shape[1]
+    flat = np.asarray(grads, np.float32).reshape(-1, width)
+    lr, b1, b2, b1t, b2t, eps, wd = (f32(x) for x in (lr, beta1, beta2, beta1t, beta2t, eps,
+                                                      weight_decay))
+    one = f32(1)
+    rows = _ids(ids)
+    updates = np.zeros_like(flat)
+    for n, i in enumerate(rows):
+        g = flat[n]
+        cm = b1 * m[i] + (one - b1) * g
+        cv = b2 * v[i] + (one - b2) * g * g
+        m[i], v[i] = cm, cv
+        cm = cm / (one - b1t)
+        cv = cv / (one - b2t)
+        updates[n] = cm / (np.sqrt(cv) + eps)
+    norm_p = f32(np.sqrt(np.sum(param[rows].astype(np.float64) ** 2)))
+    norm_u = f32(np.sqrt(np.sum(updates.astype(np.float64) ** 2)))
+    for n, i in enumerate(rows):
+        param[i] = param[i] - lr * (norm_p / norm_u) * (updates[n] + wd * param[i])
+    return param, m, v
+
+
 def adagrad_sparse_update(param, ids, grads, acc, lr, eps):
     """src/ops/OptimizersSparse.cu:331-350 — ids must already be unique."""
     param, acc = np.array(param, np.float32), np.array(acc, np.float32)

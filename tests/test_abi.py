@@ -32,7 +32,7 @@ def test_header_declares_the_reference_surface():
     for must in ["DLGpuEmbeddingLookUp", "DLGpuEmbeddingLookUp_Gradient", "DeduplicateIndexedSlices",
                  "IndexedSlices2Dense", "IndexedSlicesOneSideAdd", "SGDOptimizerSparseUpdate",
                  "MomentumOptimizerSparseUpdate", "AdaGradOptimizerSparseUpdate",
-                 "AdamOptimizerSparseUpdate", "AdamWOptimizerSparseUpdate",
+                 "AdamOptimizerSparseUpdate", "AdamWOptimizerSparseUpdate", "LambOptimizerSparseUpdate",
                  "AddL2RegularizationSparse", "DLGpuArraySet", "DLArrayAlloc", "DLArrayFree",
                  "DLArrayCopyFromTo", "DLStreamCreate", "DLStreamDestroy", "DLStreamSync",
                  "DLEventCreate", "DLEventDestroy", "DLEventRecord", "DLEventSync",

@@ -191,6 +191,34 @@ def test_adamw_sparse_reference_formula(hb):
     np.testing.assert_allclose(vd.asnumpy(), v2, rtol=RTOL, atol=1e-5)
 
 
+def test_lamb_sparse_reference_formula(hb):
+    """tests/test_optimizer.py:200-298 (test_lamb_sparse): duplicate ids, norms over the indexed
+    rows only, atol 1e-5."""
+    from herald_b200 import gpu_links
+    from oracle import ops_port
+    rng = np.random.default_rng(18)
+    for (V, D, n) in ((500, 400, 100), (64, 128, 40), (37, 5, 9)):
+        param = rng.uniform(-10, 10, size=(V, D)).astype(np.float32)
+        ids = rng.integers(0, V, n).astype(np.float32)
+        g = rng.uniform(-10, 10, size=(n, D)).astype(np.float32)
+        m = rng.uniform(-10, 10, size=(V, D)).astype(np.float32)
+        v = rng.uniform(0, 10, size=(V, D)).astype(np.float32)
+        lr, b1, b2, b1t, b2t, eps, wd = 1e-2, 0.9, 0.99, 0.9 ** 10, 0.99 ** 10, 1e-7, 0.1
+        pd, md, vd = _dev(hb, param), _dev(hb, m), _dev(hb, v)
+        gpu_links.lamb_update(pd, hb.IndexedSlices(_dev(hb, ids), _dev(hb, g), (V, D)), md, vd, lr,
+                              b1, b2, b1t, b2t, eps, wd)
+        uniq, inv = ops_port.unique_inverse(ids)
+        cg = ops_port.deduplicate(g, inv, len(uniq))
+        p2, m2, v2 = ops_port.lamb_sparse_update(param, uniq, cg, m, v, lr, b1, b2, b1t, b2t, eps,
+                                                 wd)
+        np.testing.assert_allclose(pd.asnumpy(), p2, rtol=RTOL, atol=1e-5)
+        np.testing.assert_allclose(md.asnumpy(), m2, rtol=RTOL, atol=1e-5)
+        np.testing.assert_allclose(vd.asnumpy(), v2, rtol=RTOL, atol=1e-5)
+    # rows that are not listed stay untouched
+    untouched = np.setdiff1d(np.arange(V), ids.astype(np.int64))
+    assert np.array_equal(pd.asnumpy()[untouched], param[untouched])
+
+
 def test_adagrad_and_momentum_sparse(hb):
     from herald_b200 import gpu_links
     from oracle import ops_port

@@ -34,6 +34,40 @@ def test_adamw_sparse_against_reference_test_formula():
     np.testing.assert_allclose(v2, ev, atol=1e-5)
 
 
+def test_lamb_sparse_against_reference_test_formula():
+    # reference tests/test_optimizer.py:200-298 (test_lamb_sparse): dict-based dedup, Adam
+    # direction :262-268, norms over the indexed rows only :275-276, step :281, atol 1e-5
+    rng = np.random.default_rng(3)
+    V, D, n = 500, 400, 100
+    param = rng.uniform(-10, 10, size=(V, D)).astype(np.float32)
+    idx = rng.integers(0, V, n)
+    g = rng.uniform(-10, 10, size=(n, D)).astype(np.float32)
+    m = rng.uniform(-10, 10, size=(V, D)).astype(np.float32)
+    v = rng.uniform(0, 10, size=(V, D)).astype(np.float32)
+    lr, b1, b2, eps, wd = 1e-2, 0.9, 0.99, 1e-7, 0.1
+    b1t, b2t = b1 ** 10, b2 ** 10
+    acc = {}
+    for i, k in enumerate(idx):
+        acc[k] = acc.get(k, np.zeros(D, np.float32)) + g[i]
+    ep, em, ev = param.copy(), m.copy(), v.copy()
+    ups = []
+    for k, gk in acc.items():
+        em[k] = b1 * em[k] + (1 - b1) * gk
+        ev[k] = b2 * ev[k] + (1 - b2) * gk * gk
+        ups.append((em[k] / (1 - b1t)) / (np.sqrt(ev[k] / (1 - b2t)) + eps))
+    ups = np.array(ups)
+    norm_p = np.sqrt(np.sum(np.power(np.array([ep[k] for k in acc]), 2)))
+    norm_u = np.sqrt(np.sum(np.power(ups, 2)))
+    for k, u in zip(acc, ups):
+        ep[k] = ep[k] - lr * norm_p / norm_u * (u + wd * ep[k])
+    uniq, inv = ops_port.unique_inverse(idx.astype(np.float32))
+    cg = ops_port.deduplicate(g, inv, len(uniq))
+    p2, m2, v2 = ops_port.lamb_sparse_update(param, uniq, cg, m, v, lr, b1, b2, b1t, b2t, eps, wd)
+    np.testing.assert_allclose(p2, ep, rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(m2, em, atol=1e-5)
+    np.testing.assert_allclose(v2, ev, atol=1e-5)
+
+
 def test_toy_embedding_sgd_dup_ids():
     # reference tests/test_embedding_op.py:25-89: 5x5 table, ids [[0,1],[0,1]]; duplicate-id SGD
     rng = np.random.default_rng(1)
