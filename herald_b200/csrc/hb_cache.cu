@@ -19,6 +19,7 @@
 //     corner cases in which freshly inserted lines evict each other;
 //   * gradients are accumulated per unique row in occurrence order by one warp (bit-identical
 //     to Line::accumulate, embedding.h:78-91), fused with the push to the owner row.
+#include <cstdio>
 #include <algorithm>
 #include <cstring>
 #include <map>
@@ -1035,6 +1036,67 @@ __global__ void __launch_bounds__(kRowBlock) flush_remote_kernel(CacheView c) {
             c.free_stack[atomicAdd(&c.regs->free_top, 1u)] = s;
         }
     }
+}
+
+// Checkpoint support: push every RESIDENT dirty line (updates != 0) to its owner and mark it
+// clean, exactly what a push does to a line over the bound (cache.cc:171-177,
+// PSFhandle_embedding.cc:24-26).  The reference has no such call — ParamSave writes the server
+// table while the workers' pending updates stay in their caches.  A warp takes 32 slots, tests
+// them lane-parallel and walks the dirty ones.  Multi-GPU: ranks take turns (host barriers), the
+// owner row is updated in place through the peer mapping.
+template <int VEC>
+__global__ void __launch_bounds__(kRowBlock) flush_resident_kernel(CacheView c) {
+    using V = RowVec<VEC>;
+    const unsigned lane = lane_id();
+    const size_t warp_global = (size_t)blockIdx.x * kRowWarps + (threadIdx.x >> 5);
+    const size_t nwarps = (size_t)gridDim.x * kRowWarps;
+    const size_t D = c.width, nvec = D / VEC;
+    const size_t hw = c.regs->slot_hw;
+    u32 flushed = 0;
+    for (size_t base = warp_global * 32; base < hw; base += nwarps * 32) {
+        const size_t s = base + lane;
+        i32 upd = 0;
+        u64 key = 0;
+        if (s < hw) {
+            const u8 st = c.slot_state[s];
+            if (st == S_CACHED || st == S_STORE) {
+                upd = c.slot_updates[s];
+                key = c.slot_key[s];
+                if (key >= c.table_len)
+                    upd = 0;
+            }
+        }
+        unsigned m = __ballot_sync(FULL, upd != 0);
+        while (m) {
+            const int from = __ffs(m) - 1;
+            m &= m - 1;
+            const u64 k = __shfl_sync(FULL, key, from);
+            const i32 u = __shfl_sync(FULL, upd, from);
+            const size_t slot = base + from;
+            float *rows = c.trows;
+            i64 *ver = c.tver;
+            u64 trow = k - c.row_begin;
+            if (c.pv.world > 1) {
+                const int owner = owner_of(c.pv, k, trow);
+                rows = const_cast<float *>(c.pv.rows[owner]);
+                ver = const_cast<i64 *>(c.pv.ver[owner]);
+            } else if (trow >= c.nrows_local) {
+                continue;
+            }
+            for (size_t q = lane; q < nvec; q += 32) {
+                float *dst = rows + trow * D + q * VEC;
+                V::st(dst, V::add(V::ld(dst), V::ld(c.grad + slot * D + q * VEC)));
+            }
+            if (lane == 0) {
+                ver[trow] += u;
+                c.slot_version[slot] += u;
+                c.slot_updates[slot] = 0;
+                flushed++;
+            }
+        }
+    }
+    if (lane == 0 && flushed)
+        atomicAdd(&c.regs->pushed, flushed);
 }
 
 // Tell every owner how many slots of its two sections this rank filled.
@@ -2095,6 +2157,96 @@ int hb_cache_push_pull(hb_cache *c, const void *pull_keys, int pull_kind, size_t
     if (host_dest)
         HB_CUDA(cudaMemcpyAsync(dest, ddest, n_pull * c->width * sizeof(float),
                                 cudaMemcpyDeviceToHost, st));
+    HB_API_END();
+}
+
+int hb_cache_flush(hb_cache *c) {
+    HB_API_BEGIN();
+    // 1. the dirty victims waiting in evict_ (an update of zero keys flushes them; collective)
+    do_update(c, nullptr, HB_KEYS_U64, 0, nullptr, nullptr, 0, 0, false);
+    // 2. the resident dirty lines, one rank at a time so that the adds on a row happen in rank order
+    Guard g(c->device);
+    const int world = c->view.pv.world, rank = c->view.pv.rank;
+    for (int turn = 0; turn < world; turn++) {
+        if (world > 1) {
+            HB_CUDA(cudaStreamSynchronize(c->stream));
+            HB_CHECK(hb_comm_barrier() == 0, "barrier failed");
+        }
+        if (turn != rank)
+            continue;
+        int grid = row_grid((c->view.capacity + 31) / 32);
+        if (c->width % 4 == 0)
+            flush_resident_kernel<4><<<grid, kRowBlock, 0, c->stream>>>(c->view);
+        else
+            flush_resident_kernel<1><<<grid, kRowBlock, 0, c->stream>>>(c->view);
+        HB_LAUNCHED();
+    }
+    HB_CUDA(cudaStreamSynchronize(c->stream));
+    if (world > 1)
+        HB_CHECK(hb_comm_barrier() == 0, "barrier failed");
+    HB_API_END();
+}
+
+// ---- checkpoint of the owner shard --------------------------------------------------------
+// File layout of the reference (ps-lite/include/ps/worker/PSAgent.h:447-476,
+// ps-lite/include/ps/server/PSFHandle.h:401-439): "<dir>/<node_id>_<partition>.dat", the
+// partition's rows as raw row-major float32.  Partition index = rank (AveragePartitioner order).
+// Extension: "<dir>/<node_id>_<partition>.ver" holds the int64 row versions, which the reference
+// does not save (a reloaded reference table restarts every version at its in-memory value);
+// hb_table_load restores them when the file exists.
+static std::string shard_path(const hb_table *t, const char *dir, const char *ext) {
+    return std::string(dir) + "/" + std::to_string(t->node_id) + "_" + std::to_string(t->rank) + ext;
+}
+
+static void stream_file(void *dev, size_t bytes, const std::string &path, bool save) {
+    FILE *f = fopen(path.c_str(), save ? "wb" : "rb");
+    if (!f)
+        throw Error("cannot open " + path);
+    const size_t chunk = (size_t)64 << 20;
+    void *host = nullptr;
+    if (cudaHostAlloc(&host, chunk, cudaHostAllocDefault) != cudaSuccess) {
+        fclose(f);
+        throw Error("cannot allocate the pinned staging buffer");
+    }
+    bool ok = true;
+    for (size_t off = 0; off < bytes && ok; off += chunk) {
+        const size_t len = std::min(chunk, bytes - off);
+        if (save) {
+            ok = cudaMemcpy(host, (char *)dev + off, len, cudaMemcpyDeviceToHost) == cudaSuccess &&
+                 fwrite(host, 1, len, f) == len;
+        } else {
+            ok = fread(host, 1, len, f) == len &&
+                 cudaMemcpy((char *)dev + off, host, len, cudaMemcpyHostToDevice) == cudaSuccess;
+        }
+    }
+    cudaFreeHost(host);
+    ok = (fclose(f) == 0) && ok;
+    if (!ok)
+        throw Error(std::string(save ? "short write to " : "short read from ") + path);
+}
+
+int hb_table_save(hb_table *t, const char *dir) {
+    HB_API_BEGIN();
+    HB_CHECK(t && dir, "null argument");
+    Guard g(t->device);
+    HB_CUDA(cudaDeviceSynchronize());
+    stream_file(t->rows, t->nrows * t->width * sizeof(float), shard_path(t, dir, ".dat"), true);
+    stream_file(t->ver, t->nrows * sizeof(i64), shard_path(t, dir, ".ver"), true);
+    HB_API_END();
+}
+
+int hb_table_load(hb_table *t, const char *dir) {
+    HB_API_BEGIN();
+    HB_CHECK(t && dir, "null argument");
+    Guard g(t->device);
+    HB_CUDA(cudaDeviceSynchronize());
+    stream_file(t->rows, t->nrows * t->width * sizeof(float), shard_path(t, dir, ".dat"), false);
+    const std::string vpath = shard_path(t, dir, ".ver");
+    if (FILE *f = fopen(vpath.c_str(), "rb")) {
+        fclose(f);
+        stream_file(t->ver, t->nrows * sizeof(i64), vpath, false);
+    }
+    HB_CUDA(cudaDeviceSynchronize());
     HB_API_END();
 }
 

@@ -115,6 +115,10 @@ class CacheSparseTable:
     def perf(self):
         return self.cache.perf
 
+    def flush(self):
+        """Write every pending update back to the owner shard (checkpoint barrier)."""
+        self.cache.flush()
+
     def bypass(self):
         self.cache.bypass()
 

@@ -41,6 +41,7 @@ def _proto():
     L.hb_cache_set_perf.argtypes = [_vp, ctypes.c_int]
     L.hb_cache_reserve.argtypes = [_vp, _sz]
     L.hb_cache_stream.argtypes = [_vp, ctypes.POINTER(_vp)]
+    L.hb_cache_flush.argtypes = [_vp]
     L.hb_cache_lookup.argtypes = [_vp, _vp, ctypes.c_int, _sz, _vp]
     L.hb_cache_update.argtypes = [_vp, _vp, ctypes.c_int, _sz, _vp]
     L.hb_cache_update_with_push_keys.argtypes = [_vp, _vp, ctypes.c_int, _sz, _vp, ctypes.c_int,
@@ -180,6 +181,15 @@ class CacheBase(object):
 
     def reserve(self, max_keys):
         check_call(_LIB.hb_cache_reserve(self._h, int(max_keys)))
+
+    def flush(self):
+        """Push every dirty line to its owner whatever the bound (pending victims and resident
+        lines) — not in the reference, whose ParamSave loses the updates still held in worker
+        caches.  Call before SaveParam.  Synchronous."""
+        self._drain()
+        check_call(_LIB.hb_cache_flush(self._h))
+        self._issued += 1      # the flush runs one (empty) update call on the device
+        self._drain()
 
     @property
     def stream(self):

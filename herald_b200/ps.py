@@ -26,6 +26,8 @@ _LIB.hb_table_read_rows.argtypes = [_vp, _sz, _sz, _vp]
 _LIB.hb_table_read_versions.argtypes = [_vp, _sz, _sz, _vp]
 _LIB.hb_table_shard.argtypes = [_vp, ctypes.POINTER(_sz), ctypes.POINTER(_sz),
                                 ctypes.POINTER(_vp), ctypes.POINTER(_vp)]
+_LIB.hb_table_save.argtypes = [_vp, ctypes.c_char_p]
+_LIB.hb_table_load.argtypes = [_vp, ctypes.c_char_p]
 _LIB.hb_comm_rank.argtypes = [ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]
 
 
@@ -102,6 +104,15 @@ class WorkerCommunicate(object):
         t = self.tables.pop(int(node_id), None)
         if t is not None:
             check_call(_LIB.hb_table_destroy(t.h))
+
+    def SaveParam(self, node_id, address):
+        """SaveParam(node, dir) (ps-lite/src/python_binding.cc:111-113): every shard writes
+        "<dir>/<node>_<partition>.dat", raw row-major float32 (PSAgent.h:447-460)."""
+        check_call(_LIB.hb_table_save(self.tables[int(node_id)].h, str(address).encode()))
+
+    def LoadParam(self, node_id, address):
+        """LoadParam(node, dir) (ps-lite/src/python_binding.cc:115-117, PSAgent.h:462-476)."""
+        check_call(_LIB.hb_table_load(self.tables[int(node_id)].h, str(address).encode()))
 
     def BarrierWorker(self):
         if self.nrank() > 1:

@@ -183,6 +183,13 @@ int hb_table_load_rows(hb_table *t, size_t row_begin, size_t nrows, const float 
 int hb_table_read_rows(hb_table *t, size_t row_begin, size_t nrows, float *rows);
 int hb_table_read_versions(hb_table *t, size_t row_begin, size_t nrows, int64_t *versions);
 /* local shard geometry */
+/* Checkpoint of this rank's shard in the reference's on-disk format
+ * (ps-lite/include/ps/worker/PSAgent.h:447-476 ParameterSave/ParameterLoad,
+ * ps-lite/include/ps/server/PSFHandle.h:401-439): "<dir>/<node_id>_<partition>.dat", raw row-major
+ * float32, partition = rank.  "<dir>/<node_id>_<partition>.ver" (int64 row versions) is an
+ * extension the loader treats as optional.  Collective in a group (every rank its own file). */
+int hb_table_save(hb_table *t, const char *dir);
+int hb_table_load(hb_table *t, const char *dir);
 int hb_table_shard(hb_table *t, size_t *row_begin, size_t *nrows, float **dev_rows,
                    int64_t **dev_versions);
 
@@ -247,6 +254,10 @@ int hb_cache_push_pull(hb_cache *c, const void *pull_keys, int pull_kind, size_t
 /* Block until every call enqueued so far has completed; *perf receives the counters of the
  * most recent call.  Returns -1 if any of them failed on the device. */
 int hb_cache_wait(hb_cache *c, hb_perf *perf);
+/* Push every dirty line (pending victims and resident lines with updates != 0) to its owner,
+ * whatever the bound, and mark it clean: call before hb_table_save so that the checkpoint holds
+ * every update (the reference lacks this: SURVEY section 5).  Synchronous; collective in a group. */
+int hb_cache_flush(hb_cache *c);
 /* Counters of the last `max` completed calls, oldest first; returns how many were written. */
 int hb_cache_perf_history(hb_cache *c, hb_perf *out, int *kinds, int max, int *written);
 

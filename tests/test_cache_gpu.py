@@ -302,3 +302,54 @@ def test_single_key_debug_surface(oracle_impl):
         assert "Cache : 3/3" in repr(h.gc)
     finally:
         h.close()
+
+
+# ---- checkpoint: flush of dirty lines + shard save / load -------------------------
+@pytest.mark.parametrize("policy", ["lru", "lfu"])
+def test_flush_then_save_load_roundtrip(tmp_path, policy):
+    """hb_cache_flush pushes what a bound of 10 keeps in the cache; the shard file has the
+    reference's layout (PSAgent.h:447-476: "<dir>/<node>_<part>.dat", raw row-major float32)."""
+    from oracle import port
+    rng = np.random.default_rng(5)
+    V, D, limit = 200, 8, 40
+    h = GpuHarness(port, policy, limit, 10, _rows(rng, V, D))
+    try:
+        for t in range(25):
+            keys = zipf_keys(rng, int(rng.integers(1, 60)), V, 1.3)
+            h.lookup(keys, "t%d" % t)
+            h.update(keys, rng.normal(0, 1e-3, (len(keys), D)).astype(np.float32), None, "t%d" % t)
+        # expected owner state: the oracle flushes evict_ on any update call (cache.cc:142-166) ...
+        h.oc.embedding_update(np.zeros(0, np.uint64), np.zeros((0, D), np.float32))
+        rows, vers = h.osrv.rows().copy(), h.osrv.versions().copy()
+        dirty = 0
+        for k in h.oc.keys():  # ... and a push of a resident line is row += grad; ver += updates
+            ln = h.oc.line(int(k))
+            if ln["updates"]:
+                rows[int(k)] = rows[int(k)] + ln["grad"]
+                vers[int(k)] += ln["updates"]
+                dirty += 1
+        assert dirty > 0, "sequence left nothing dirty: the test would be vacuous"
+        h.gc.flush()
+        assert_bits_equal(h.table.read_rows(), rows, "owner rows after flush")
+        assert np.array_equal(h.table.read_versions(), vers)
+        for k in h.gc.keys():
+            assert h.gc.peek(int(k)).updates == 0
+        # second flush is a no-op
+        h.gc.flush()
+        assert_bits_equal(h.table.read_rows(), rows, "owner rows after 2nd flush")
+        # save, clobber, load
+        h.comm.SaveParam(h.node_id, str(tmp_path))
+        raw = np.fromfile(str(tmp_path / ("%d_0.dat" % h.node_id)), np.float32).reshape(V, D)
+        assert_bits_equal(raw, rows, "file contents")
+        h.table.load_rows(np.zeros((V, D), np.float32))
+        h.comm.LoadParam(h.node_id, str(tmp_path))
+        assert_bits_equal(h.table.read_rows(), rows, "owner rows after load")
+        assert np.array_equal(h.table.read_versions(), vers)
+        # a file written by the reference (rows only, no .ver) loads too and keeps the versions
+        (tmp_path / ("%d_0.ver" % h.node_id)).unlink()
+        (rows * 2).astype(np.float32).tofile(str(tmp_path / ("%d_0.dat" % h.node_id)))
+        h.comm.LoadParam(h.node_id, str(tmp_path))
+        assert_bits_equal(h.table.read_rows(), rows * 2, "rows from a reference-format file")
+        assert np.array_equal(h.table.read_versions(), vers)
+    finally:
+        h.close()
