@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(kRowBlock)
 // One persistent kernel does the whole reduce:
 //   * hot phase — a Zipf batch has ids that occur thousands of times and the add ORDER is fixed
 //     by the parity contract, so such a segment cannot be split by rows; it is split by COLUMNS.
-//     A work item is (hot row, 32-float column chunk).  The CTA streams the chunk of every
+//     A work item is (hot row, 32-float column chunk) — 16-float chunks for the very hot rows.  The CTA streams the chunk of every
 //     occurrence through a kHotStages-deep cp.async ring in shared memory (all 8 warps issue,
 //     128 occurrences x 128 B per stage) while warp 0 adds them in order, one column per lane:
 //     the critical path is the dependent FADD chain itself, not memory latency.  Items are taken
@@ -241,6 +241,128 @@ __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
+// One hot work item: columns [q*W, q*W + W) of one hot row, all its occurrences in order.
+// The CTA streams the W-float chunk of every occurrence through an S-deep cp.async ring
+// ([S][kHotTileRows][W] floats); warp 0 adds them, one column per lane (lanes >= W idle).
+// WIDE (rows 16 B aligned, D % 4 == 0): a thread copies 16 B, W/4 threads cover one occurrence
+// (LDGSTS costs ~8 cycles per warp instruction whatever its width, so 16 B copies are what keeps
+// the ring ahead of the adder); otherwise 4 B per thread and W == 32, one occurrence per warp
+// instruction.
+template <int W, bool WIDE, class F1>
+__device__ __forceinline__ void hot_chunk(const F1 &f1, const typename F1::Ctx &ctx, float *s_ring,
+                                          u32 S, const u32 *__restrict__ perm,
+                                          const float *__restrict__ vals, size_t D, u32 s0, u32 s1,
+                                          u32 q) {
+    static_assert(WIDE || W == 32, "the 4-byte copy path moves one 32-column chunk per warp");
+    constexpr int RPW = kHotTileRows / kRowWarps;              // rows of a stage per warp (4 B path)
+    constexpr int TPR = W / 4;                                 // threads per occurrence (16 B path)
+    constexpr int RPI = kRowBlock / TPR;                       // occurrences per CTA-wide copy round
+    constexpr int CPT = WIDE ? kHotTileRows / RPI : RPW;       // copies per thread per stage
+    const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
+    const u32 cnt = s1 - s0;
+    const size_t col = (size_t)q * W + lane;
+    const bool active = lane < (unsigned)W && col < D;
+    decltype(f1.load(ctx, 0)) acc;
+    if (warp == 0 && active)
+        acc = f1.load(ctx, col);
+    const u32 ntiles = (cnt + kHotTileRows - 1) / kHotTileRows;
+    const u32 my_row = WIDE ? (threadIdx.x / TPR) : warp * RPW;       // first row it copies
+    const u32 my_off = WIDE ? (threadIdx.x % TPR) * 4 : lane;         // float offset in the chunk
+    const bool cp_active = (size_t)q * W + my_off < D;
+    const float *my_src = vals + (size_t)q * W + my_off;
+    u32 pv[CPT];
+    auto load_perm = [&](u32 tile) {
+#pragma unroll
+        for (int j = 0; j < CPT; j++) {
+            const u32 p = s0 + tile * kHotTileRows + my_row + (WIDE ? RPI * j : j);
+            pv[j] = (tile < ntiles && p < s1) ? perm[p] : 0xffffffffu;
+        }
+    };
+    u32 issue_slot = 0; // (next tile to issue) % S, kept without a division
+    auto issue = [&]() {
+        float *stage = s_ring + (size_t)issue_slot * kHotTileRows * W;
+        issue_slot = issue_slot + 1 == S ? 0 : issue_slot + 1;
+#pragma unroll
+        for (int j = 0; j < CPT; j++) {
+            const u32 row = my_row + (WIDE ? RPI * j : j);
+            if (pv[j] != 0xffffffffu && cp_active) {
+                if (WIDE)
+                    cp_async_16(stage + row * W + my_off, my_src + (size_t)pv[j] * D);
+                else
+                    cp_async_f32(stage + row * W + my_off, my_src + (size_t)pv[j] * D);
+            }
+        }
+        cp_async_commit();
+    };
+#pragma unroll 1
+    for (u32 k = 0; k < S - 1; k++) {
+        load_perm(k);
+        issue();
+    }
+    load_perm(S - 1);
+    u32 read_slot = 0;
+    for (u32 k = 0; k < ntiles; k++) {
+        // groups are committed one per tile, in order: at most S - 2 newer than tile k may still
+        // be pending (wait_group takes an immediate, so the depth is switched; waiting for more
+        // than necessary on a deeper ring is still correct)
+        if (S >= 24)
+            cp_async_wait<22>();
+        else if (S >= 20)
+            cp_async_wait<18>();
+        else if (S >= 16)
+            cp_async_wait<14>();
+        else if (S >= 12)
+            cp_async_wait<10>();
+        else if (S >= 10)
+            cp_async_wait<8>();
+        else if (S >= 8)
+            cp_async_wait<6>();
+        else if (S >= 6)
+            cp_async_wait<4>();
+        else if (S == 5)
+            cp_async_wait<3>();
+        else if (S == 4)
+            cp_async_wait<2>();
+        else
+            cp_async_wait<1>();
+        __syncthreads(); // ... everyone's has; and stage k-1 has been consumed
+        issue();         // tile k + S - 1 into the slot tile k - 1 occupied
+        load_perm(k + S);
+        if (warp == 0 && active) {
+            const float *stage = s_ring + (size_t)read_slot * kHotTileRows * W + lane;
+            const u32 rows = min((u32)kHotTileRows, cnt - k * kHotTileRows);
+            if (rows == kHotTileRows) {
+                // full tile: completely unrolled, so the shared-memory loads run ahead of the
+                // dependent adds as far as the register file allows
+                float g[kHotTileRows];
+#pragma unroll
+                for (int j = 0; j < kHotTileRows; j++)
+                    g[j] = stage[j * W];
+#pragma unroll
+                for (int j = 0; j < kHotTileRows; j++)
+                    acc = f1.step(acc, g[j]);
+            } else {
+                u32 r = 0;
+                for (; r + 16 <= rows; r += 16) {
+                    float g[16];
+#pragma unroll
+                    for (int j = 0; j < 16; j++)
+                        g[j] = stage[(r + j) * W];
+#pragma unroll
+                    for (int j = 0; j < 16; j++)
+                        acc = f1.step(acc, g[j]);
+                }
+                for (; r < rows; r++)
+                    acc = f1.step(acc, stage[r * W]);
+            }
+        }
+        read_slot = read_slot + 1 == S ? 0 : read_slot + 1;
+    }
+    cp_async_wait<0>();
+    if (warp == 0 && active)
+        f1.store(ctx, col, acc);
+}
+
 // FV: the functor instantiated for the cold path's vector width VEC; F1: the same functor for
 // VEC = 1 (the hot path addresses single columns).
 template <int VEC, int ROWS, class FV, class F1>
@@ -266,10 +388,13 @@ __global__ void __launch_bounds__(kRowBlock, 2)
 
     // ------------------------------- hot phase -------------------------------------------
     if (hot_threshold != 0xffffffffu) {
-        constexpr int RPW = kHotTileRows / kRowWarps; // rows of a stage issued by one warp: 16
-        const u32 Q = (u32)((D + 31) / 32);
+        // very hot rows are cut into 16-column chunks when the rows allow 16 B copies: half the
+        // bytes per occurrence in the ring = twice the occurrences in flight on the longest chains
+        const u32 QB = (u32)((D + 31) / 32);
+        const u32 QA = WIDE ? (u32)((D + 15) / 16) : QB;
         const u32 nA = hl.ctrl[0], nB = hl.ctrl[1];
-        const u32 total = (nA + nB) * Q;
+        const u32 itemsA = nA * QA;
+        const u32 total = itemsA + nB * QB;
         while (true) {
             __syncthreads(); // the ring and s_item of the previous item are no longer in use
             if (threadIdx.x == 0)
@@ -281,113 +406,25 @@ __global__ void __launch_bounds__(kRowBlock, 2)
             items_taken++;
             if (trace && threadIdx.x == 0 && t < kTraceItems)
                 trace[2 + 4 * (size_t)kTraceCtas + 3 * t] = global_timer_ns();
-            const u32 h = t / Q, q = t % Q;
-            const u32 u = h < nA ? hl.very_hot[h] : hl.hot[h - nA];
-            u32 *done = h < nA ? &hl.done_a[h] : &hl.done_b[h - nA];
+            const bool very = t < itemsA;
+            const u32 h = very ? t / QA : nA + (t - itemsA) / QB;
+            const u32 q = very ? t % QA : (t - itemsA) % QB;
+            const u32 u = very ? hl.very_hot[h] : hl.hot[h - nA];
+            u32 *done = very ? &hl.done_a[h] : &hl.done_b[h - nA];
+            const u32 nchunks = very ? QA : QB;
             const u32 s0 = seg_start[u], s1 = seg_start[u + 1];
             const u32 cnt = s1 - s0;
             typename F1::Ctx ctx;
             const bool ok = f1.begin(u, cnt, ctx);
             if (ok) {
-                const size_t col = (size_t)q * 32 + lane;
-                const bool active = col < D;
-                decltype(f1.load(ctx, 0)) acc;
-                if (warp == 0 && active)
-                    acc = f1.load(ctx, col);
-                const u32 ntiles = (cnt + kHotTileRows - 1) / kHotTileRows;
-                // Stage layout [kHotTileRows][32 floats].  WIDE (rows 16 B aligned): a thread
-                // copies 16 B, eight threads cover one occurrence, a warp instruction four of them
-                // (LDGSTS costs ~8 cycles per warp instruction whatever its width, so 16 B
-                // copies are what keeps the ring ahead of the adder); otherwise 4 B per thread,
-                // one occurrence per warp instruction.
-                constexpr int CPT = WIDE ? kHotTileRows / 32 : RPW; // copies per thread per stage
-                const u32 my_row = WIDE ? (threadIdx.x >> 3) : warp * RPW; // first row it copies
-                const u32 my_off = WIDE ? (threadIdx.x & 7) * 4 : lane;    // float offset in row
-                const bool cp_active = (size_t)q * 32 + my_off < D;
-                const float *my_src = vals + (size_t)q * 32 + my_off;
-                u32 pv[CPT];
-                auto load_perm = [&](u32 tile) {
-#pragma unroll
-                    for (int j = 0; j < CPT; j++) {
-                        const u32 p = s0 + tile * kHotTileRows + my_row + (WIDE ? 32 * j : j);
-                        pv[j] = (tile < ntiles && p < s1) ? perm[p] : 0xffffffffu;
-                    }
-                };
-                u32 issue_slot = 0; // tile % S of the next tile to issue, kept without a division
-                auto issue = [&](u32 tile) {
-                    float *stage = s_ring + (size_t)issue_slot * kHotTileRows * 32;
-                    issue_slot = issue_slot + 1 == S ? 0 : issue_slot + 1;
-                    (void)tile;
-#pragma unroll
-                    for (int j = 0; j < CPT; j++) {
-                        const u32 row = my_row + (WIDE ? 32 * j : j);
-                        if (pv[j] != 0xffffffffu && cp_active) {
-                            if (WIDE)
-                                cp_async_16(stage + row * 32 + my_off, my_src + (size_t)pv[j] * D);
-                            else
-                                cp_async_f32(stage + row * 32 + my_off, my_src + (size_t)pv[j] * D);
-                        }
-                    }
-                    cp_async_commit();
-                };
-#pragma unroll 1
-                for (u32 k = 0; k < S - 1; k++) {
-                    load_perm(k);
-                    issue(k);
+                if constexpr (WIDE) {
+                    if (very)
+                        hot_chunk<16, true>(f1, ctx, s_ring, S * 2, perm, vals, D, s0, s1, q);
+                    else
+                        hot_chunk<32, true>(f1, ctx, s_ring, S, perm, vals, D, s0, s1, q);
+                } else {
+                    hot_chunk<32, false>(f1, ctx, s_ring, S, perm, vals, D, s0, s1, q);
                 }
-                load_perm(S - 1);
-                u32 read_slot = 0;
-                for (u32 k = 0; k < ntiles; k++) {
-                    // groups are committed one per tile, in order: at most S - 2 newer than tile k
-                    // may still be pending (wait_group takes an immediate, so the depth is switched)
-                    switch (S) {
-                    case 3: cp_async_wait<1>(); break;
-                    case 4: cp_async_wait<2>(); break;
-                    case 5: cp_async_wait<3>(); break;
-                    case 6: cp_async_wait<4>(); break;
-                    case 7: cp_async_wait<5>(); break;
-                    case 8: cp_async_wait<6>(); break;
-                    case 9: cp_async_wait<7>(); break;
-                    case 10: cp_async_wait<8>(); break;
-                    case 11: cp_async_wait<9>(); break;
-                    default: cp_async_wait<10>(); break;
-                    }
-                    __syncthreads(); // ... everyone's has; and stage k-1 has been consumed
-                    issue(k + S - 1);
-                    load_perm(k + S);
-                    if (warp == 0 && active) {
-                        const float *stage = s_ring + (size_t)read_slot * kHotTileRows * 32 + lane;
-                        const u32 rows = min((u32)kHotTileRows, cnt - k * kHotTileRows);
-                        if (rows == kHotTileRows) {
-                            // full tile: completely unrolled, so the shared-memory loads run ahead
-                            // of the dependent adds as far as the register file allows
-                            float g[kHotTileRows];
-#pragma unroll
-                            for (int j = 0; j < kHotTileRows; j++)
-                                g[j] = stage[j * 32];
-#pragma unroll
-                            for (int j = 0; j < kHotTileRows; j++)
-                                acc = f1.step(acc, g[j]);
-                        } else {
-                            u32 r = 0;
-                            for (; r + 16 <= rows; r += 16) {
-                                float g[16];
-#pragma unroll
-                                for (int j = 0; j < 16; j++)
-                                    g[j] = stage[(r + j) * 32];
-#pragma unroll
-                                for (int j = 0; j < 16; j++)
-                                    acc = f1.step(acc, g[j]);
-                            }
-                            for (; r < rows; r++)
-                                acc = f1.step(acc, stage[r * 32]);
-                        }
-                    }
-                    read_slot = read_slot + 1 == S ? 0 : read_slot + 1;
-                }
-                cp_async_wait<0>();
-                if (warp == 0 && active)
-                    f1.store(ctx, col, acc);
             }
             // the CTA that completes the row's last chunk applies the per-row scalars
             if (warp == 0) {
@@ -398,7 +435,7 @@ __global__ void __launch_bounds__(kRowBlock, 2)
                     prev = atomicAdd(done, 1u);
                 }
                 prev = __shfl_sync(FULL, prev, 0);
-                if (prev == Q - 1 && ok && lane == 0) {
+                if (prev == nchunks - 1 && ok && lane == 0) {
                     __threadfence();
                     f1.end(ctx);
                 }

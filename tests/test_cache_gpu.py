@@ -88,11 +88,13 @@ def test_hot_segment_path(oracle_impl, policy, bound, D, mode):
         set_hot_threshold(64)
 
 
-def test_very_hot_id(oracle_impl):
-    """One id repeated thousands of times (> kVeryHot, several 256-row tiles) among cold ids."""
+@pytest.mark.parametrize("D,bound", [(128, 0), (40, 0), (8, 2), (512, 10), (6, 0), (20, 0)])
+def test_very_hot_id(oracle_impl, D, bound):
+    """One id repeated thousands of times (> kVeryHot: the 16-column chunks of the hot phase, with
+    partial last chunks at D = 40 / 20 / 8 and the 4-byte copy path at D = 6) among cold ids."""
     rng = np.random.default_rng(17)
-    V, D = 400, 128
-    h = GpuHarness(oracle_impl, "lru", 100, 0, _rows(rng, V, D))
+    V = 400
+    h = GpuHarness(oracle_impl, "lru", 100, bound, _rows(rng, V, D))
     try:
         for t in range(3):
             keys = zipf_keys(rng, 6000, V, 1.3)
