@@ -52,6 +52,8 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-steps", type=int, default=8)
+    ap.add_argument("--seg-trace", default=None,
+                    help="diagnostics: write the per-CTA timeline of one segment_reduce launch here")
     return ap.parse_args()
 
 
@@ -242,6 +244,33 @@ def dl_stream_of(cuda_stream_value):
     return s
 
 
+def seg_trace(path, run_step):
+    """Diagnostics (untimed): per-CTA / per-hot-item timeline of one segment_reduce launch."""
+    from herald_b200._base import _LIB, check_call
+    words = 2 + 4 * 2048 + 3 * 1024
+    check_call(_LIB.HBSegTraceEnable(1))
+    run_step()
+    buf = (ctypes.c_ulonglong * words)()
+    check_call(_LIB.HBSegTraceRead(buf, ctypes.c_size_t(words)))
+    check_call(_LIB.HBSegTraceEnable(0))
+    a = np.frombuffer(buf, dtype=np.uint64).astype(np.int64)
+    grid, nitems = int(a[0]), int(a[1])
+    cta = a[2:2 + 4 * 2048].reshape(2048, 4)[:grid]
+    items = a[2 + 4 * 2048:].reshape(1024, 3)[:min(nitems, 1024)]
+    t0 = int(cta[:, 0].min())
+    out = {"grid": grid, "hot_items": nitems,
+           "kernel_span_us": (int(cta[:, 2].max()) - t0) / 1e3,
+           "cta_start_us": np.percentile((cta[:, 0] - t0) / 1e3, [0, 50, 100]).tolist(),
+           "cta_hot_end_us": np.percentile((cta[:, 1] - t0) / 1e3, [0, 10, 50, 90, 100]).tolist(),
+           "cta_end_us": np.percentile((cta[:, 2] - t0) / 1e3, [0, 10, 50, 90, 100]).tolist(),
+           "cta_items": np.percentile(cta[:, 3], [0, 50, 100]).tolist(),
+           "items": [[(int(x[0]) - t0) / 1e3, (int(x[1]) - t0) / 1e3, int(x[2])] for x in items[:64]],
+           "item_ns_per_occurrence": [float((x[1] - x[0]) / max(1, x[2])) for x in items[:64]],
+           "last_item_end_us": (int(items[:, 1].max()) - t0) / 1e3 if len(items) else 0.0}
+    with open(path, "w") as f:
+        json.dump(out, f)
+
+
 def herald_main(args, rank, world, local_rank):
     import herald_b200 as hb
     from herald_b200 import ps, stream as hstream
@@ -326,6 +355,9 @@ def herald_main(args, rank, world, local_rank):
     ms = ev[1].time_since(ev[0])
     perf = list(cst.perf)[-2 * K:]
     clocks = sampler.stop() if rank == 0 else None
+
+    if args.seg_trace and rank == 0:
+        seg_trace(args.seg_trace, lambda: step(W + K - 1, ids_dev, grads_dev, dest_dev, True))
 
     # ---- end to end with host buffers (pinned NDArrays: the reference's calling convention) ----
     e2e = None

@@ -58,7 +58,9 @@ __device__ __forceinline__ i32 ht_find(const HtEntry *ht, u32 mask, u64 key) {
 }
 
 // key must be absent.  Returns false when the table has no free entry.
-__device__ __forceinline__ bool ht_insert(HtEntry *ht, u32 mask, u64 key, u32 slot, u32 *occupied) {
+// `fresh` counts the EMPTY entries taken (the caller adds the warp's sum to regs->ht_occupied with
+// one atomic: add_occupied()).
+__device__ __forceinline__ bool ht_insert(HtEntry *ht, u32 mask, u64 key, u32 slot, u32 &fresh) {
     u32 h = hash_key(key) & mask;
     for (u32 probes = 0; probes <= mask;) {
         u64 cur = *reinterpret_cast<volatile u64 *>(&ht[h].key);
@@ -67,7 +69,7 @@ __device__ __forceinline__ bool ht_insert(HtEntry *ht, u32 mask, u64 key, u32 sl
             if (old == cur) {
                 ht[h].slot = slot;
                 if (cur == HT_EMPTY)
-                    atomicAdd(occupied, 1u);
+                    fresh++;
                 return true;
             }
             continue; // lost the race for this entry: look at it again
@@ -90,6 +92,16 @@ __device__ __forceinline__ void ht_erase(HtEntry *ht, u32 mask, u64 key) {
             return;
         h = (h + 1) & mask;
     }
+}
+
+// End of a kernel (all lanes converged): one atomic per warp for the index entries it took.
+__device__ __forceinline__ void add_occupied(u32 *occupied, u32 fresh) {
+    __syncwarp();
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1)
+        fresh += __shfl_xor_sync(0xffffffffu, fresh, d);
+    if ((threadIdx.x & 31) == 0 && fresh)
+        atomicAdd(occupied, fresh);
 }
 
 // One atomic per warp: every lane of the warp must call this (pred may differ per lane).
@@ -125,6 +137,7 @@ __device__ __forceinline__ u64 make_prio(u32 use, u64 stamp) {
 // clk[s+1], so no kernel reads a word that another block of the same kernel writes.
 // flush != 0: the call pushes, so it also flushes the dirty victims collected so far (evict_)
 __global__ void op_begin_kernel(CacheRegs *r, u64 *clk, int flush) {
+    pdl_enter();
     r->clock0 = r->clock;
     clk[0] = r->clock;
     clk[1] = clk[2] = clk[3] = r->clock;
@@ -137,6 +150,7 @@ __global__ void op_begin_kernel(CacheRegs *r, u64 *clk, int flush) {
 
 __global__ void op_end_kernel(CacheView c, const u64 *clk, int last_stage, PerfRecord *rec, u32 kind,
                               u32 num_all, int inserted_batch) {
+    pdl_enter();
     CacheRegs *r = c.regs;
     r->clock = clk[last_stage];
     if (inserted_batch) {
@@ -172,18 +186,33 @@ __global__ void op_end_kernel(CacheView c, const u64 *clk, int last_stage, PerfR
 // resolve: policy lookup of every unique key (+ touch), ordered compaction of the misses
 // =====================================================================================
 // batch 0 writes U/M/alloc_base, batch 1 (push side of push_pull) writes U2/M2/alloc_base2.
+constexpr int kResolveItems = 1; // measured: 4 per thread is slower (the probes of one thread serialise: 16 -> 19 us)
+
 __global__ void __launch_bounds__(kScanBlock)
     resolve_kernel(CacheView c, const u64 *uniq, const u32 *num_unique, i32 *uslot, u32 *miss_list,
                    int bypass, ScanState st, u32 ntiles, const u64 *clk_in, u64 *clk_out, int batch) {
+    pdl_enter();
     const u32 tile = take_ticket(st.ticket);
     const u32 U = *num_unique;
     const u64 base = *clk_in;
-    const u32 i = tile * kScanBlock + threadIdx.x;
+    // kResolveItems consecutive uniques per thread
+    const u32 i0 = (tile * kScanBlock + threadIdx.x) * kResolveItems;
+    u64 key[kResolveItems];
+    i32 sl[kResolveItems];
+#pragma unroll
+    for (int j = 0; j < kResolveItems; j++)
+        key[j] = i0 + j < U ? uniq[i0 + j] : 0;
+#pragma unroll
+    for (int j = 0; j < kResolveItems; j++)
+        sl[j] = (i0 + j < U && !bypass) ? ht_find(c.ht, c.ht_mask, key[j]) : -1;
     u32 miss = 0;
-    if (i < U) {
-        const u64 key = uniq[i];
-        i32 s = bypass ? -1 : ht_find(c.ht, c.ht_mask, key);
-        if (key >= c.table_len)
+#pragma unroll
+    for (int j = 0; j < kResolveItems; j++) {
+        const u32 i = i0 + j;
+        if (i >= U)
+            continue;
+        const i32 s = sl[j];
+        if (key[j] >= c.table_len)
             atomicMax(&c.regs->error, (u32)E_KEY_RANGE);
         if (s >= 0) {
             const u64 stamp = base + i;
@@ -212,13 +241,16 @@ __global__ void __launch_bounds__(kScanBlock)
                 break;
             }
         } else {
-            miss = 1;
+            miss++;
         }
         uslot[i] = s;
     }
     ScanResult sr = grid_exclusive_scan<kScanBlock>(st, miss, tile);
-    if (miss)
-        miss_list[sr.excl] = i;
+    u32 pos = sr.excl;
+#pragma unroll
+    for (int j = 0; j < kResolveItems; j++)
+        if (i0 + j < U && sl[j] < 0)
+            miss_list[pos++] = i0 + j;
     if (tile == ntiles - 1 && threadIdx.x == 0) {
         CacheRegs *r = c.regs;
         u32 M = sr.tile_prefix + sr.tile_total;
@@ -247,6 +279,7 @@ __global__ void __launch_bounds__(kScanBlock)
 // Give every miss a fresh line (cache.cc:70-76 with data, :146-151 dataless).
 __global__ void alloc_kernel(CacheView c, const u64 *uniq, i32 *uslot, const u32 *miss_list,
                              int batch, int dataless) {
+    pdl_enter();
     const CacheRegs *r = c.regs;
     const u32 M = batch == 0 ? r->M : r->M2;
     const u32 alloc_base = batch == 0 ? r->alloc_base : r->alloc_base2;
@@ -276,6 +309,7 @@ template <int VEC, int ROWS>
 __global__ void __launch_bounds__(kRowBlock)
     sync_kernel(CacheView c, const u64 *__restrict__ uniq, const i32 *__restrict__ uslot,
                 i64 pull_bound) {
+    pdl_enter();
     using V = RowVec<VEC>;
     const unsigned lane = lane_id();
     const size_t warp_global = (size_t)blockIdx.x * kRowWarps + (threadIdx.x >> 5);
@@ -373,11 +407,16 @@ struct IndexFromSlots {
 // =====================================================================================
 __global__ void __launch_bounds__(256)
     plan_insert_kernel(CacheView c, int bypass, const u64 *clk_in, u64 *clk_out) {
-    for (int b = threadIdx.x; b < kSelBins; b += blockDim.x)
+    pdl_enter();
+    for (int b = threadIdx.x; b < 2 * kSelBins; b += blockDim.x)
         c.sel_hist[b] = 0;
     if (threadIdx.x != 0)
         return;
     CacheRegs *r = c.regs;
+    r->sel_done2 = 0;
+    r->sel_above = 0;
+    r->sel_fallback = 0;
+    r->sel_cut_eff = r->sel_cut ? r->sel_cut : (u32)kSelBins;
     const u32 M = r->M, size_old = r->size, limit = c.limit;
     u32 E = 0;
     if (!bypass) {
@@ -407,31 +446,41 @@ __global__ void __launch_bounds__(256)
     r->sel_shift = bits > kSelBits ? (u32)(bits - kSelBits) : 0;
 }
 
-// Block-wide: exclusive prefix of sh[0..kSelBins) in place; returns total.  blockDim.x == 256.
+constexpr int kSelUnroll = 4; // slot priorities a thread loads before it uses the first
+
+// Block-wide: exclusive prefix of sh[0..kSelBins) in place; returns total.  blockDim.x is a
+// multiple of 256 (the first 256 threads do the work, every thread must call it).
 __device__ __forceinline__ u32 block_scan_bins(u32 *sh) {
     __shared__ u32 s_part[256];
     constexpr int PER = kSelBins / 256;
+    const bool act = threadIdx.x < 256;
+    const unsigned t256 = threadIdx.x & 255;
     u32 local[PER];
     u32 sum = 0;
+    if (act) {
 #pragma unroll
-    for (int k = 0; k < PER; k++) {
-        local[k] = sh[threadIdx.x * PER + k];
-        sum += local[k];
+        for (int k = 0; k < PER; k++) {
+            local[k] = sh[t256 * PER + k];
+            sum += local[k];
+        }
+        s_part[t256] = sum;
     }
-    s_part[threadIdx.x] = sum;
     __syncthreads();
     // Hillis-Steele over 256 partials
     for (int d = 1; d < 256; d <<= 1) {
-        u32 t = threadIdx.x >= (unsigned)d ? s_part[threadIdx.x - d] : 0;
+        u32 t = (act && t256 >= (unsigned)d) ? s_part[t256 - d] : 0;
         __syncthreads();
-        s_part[threadIdx.x] += t;
+        if (act)
+            s_part[t256] += t;
         __syncthreads();
     }
-    u32 run = s_part[threadIdx.x] - sum;
+    if (act) {
+        u32 run = s_part[t256] - sum;
 #pragma unroll
-    for (int k = 0; k < PER; k++) {
-        sh[threadIdx.x * PER + k] = run;
-        run += local[k];
+        for (int k = 0; k < PER; k++) {
+            sh[t256 * PER + k] = run;
+            run += local[k];
+        }
     }
     u32 total = s_part[255];
     __syncthreads();
@@ -441,53 +490,96 @@ __device__ __forceinline__ u32 block_scan_bins(u32 *sh) {
 // Level-one histogram of the victim class over [floor, now).  The block that adds its bins last
 // scans the finished histogram ONCE and leaves the selection plan in the registers: threshold bin,
 // victims to take inside it, and the closed-form corner cases of DESIGN.md 4.3.
-__global__ void __launch_bounds__(256) sel_hist_kernel(CacheView c) {
+// level 0 counts only the bins below a window (`sel_cut_eff`, twice the previous call's threshold
+// bin): the victims of a steady-state batch are the oldest few per cent of the class, so 97 % of
+// the lines cost a compare instead of a shared-memory atomic on a handful of contended bins; the
+// lines above the window are only counted.  If the threshold turns out to lie above the window
+// (first call, a burst of evictions), level 1 — launched right after, a no-op otherwise — repeats
+// the sweep over all bins.
+__global__ void __launch_bounds__(1024) sel_hist_kernel(CacheView c, int level) {
+    pdl_enter();
     CacheRegs *r = c.regs;
     const u32 E = r->E;
     if (E == 0)
         return;
+    if (level == 1 && !r->sel_fallback)
+        return;
     __shared__ u32 sh[kSelBins];
-    __shared__ u32 s_bin;
+    __shared__ u32 s_bin, s_above;
     __shared__ bool s_last;
+    u32 *const ghist = c.sel_hist + (level ? kSelBins : 0);
+    u32 *const done = level ? &r->sel_done2 : &r->sel_done;
+    const u32 cut = level ? (u32)kSelBins : r->sel_cut_eff;
     for (int b = threadIdx.x; b < kSelBins; b += blockDim.x)
         sh[b] = 0;
+    if (threadIdx.x == 0)
+        s_above = 0;
     __syncthreads();
     const u64 floor = r->floor;
     const u32 shift = r->sel_shift;
     const u64 cls = (u64)class_use_of(c.policy);
     const size_t hw = r->slot_hw;
-    for (size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x; s < hw;
-         s += (size_t)gridDim.x * blockDim.x) {
-        const u64 p = c.slot_prio[s];
-        if (p != PRIO_NONE && (p >> kStampBits) == cls) {
-            u64 bin = ((p & kStampMask) - floor) >> shift;
-            atomicAdd(&sh[min(bin, (u64)(kSelBins - 1))], 1u);
+    // kSelUnroll independent loads per thread before the first use: the sweep is a dependent-load
+    // loop otherwise (one L2/HBM latency per 8 bytes per thread)
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    u32 above = 0;
+    for (size_t s0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x; s0 < hw;
+         s0 += stride * kSelUnroll) {
+        u64 pr[kSelUnroll];
+#pragma unroll
+        for (int k = 0; k < kSelUnroll; k++) {
+            const size_t s = s0 + (size_t)k * stride;
+            pr[k] = s < hw ? c.slot_prio[s] : PRIO_NONE;
+        }
+#pragma unroll
+        for (int k = 0; k < kSelUnroll; k++) {
+            const u64 p = pr[k];
+            if (p != PRIO_NONE && (p >> kStampBits) == cls) {
+                const u64 bin = min(((p & kStampMask) - floor) >> shift, (u64)(kSelBins - 1));
+                if (bin < cut)
+                    atomicAdd(&sh[bin], 1u);
+                else
+                    above++;
+            }
         }
     }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1)
+        above += __shfl_xor_sync(FULL, above, d);
+    if (lane_id() == 0 && above)
+        atomicAdd(&s_above, above);
     __syncthreads();
-    for (int b = threadIdx.x; b < kSelBins; b += blockDim.x)
+    for (int b = threadIdx.x; b < (int)cut; b += blockDim.x)
         if (sh[b])
-            atomicAdd(&c.sel_hist[b], sh[b]);
+            atomicAdd(&ghist[b], sh[b]);
+    if (threadIdx.x == 0 && s_above)
+        atomicAdd(&r->sel_above, s_above);
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0)
-        s_last = atomicAdd(&r->sel_done, 1u) == gridDim.x - 1;
+        s_last = atomicAdd(done, 1u) == gridDim.x - 1;
     __syncthreads();
     if (!s_last)
         return;
     __threadfence();
     for (int b = threadIdx.x; b < kSelBins; b += blockDim.x)
-        sh[b] = __ldcg(&c.sel_hist[b]);
+        sh[b] = __ldcg(&ghist[b]);
     if (threadIdx.x == 0)
         s_bin = 0;
     __syncthreads();
-    const u32 class_count = block_scan_bins(sh); // sh = exclusive prefix
+    const u32 in_window = block_scan_bins(sh); // sh = exclusive prefix
+    const u32 class_count = in_window + (level ? 0u : __ldcg(&r->sel_above));
     const u32 k_old = min(E, class_count);
+    if (k_old > in_window) { // level 0 only: the threshold bin is above the window
+        if (threadIdx.x == 0)
+            r->sel_fallback = 1;
+        return;
+    }
     // threshold bin: the last bin whose exclusive prefix is < k_old (k_old > 0)
     if (k_old > 0) {
         for (int b = threadIdx.x; b < kSelBins; b += blockDim.x) {
             u32 ex = sh[b];
-            u32 nxt = b + 1 < kSelBins ? sh[b + 1] : class_count;
+            u32 nxt = b + 1 < kSelBins ? sh[b + 1] : in_window;
             if (ex < k_old && nxt >= k_old)
                 s_bin = b; // unique b: prefix is monotone and nxt > ex here
         }
@@ -521,6 +613,7 @@ __global__ void __launch_bounds__(256) sel_hist_kernel(CacheView c) {
         r->need_min = need_min;
         r->sel_bin = bstar;
         r->sel_rem = k_old > 0 ? k_old - sh[bstar] : 0;
+        r->sel_cut = k_old > 0 ? min((u32)kSelBins, 2 * bstar + 64) : 0;
     }
 }
 
@@ -529,9 +622,10 @@ __global__ void __launch_bounds__(256) sel_hist_kernel(CacheView c) {
 // shared memory and appended with ONE global atomic per block and flush (the victims of a
 // steady-state batch are a few per cent of the slots, so a per-warp append would put tens of
 // thousands of atomics on one address).
-constexpr int kCollectCap = 1024;
+constexpr int kCollectCap = 2048;
 
 __global__ void __launch_bounds__(256) sel_collect_kernel(CacheView c) {
+    pdl_enter();
     CacheRegs *r = c.regs;
     if (r->E == 0 || r->k_old == 0)
         return;
@@ -550,20 +644,30 @@ __global__ void __launch_bounds__(256) sel_collect_kernel(CacheView c) {
     const u64 cls = (u64)class_use_of(c.policy);
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     const size_t hw = r->slot_hw;
-    const size_t rounds = (hw + stride - 1) / stride;
+    const size_t rounds = (hw + stride * kSelUnroll - 1) / (stride * kSelUnroll);
+    constexpr u32 kPerRound = 256 * kSelUnroll; // most entries one round can add to a list
+    static_assert(kPerRound * 2 <= kCollectCap, "a round must fit behind a flushed list");
     for (size_t it = 0; it <= rounds; it++) {
         if (it < rounds) {
-            const size_t s = it * stride + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-            if (s < hw) {
-                const u64 p = c.slot_prio[s];
+            const size_t s0 = it * stride * kSelUnroll + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+            u64 pr[kSelUnroll];
+#pragma unroll
+            for (int k = 0; k < kSelUnroll; k++) {
+                const size_t s = s0 + (size_t)k * stride;
+                pr[k] = s < hw ? c.slot_prio[s] : PRIO_NONE;
+            }
+#pragma unroll
+            for (int k = 0; k < kSelUnroll; k++) {
+                const u64 p = pr[k];
+                const size_t s = s0 + (size_t)k * stride;
                 if (p != PRIO_NONE && (p >> kStampBits) == cls) {
                     const u64 bin = min(((p & kStampMask) - floor) >> shift, (u64)(kSelBins - 1));
                     if (bin < bstar) {
                         s_vic[atomicAdd(&s_nv, 1u)] = (u32)s;
                     } else if (bin == bstar) {
-                        const u32 k = atomicAdd(&s_nc, 1u);
-                        s_cprio[k] = p & kStampMask;
-                        s_cslot[k] = (u32)s;
+                        const u32 j = atomicAdd(&s_nc, 1u);
+                        s_cprio[j] = p & kStampMask;
+                        s_cslot[j] = (u32)s;
                     }
                 }
             }
@@ -572,7 +676,7 @@ __global__ void __launch_bounds__(256) sel_collect_kernel(CacheView c) {
         // block-uniform: flush when the next round could overflow a list, and after the last round
         const u32 nv = s_nv, nc = s_nc;
         const bool last = it == rounds;
-        if (last || nv + 256 > kCollectCap || nc + 256 > kCollectCap) {
+        if (last || nv + kPerRound > kCollectCap || nc + kPerRound > kCollectCap) {
             if (threadIdx.x == 0) {
                 s_vbase = nv ? atomicAdd(&r->nv, nv) : 0;
                 s_cbase = nc ? atomicAdd(&r->nc, nc) : 0;
@@ -596,6 +700,7 @@ __global__ void __launch_bounds__(256) sel_collect_kernel(CacheView c) {
 
 // One block finishes the selection inside the threshold bin: 12 more bits per round.
 __global__ void __launch_bounds__(1024) sel_refine_kernel(CacheView c) {
+    pdl_enter();
     CacheRegs *r = c.regs;
     if (r->E == 0 || r->k_old == 0)
         return;
@@ -700,6 +805,7 @@ __global__ void __launch_bounds__(1024) sel_refine_kernel(CacheView c) {
 
 // LFU corner: the single resident line with the smallest (use, stamp).
 __global__ void min_use_kernel(CacheView c) {
+    pdl_enter();
     CacheRegs *r = c.regs;
     if (!r->need_min)
         return;
@@ -714,6 +820,7 @@ __global__ void min_use_kernel(CacheView c) {
         atomicMin(&r->min_use, best);
 }
 __global__ void min_prio_kernel(CacheView c) {
+    pdl_enter();
     CacheRegs *r = c.regs;
     if (!r->need_min)
         return;
@@ -729,6 +836,7 @@ __global__ void min_prio_kernel(CacheView c) {
         atomicMin(&r->min_prio, best);
 }
 __global__ void min_pick_kernel(CacheView c) {
+    pdl_enter();
     CacheRegs *r = c.regs;
     if (!r->need_min)
         return;
@@ -744,31 +852,43 @@ __global__ void min_pick_kernel(CacheView c) {
 // Remove the victims from the index; dirty ones wait for the next push (evict_), clean ones
 // are freed (lru_cache.cc:17-24).
 __global__ void evict_apply_kernel(CacheView c) {
+    pdl_enter();
     CacheRegs *r = c.regs;
     const u32 nv = r->nv;
-    for (u32 v = blockIdx.x * blockDim.x + threadIdx.x; v < nv; v += gridDim.x * blockDim.x) {
-        const u32 s = c.victims[v];
-        ht_erase(c.ht, c.ht_mask, c.slot_key[s]);
-        c.slot_prio[s] = PRIO_NONE;
-        if (c.slot_updates[s] != 0) {
-            c.slot_state[s] = S_PENDING;
-            u32 pos = atomicAdd(&r->pending, 1u);
-            if (pos < c.capacity)
-                c.pending_list[pos] = s;
+    const u32 stride = gridDim.x * blockDim.x;
+    for (u32 v0 = blockIdx.x * blockDim.x; v0 < nv; v0 += stride) { // block-uniform trip count
+        const u32 v = v0 + threadIdx.x;
+        const bool act = v < nv;
+        u32 s = 0;
+        bool dirty = false;
+        if (act) {
+            s = c.victims[v];
+            ht_erase(c.ht, c.ht_mask, c.slot_key[s]);
+            c.slot_prio[s] = PRIO_NONE;
+            dirty = c.slot_updates[s] != 0;
+            c.slot_state[s] = dirty ? S_PENDING : S_FREE;
+        }
+        // one atomic per warp and list instead of one per victim on the same two words
+        const u32 pp = warp_append(&r->pending, act && dirty);
+        if (act && dirty) {
+            if (pp < c.capacity)
+                c.pending_list[pp] = s;
             else
                 atomicMax(&r->error, (u32)E_EVICT_OVERFLOW);
-        } else {
-            c.slot_state[s] = S_FREE;
-            c.free_stack[atomicAdd(&r->free_top, 1u)] = s;
         }
+        const u32 fp = warp_append(&r->free_top, act && !dirty);
+        if (act && !dirty)
+            c.free_stack[fp] = s;
     }
 }
 
 __global__ void insert_new_kernel(CacheView c, const i32 *uslot, const u32 *miss_list) {
+    pdl_enter();
     CacheRegs *r = c.regs;
     const u32 M = r->M, n_drop = r->n_drop;
     const u64 clock0 = r->ins_clock0;
     const u32 use0 = c.policy == HB_POLICY_LFU ? 1u : 0u;
+    u32 fresh = 0;
     for (u32 j = blockIdx.x * blockDim.x + threadIdx.x; j < M; j += gridDim.x * blockDim.x) {
         const u32 s = (u32)uslot[miss_list[j]];
         if (j < n_drop) { // served to the caller but never resident after the call
@@ -776,12 +896,13 @@ __global__ void insert_new_kernel(CacheView c, const i32 *uslot, const u32 *miss
             c.free_stack[atomicAdd(&r->free_top, 1u)] = s;
             continue;
         }
-        if (!ht_insert(c.ht, c.ht_mask, c.slot_key[s], s, &r->ht_occupied))
+        if (!ht_insert(c.ht, c.ht_mask, c.slot_key[s], s, fresh))
             atomicMax(&r->error, (u32)E_INDEX_FULL);
         c.slot_use[s] = use0;
         c.slot_prio[s] = make_prio(use0, clock0 + j);
         c.slot_state[s] = S_CACHED;
     }
+    add_occupied(&r->ht_occupied, fresh);
 }
 
 // =====================================================================================
@@ -973,6 +1094,7 @@ struct FlushPending {
 // contiguous per-owner slices exactly as PSAgent splits them with lower_bound (PSAgent.h:541-559)
 __global__ void owner_bounds_kernel(CacheView c, const u64 *__restrict__ uniq,
                                     const u32 *__restrict__ num_unique) {
+    pdl_enter();
     const int o = threadIdx.x;
     if (o > c.pv.world)
         return;
@@ -997,6 +1119,7 @@ __global__ void owner_bounds_kernel(CacheView c, const u64 *__restrict__ uniq,
 // Dirty victims go to their owner's "flush" section (one warp per line).
 template <int VEC>
 __global__ void __launch_bounds__(kRowBlock) flush_remote_kernel(CacheView c) {
+    pdl_enter();
     using V = RowVec<VEC>;
     const unsigned lane = lane_id();
     const size_t warp_global = (size_t)blockIdx.x * kRowWarps + (threadIdx.x >> 5);
@@ -1046,6 +1169,7 @@ __global__ void __launch_bounds__(kRowBlock) flush_remote_kernel(CacheView c) {
 // owner row is updated in place through the peer mapping.
 template <int VEC>
 __global__ void __launch_bounds__(kRowBlock) flush_resident_kernel(CacheView c) {
+    pdl_enter();
     using V = RowVec<VEC>;
     const unsigned lane = lane_id();
     const size_t warp_global = (size_t)blockIdx.x * kRowWarps + (threadIdx.x >> 5);
@@ -1101,6 +1225,7 @@ __global__ void __launch_bounds__(kRowBlock) flush_resident_kernel(CacheView c) 
 
 // Tell every owner how many slots of its two sections this rank filled.
 __global__ void publish_counts_kernel(CacheView c) {
+    pdl_enter();
     const int o = threadIdx.x;
     if (o >= c.pv.world)
         return;
@@ -1115,6 +1240,7 @@ __global__ void publish_counts_kernel(CacheView c) {
 // applies the pushed ones ROWS at a time.
 template <int VEC, int ROWS>
 __global__ void __launch_bounds__(kRowBlock) apply_mailbox_kernel(CacheView c, int src, int section) {
+    pdl_enter();
     using V = RowVec<VEC>;
     const unsigned lane = lane_id();
     const size_t warp_global = (size_t)blockIdx.x * kRowWarps + (threadIdx.x >> 5);
@@ -1164,6 +1290,7 @@ __global__ void __launch_bounds__(kRowBlock) apply_mailbox_kernel(CacheView c, i
 }
 
 __global__ void barrier_error_kernel(CacheRegs *r, const u32 *barrier_err) {
+    pdl_enter();
     if (*barrier_err)
         atomicMax(&r->error, (u32)E_BARRIER);
 }
@@ -1171,6 +1298,7 @@ __global__ void barrier_error_kernel(CacheRegs *r, const u32 *barrier_err) {
 // dataless lines are dropped after the push (never inserted)
 __global__ void free_transient_kernel(CacheView c, const i32 *uslot, const u32 *miss_list, int batch,
                                       int flushed) {
+    pdl_enter();
     CacheRegs *r = c.regs;
     if (flushed && blockIdx.x == 0 && threadIdx.x == 0)
         r->pending = 0; // the pending victims have just been pushed
@@ -1187,6 +1315,7 @@ __global__ void free_transient_kernel(CacheView c, const i32 *uslot, const u32 *
 // Deferred cleanup of push_pull (cache.cc:413-421): version += updates; zeroGrad — on every line
 // of the push batch that was pushed and holds data, wherever it is now (resident or evicted).
 __global__ void cleanup_pushed_kernel(CacheView c, const i32 *uslot, i64 push_bound) {
+    pdl_enter();
     const u32 U = c.regs->U2;
     for (u32 u = blockIdx.x * blockDim.x + threadIdx.x; u < U; u += gridDim.x * blockDim.x) {
         const i32 s = uslot[u];
@@ -1201,6 +1330,7 @@ __global__ void cleanup_pushed_kernel(CacheView c, const i32 *uslot, i64 push_bo
 }
 
 __global__ void convert_keys_kernel(const float *in, u64 *out, size_t n) {
+    pdl_enter();
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n)
         out[i] = key_from_f32(in[i]);
@@ -1210,6 +1340,7 @@ __global__ void convert_keys_kernel(const float *in, u64 *out, size_t n) {
 // maintenance / debug kernels
 // =====================================================================================
 __global__ void init_slots_kernel(CacheView c) {
+    pdl_enter();
     for (size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x; s < c.capacity;
          s += (size_t)gridDim.x * blockDim.x) {
         c.slot_prio[s] = PRIO_NONE;
@@ -1224,16 +1355,20 @@ __global__ void init_slots_kernel(CacheView c) {
 }
 
 __global__ void rebuild_index_kernel(CacheView c) {
+    pdl_enter();
+    u32 fresh = 0;
     for (size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x; s < c.capacity;
          s += (size_t)gridDim.x * blockDim.x) {
         u8 stt = c.slot_state[s];
         if (stt == S_CACHED || stt == S_STORE)
-            if (!ht_insert(c.ht, c.ht_mask, c.slot_key[s], (u32)s, &c.regs->ht_occupied))
+            if (!ht_insert(c.ht, c.ht_mask, c.slot_key[s], (u32)s, fresh))
                 atomicMax(&c.regs->error, (u32)E_INDEX_FULL);
     }
+    add_occupied(&c.regs->ht_occupied, fresh);
 }
 
 __global__ void collect_keys_kernel(CacheView c, u64 *out, u32 *count) {
+    pdl_enter();
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     const size_t rounds = (c.capacity + stride - 1) / stride;
     for (size_t it = 0; it < rounds; it++) {
@@ -1257,6 +1392,7 @@ struct PeekResult {
     u32 state;
 };
 __global__ void peek_kernel(CacheView c, u64 key, PeekResult *out) {
+    pdl_enter();
     i32 s = ht_find(c.ht, c.ht_mask, key);
     out->slot = s;
     if (s >= 0) {
@@ -1269,6 +1405,7 @@ __global__ void peek_kernel(CacheView c, u64 key, PeekResult *out) {
 
 // single-line insert(Embedding) support: overwrite or stage one line
 __global__ void set_line_kernel(CacheView c, i32 slot, i64 version, const float *data) {
+    pdl_enter();
     for (u32 k = threadIdx.x; k < c.width; k += blockDim.x)
         c.data[(size_t)slot * c.width + k] = data[k];
     if (threadIdx.x == 0) {
@@ -1280,6 +1417,7 @@ __global__ void set_line_kernel(CacheView c, i32 slot, i64 version, const float 
 // policy effect of re-inserting a resident key (lru_cache.cc:11-16, lfu_cache.cc:16-19,
 // lfuopt_cache.cc:10-17)
 __global__ void reinsert_touch_kernel(CacheView c, i32 s) {
+    pdl_enter();
     CacheRegs *r = c.regs;
     const u64 stamp = r->clock;
     if (c.policy == HB_POLICY_LRU) {
@@ -1293,10 +1431,12 @@ __global__ void reinsert_touch_kernel(CacheView c, i32 s) {
     }
 }
 __global__ void single_key_kernel(u64 *uniq, u32 *num_unique, u64 key) {
+    pdl_enter();
     uniq[0] = key;
     *num_unique = 1;
 }
 __global__ void read_slot_kernel(const i32 *uslot, i32 *out) {
+    pdl_enter();
     *out = uslot[0];
 }
 
@@ -1312,6 +1452,7 @@ __device__ __forceinline__ float u01(u64 bits) { // (0,1]
 }
 __global__ void table_init_kernel(float *rows, size_t nelem, size_t elem_begin, int init_type,
                                   float a, float b, u64 seed) {
+    pdl_enter();
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nelem;
          i += (size_t)gridDim.x * blockDim.x) {
         const u64 g = elem_begin + i;
@@ -1466,16 +1607,33 @@ float *rows_stage(hb_cache *c, size_t n, int which) {
 
 void maybe_rebuild_index(hb_cache *c, size_t incoming) {
     c->occ_upper += incoming;
-    if (c->occ_upper * 4 <= c->ht_size * 3)
+    c->incoming_ring[c->calls % hb_cache::kRing] = incoming;
+    if (c->occ_upper * 2 <= c->ht_size)
+        return;
+    // the records of finished calls carry the real occupancy: refresh the bound from the newest
+    // one that has completed before paying for a synchronisation
+    for (uint64_t back = 1; back <= std::min<uint64_t>(c->calls, 64); back++) {
+        const uint64_t call = c->calls - back;
+        const int idx = (int)(call % hb_cache::kRing);
+        if (cudaEventQuery(c->ev_end[idx]) != cudaSuccess)
+            continue;
+        size_t since = incoming;
+        for (uint64_t k = call + 1; k < c->calls; k++)
+            since += c->incoming_ring[k % hb_cache::kRing];
+        c->occ_upper = std::min(c->occ_upper, (size_t)c->ring[idx].ht_occupied + since);
+        break;
+    }
+    (void)cudaGetLastError(); // cudaErrorNotReady of the queries is not an error
+    if (c->occ_upper * 2 <= c->ht_size)
         return;
     HB_CUDA(cudaStreamSynchronize(c->stream));
     CacheRegs regs;
     HB_CUDA(cudaMemcpy(&regs, c->view.regs, sizeof(regs), cudaMemcpyDeviceToHost));
-    if ((size_t)regs.ht_occupied + incoming > c->ht_size * 3 / 4) {
+    if ((size_t)regs.ht_occupied + incoming > c->ht_size / 2) {
         // tombstones have piled up: clear and re-insert the resident lines
         HB_CUDA(cudaMemsetAsync(c->view.ht, 0xff, c->ht_size * sizeof(HtEntry), c->stream));
         HB_CUDA(cudaMemsetAsync(&c->view.regs->ht_occupied, 0, sizeof(u32), c->stream));
-        rebuild_index_kernel<<<lin_grid(c->view.capacity), 256, 0, c->stream>>>(c->view);
+        HB_LAUNCH(rebuild_index_kernel, lin_grid(c->view.capacity), 256, 0, c->stream, c->view);
         HB_LAUNCHED();
         c->occ_upper = regs.size + incoming;
     } else {
@@ -1496,19 +1654,20 @@ void begin_call(hb_cache *c, bool flush = false) {
     int idx = (int)(c->calls % hb_cache::kRing);
     c->phase_mask[idx] = 0;
     HB_CUDA(cudaEventRecord(c->ev_begin[idx], c->stream));
-    op_begin_kernel<<<1, 1, 0, c->stream>>>(c->view.regs, clk_of(c), flush ? 1 : 0);
+    HB_LAUNCH(op_begin_kernel, 1, 1, 0, c->stream, c->view.regs, clk_of(c), flush ? 1 : 0);
     HB_LAUNCHED();
 }
 
 void end_call(hb_cache *c, int last_stage, u32 kind, size_t n, bool inserted) {
     int idx = (int)(c->calls % hb_cache::kRing);
-    op_end_kernel<<<1, 1, 0, c->stream>>>(c->view, clk_of(c), last_stage, c->dev_record, kind, (u32)n,
+    HB_LAUNCH(op_end_kernel, 1, 1, 0, c->stream, c->view, clk_of(c), last_stage, c->dev_record, kind, (u32)n,
                                           inserted ? 1 : 0);
     HB_LAUNCHED();
     HB_CUDA(cudaMemcpyAsync(&c->ring[idx], c->dev_record, sizeof(PerfRecord), cudaMemcpyDeviceToHost,
                             c->stream));
     HB_CUDA(cudaEventRecord(c->ev_end[idx], c->stream));
     c->calls++;
+    c->incoming_ring[c->calls % hb_cache::kRing] = 0;
 }
 
 // sort + unique + resolve (+ alloc) of one key batch
@@ -1527,15 +1686,15 @@ void resolve_batch(hb_cache *c, const void *dev_keys, int kind, size_t n, int ba
     ws.sorted_n = n;
     if (marks)
         mark(c, 0);
-    u32 ntiles = (u32)std::max(1, ceil_div(n, kScanBlock));
+    u32 ntiles = (u32)std::max(1, ceil_div(n, kScanBlock * kResolveItems));
     u64 *clk = clk_of(c);
-    resolve_kernel<<<ntiles, kScanBlock, 0, st>>>(c->view, ws.uniq, ws.num_unique, c->uslot[batch],
+    HB_LAUNCH(resolve_kernel, ntiles, kScanBlock, 0, st, c->view, ws.uniq, ws.num_unique, c->uslot[batch],
                                                   c->miss_list[batch], c->bypass ? 1 : 0,
                                                   ws.next_scan(), ntiles, clk + clk_stage,
                                                   clk + clk_stage + 1, batch);
     HB_LAUNCHED();
     if (n) {
-        alloc_kernel<<<lin_grid(n), 256, 0, st>>>(c->view, ws.uniq, c->uslot[batch],
+        HB_LAUNCH(alloc_kernel, lin_grid(n), 256, 0, st, c->view, ws.uniq, c->uslot[batch],
                                                   c->miss_list[batch], batch, dataless ? 1 : 0);
         HB_LAUNCHED();
     }
@@ -1552,10 +1711,10 @@ void run_sync(hb_cache *c, size_t n) {
         return;
     int grid = row_grid((n + 31) / 32);
     if (c->width % 4 == 0)
-        sync_kernel<4, 4><<<grid, kRowBlock, 0, c->stream>>>(c->view, c->ws[0].uniq, c->uslot[0],
+        HB_LAUNCH((sync_kernel<4, 4>), grid, kRowBlock, 0, c->stream, c->view, c->ws[0].uniq, c->uslot[0],
                                                              c->pull_bound);
     else
-        sync_kernel<1, 4><<<grid, kRowBlock, 0, c->stream>>>(c->view, c->ws[0].uniq, c->uslot[0],
+        HB_LAUNCH((sync_kernel<1, 4>), grid, kRowBlock, 0, c->stream, c->view, c->ws[0].uniq, c->uslot[0],
                                                              c->pull_bound);
     HB_LAUNCHED();
 }
@@ -1566,40 +1725,42 @@ void run_gather(hb_cache *c, size_t n, float *dev_dest) {
     IndexFromSlots idx{c->uslot[0], c->ws[0].inverse};
     int grid = row_grid((n + 3) / 4);
     if (vec4(c, dev_dest))
-        gather_rows_kernel<4, 4, IndexFromSlots>
-            <<<grid, kRowBlock, 0, c->stream>>>(c->view.data, dev_dest, n, c->width, idx);
+        HB_LAUNCH((gather_rows_kernel<4, 4, IndexFromSlots>), grid, kRowBlock, 0, c->stream, c->view.data, dev_dest, n, c->width, idx);
     else
-        gather_rows_kernel<1, 4, IndexFromSlots>
-            <<<grid, kRowBlock, 0, c->stream>>>(c->view.data, dev_dest, n, c->width, idx);
+        HB_LAUNCH((gather_rows_kernel<1, 4, IndexFromSlots>), grid, kRowBlock, 0, c->stream, c->view.data, dev_dest, n, c->width, idx);
     HB_LAUNCHED();
 }
 
 void run_insert(hb_cache *c, size_t n, int clk_stage) {
     cudaStream_t st = c->stream;
     u64 *clk = clk_of(c);
-    plan_insert_kernel<<<1, 256, 0, st>>>(c->view, c->bypass ? 1 : 0, clk + clk_stage,
+    HB_LAUNCH(plan_insert_kernel, 1, 256, 0, st, c->view, c->bypass ? 1 : 0, clk + clk_stage,
                                           clk + clk_stage + 1);
     HB_LAUNCHED();
     if (!n)
         return;
     int sgrid = lin_grid(c->view.capacity);
-    sel_hist_kernel<<<sgrid, 256, 0, st>>>(c->view);
+    // few fat CTAs: every CTA ends with one global atomic per non-empty bin of its histogram
+    const int hgrid = sm_count() * 2;
+    HB_LAUNCH(sel_hist_kernel, hgrid, 1024, 0, st, c->view, 0);
     HB_LAUNCHED();
-    sel_collect_kernel<<<sgrid, 256, 0, st>>>(c->view);
+    HB_LAUNCH(sel_hist_kernel, hgrid, 1024, 0, st, c->view, 1);
     HB_LAUNCHED();
-    sel_refine_kernel<<<1, 1024, 0, st>>>(c->view);
+    HB_LAUNCH(sel_collect_kernel, sgrid, 256, 0, st, c->view);
+    HB_LAUNCHED();
+    HB_LAUNCH(sel_refine_kernel, 1, 1024, 0, st, c->view);
     HB_LAUNCHED();
     if (c->policy != HB_POLICY_LRU) {
-        min_use_kernel<<<sgrid, 256, 0, st>>>(c->view);
+        HB_LAUNCH(min_use_kernel, sgrid, 256, 0, st, c->view);
         HB_LAUNCHED();
-        min_prio_kernel<<<sgrid, 256, 0, st>>>(c->view);
+        HB_LAUNCH(min_prio_kernel, sgrid, 256, 0, st, c->view);
         HB_LAUNCHED();
-        min_pick_kernel<<<sgrid, 256, 0, st>>>(c->view);
+        HB_LAUNCH(min_pick_kernel, sgrid, 256, 0, st, c->view);
         HB_LAUNCHED();
     }
-    evict_apply_kernel<<<lin_grid(n), 256, 0, st>>>(c->view);
+    HB_LAUNCH(evict_apply_kernel, lin_grid(n), 256, 0, st, c->view);
     HB_LAUNCHED();
-    insert_new_kernel<<<lin_grid(n), 256, 0, st>>>(c->view, c->uslot[0], c->miss_list[0]);
+    HB_LAUNCH(insert_new_kernel, lin_grid(n), 256, 0, st, c->view, c->uslot[0], c->miss_list[0]);
     HB_LAUNCHED();
 }
 
@@ -1610,20 +1771,20 @@ void run_insert(hb_cache *c, size_t n, int clk_stage) {
 void exchange_pushes(hb_cache *c) {
     cudaStream_t st = c->stream;
     const int world = c->view.pv.world;
-    publish_counts_kernel<<<1, 32, 0, st>>>(c->view);
+    HB_LAUNCH(publish_counts_kernel, 1, 32, 0, st, c->view);
     HB_LAUNCHED();
     device_barrier(st);
     const int grid = sm_count() * 4;
     for (int src = 0; src < world; src++)
         for (int section = 0; section < 2; section++) {
             if (c->width % 4 == 0)
-                apply_mailbox_kernel<4, 4><<<grid, kRowBlock, 0, st>>>(c->view, src, section);
+                HB_LAUNCH((apply_mailbox_kernel<4, 4>), grid, kRowBlock, 0, st, c->view, src, section);
             else
-                apply_mailbox_kernel<1, 4><<<grid, kRowBlock, 0, st>>>(c->view, src, section);
+                HB_LAUNCH((apply_mailbox_kernel<1, 4>), grid, kRowBlock, 0, st, c->view, src, section);
             HB_LAUNCHED();
         }
     device_barrier(st);
-    barrier_error_kernel<<<1, 1, 0, st>>>(c->view.regs, g_comm.barrier_err);
+    HB_LAUNCH(barrier_error_kernel, 1, 1, 0, st, c->view.regs, g_comm.barrier_err);
     HB_LAUNCHED();
 }
 
@@ -1633,7 +1794,7 @@ void run_accumulate(hb_cache *c, size_t n, int batch, const float *dev_grads, co
     cudaStream_t st = c->stream;
     KeyWorkspace &ws = c->ws[batch];
     if (c->view.pv.world > 1) {
-        owner_bounds_kernel<<<1, 32, 0, st>>>(c->view, ws.uniq, ws.num_unique);
+        HB_LAUNCH(owner_bounds_kernel, 1, 32, 0, st, c->view, ws.uniq, ws.num_unique);
         HB_LAUNCHED();
     }
     if (n) {
@@ -1659,9 +1820,9 @@ void run_accumulate(hb_cache *c, size_t n, int batch, const float *dev_grads, co
         if (pend) {
             int grid = row_grid(pend);
             if (c->width % 4 == 0)
-                flush_remote_kernel<4><<<grid, kRowBlock, 0, st>>>(c->view);
+                HB_LAUNCH(flush_remote_kernel<4>, grid, kRowBlock, 0, st, c->view);
             else
-                flush_remote_kernel<1><<<grid, kRowBlock, 0, st>>>(c->view);
+                HB_LAUNCH(flush_remote_kernel<1>, grid, kRowBlock, 0, st, c->view);
             HB_LAUNCHED();
         }
         exchange_pushes(c);
@@ -1669,17 +1830,15 @@ void run_accumulate(hb_cache *c, size_t n, int batch, const float *dev_grads, co
         int grid = row_grid(pend);
         if (c->width % 4 == 0) {
             FlushPending<4> f{c->view, 0};
-            foreach_row_kernel<4, FlushPending<4>>
-                <<<grid, kRowBlock, 0, st>>>(0, &c->view.regs->flushed, c->width, f);
+            HB_LAUNCH((foreach_row_kernel<4, FlushPending<4>>), grid, kRowBlock, 0, st, 0, &c->view.regs->flushed, c->width, f);
         } else {
             FlushPending<1> f{c->view, 0};
-            foreach_row_kernel<1, FlushPending<1>>
-                <<<grid, kRowBlock, 0, st>>>(0, &c->view.regs->flushed, c->width, f);
+            HB_LAUNCH((foreach_row_kernel<1, FlushPending<1>>), grid, kRowBlock, 0, st, 0, &c->view.regs->flushed, c->width, f);
         }
         HB_LAUNCHED();
     }
     c->pending_upper = 0;
-    free_transient_kernel<<<lin_grid(n), 256, 0, st>>>(c->view, c->uslot[batch], c->miss_list[batch],
+    HB_LAUNCH(free_transient_kernel, lin_grid(n), 256, 0, st, c->view, c->uslot[batch], c->miss_list[batch],
                                                        batch, 1);
     HB_LAUNCHED();
 }
@@ -1705,7 +1864,7 @@ const u64 *stage_push_keys(hb_cache *c, const void *push_keys, int kind, size_t 
         dev = raw;
     }
     if (kind == HB_KEYS_F32) {
-        convert_keys_kernel<<<ceil_div(n_push, 256), 256, 0, st>>>((const float *)dev, out, n_push);
+        HB_LAUNCH(convert_keys_kernel, ceil_div(n_push, 256), 256, 0, st, (const float *)dev, out, n_push);
         HB_LAUNCHED();
         return out;
     }
@@ -1807,7 +1966,7 @@ int hb_table_init(hb_table *t, int init_type, double a, double b, unsigned long 
     Guard g(t->device);
     size_t nelem = t->nrows * t->width;
     if (nelem) {
-        table_init_kernel<<<lin_grid(nelem), 256>>>(t->rows, nelem, t->row_begin * t->width, init_type,
+        HB_LAUNCH(table_init_kernel, lin_grid(nelem), 256, 0, 0, t->rows, nelem, t->row_begin * t->width, init_type,
                                                     (float)a, (float)b, splitmix64(seed));
         HB_LAUNCHED();
         HB_CUDA(cudaDeviceSynchronize());
@@ -1903,7 +2062,10 @@ int hb_cache_create(int policy, size_t limit, size_t length, size_t width, int n
     v.width = (u32)width;
     v.policy = policy;
     size_t hs = 1024;
-    while (hs < 2 * std::max<size_t>(limit, 1))
+    // >= 4 entries per resident line and a rebuild when half of the entries are used (lines +
+    // tombstones): an unsuccessful probe (every miss of a batch) walks (1 + 1/(1-a)^2)/2 entries,
+    // 2.5 at a = 1/2 against 8.5 at 3/4; 16 B per entry is cheap next to the rows
+    while (hs < 4 * std::max<size_t>(limit, 1))
         hs <<= 1;
     c->ht_size = hs;
     v.ht_mask = (u32)(hs - 1);
@@ -1922,7 +2084,7 @@ int hb_cache_create(int policy, size_t limit, size_t length, size_t width, int n
     dmalloc(v.victims, cap);
     dmalloc(v.cand_prio, 2 * cap);
     dmalloc(v.cand_slot, 2 * cap);
-    dmalloc(v.sel_hist, kSelBins);
+    dmalloc(v.sel_hist, 2 * kSelBins);
     dmalloc(v.regs, 1);
     v.trows = t->rows;
     v.tver = t->ver;
@@ -1958,7 +2120,7 @@ int hb_cache_create(int policy, size_t limit, size_t length, size_t width, int n
     std::memset(&regs, 0, sizeof(regs));
     regs.free_top = (u32)cap;
     HB_CUDA(cudaMemcpy(v.regs, &regs, sizeof(regs), cudaMemcpyHostToDevice));
-    init_slots_kernel<<<lin_grid(cap), 256>>>(v);
+    HB_LAUNCH(init_slots_kernel, lin_grid(cap), 256, 0, 0, v);
     HB_LAUNCHED();
     char *rec = nullptr;
     HB_CUDA(cudaMalloc((void **)&rec, 128));
@@ -2149,7 +2311,7 @@ int hb_cache_push_pull(hb_cache *c, const void *pull_keys, int pull_kind, size_t
     run_gather(c, n_pull, ddest);
     run_insert(c, n_pull, 2);
     if (n_push) {
-        cleanup_pushed_kernel<<<lin_grid(n_push), 256, 0, st>>>(c->view, c->uslot[1], c->push_bound);
+        HB_LAUNCH(cleanup_pushed_kernel, lin_grid(n_push), 256, 0, st, c->view, c->uslot[1], c->push_bound);
         HB_LAUNCHED();
     }
     c->pending_upper += n_pull;
@@ -2176,9 +2338,9 @@ int hb_cache_flush(hb_cache *c) {
             continue;
         int grid = row_grid((c->view.capacity + 31) / 32);
         if (c->width % 4 == 0)
-            flush_resident_kernel<4><<<grid, kRowBlock, 0, c->stream>>>(c->view);
+            HB_LAUNCH(flush_resident_kernel<4>, grid, kRowBlock, 0, c->stream, c->view);
         else
-            flush_resident_kernel<1><<<grid, kRowBlock, 0, c->stream>>>(c->view);
+            HB_LAUNCH(flush_resident_kernel<1>, grid, kRowBlock, 0, c->stream, c->view);
         HB_LAUNCHED();
     }
     HB_CUDA(cudaStreamSynchronize(c->stream));
@@ -2346,7 +2508,7 @@ int hb_cache_size(hb_cache *c, size_t *size) {
 static PeekResult peek(hb_cache *c, uint64_t key) {
     PeekResult *d = nullptr, h;
     HB_CUDA(cudaMalloc((void **)&d, sizeof(PeekResult)));
-    peek_kernel<<<1, 1, 0, c->stream>>>(c->view, key, d);
+    HB_LAUNCH(peek_kernel, 1, 1, 0, c->stream, c->view, key, d);
     g_launches++;
     cudaError_t e = cudaMemcpyAsync(&h, d, sizeof(h), cudaMemcpyDeviceToHost, c->stream);
     if (e == cudaSuccess)
@@ -2371,7 +2533,7 @@ int hb_cache_keys(hb_cache *c, uint64_t *keys, size_t capacity, size_t *n) {
     dmalloc(dkeys, c->view.capacity);
     dmalloc(dcount, 1);
     HB_CUDA(cudaMemsetAsync(dcount, 0, sizeof(u32), c->stream));
-    collect_keys_kernel<<<lin_grid(c->view.capacity), 256, 0, c->stream>>>(c->view, dkeys, dcount);
+    HB_LAUNCH(collect_keys_kernel, lin_grid(c->view.capacity), 256, 0, c->stream, c->view, dkeys, dcount);
     HB_LAUNCHED();
     u32 count = 0;
     HB_CUDA(cudaMemcpyAsync(&count, dcount, sizeof(u32), cudaMemcpyDeviceToHost, c->stream));
@@ -2424,18 +2586,18 @@ int hb_cache_touch(hb_cache *c, uint64_t key, int *found, int64_t *version, floa
     begin_call(c);
     ws.reset_scans(st);
     ws.sorted_valid = false;
-    single_key_kernel<<<1, 1, 0, st>>>(ws.uniq, ws.num_unique, key);
+    HB_LAUNCH(single_key_kernel, 1, 1, 0, st, ws.uniq, ws.num_unique, key);
     HB_LAUNCHED();
     u64 *clk = clk_of(c);
-    resolve_kernel<<<1, kScanBlock, 0, st>>>(c->view, ws.uniq, ws.num_unique, c->uslot[0],
+    HB_LAUNCH(resolve_kernel, 1, kScanBlock, 0, st, c->view, ws.uniq, ws.num_unique, c->uslot[0],
                                              c->miss_list[0], c->bypass ? 1 : 0, ws.next_scan(), 1,
                                              clk, clk + 1, 0);
     HB_LAUNCHED();
     // a miss reserved a slot for a fresh line; materialise and hand it back (lookup() alone
     // allocates nothing)
-    alloc_kernel<<<1, 32, 0, st>>>(c->view, ws.uniq, c->uslot[0], c->miss_list[0], 0, 0);
+    HB_LAUNCH(alloc_kernel, 1, 32, 0, st, c->view, ws.uniq, c->uslot[0], c->miss_list[0], 0, 0);
     HB_LAUNCHED();
-    free_transient_kernel<<<1, 32, 0, st>>>(c->view, c->uslot[0], c->miss_list[0], 0, 0);
+    HB_LAUNCH(free_transient_kernel, 1, 32, 0, st, c->view, c->uslot[0], c->miss_list[0], 0, 0);
     HB_LAUNCHED();
     end_call(c, 1, 0, 1, false);
     HB_CUDA(cudaStreamSynchronize(st));
@@ -2461,10 +2623,10 @@ int hb_cache_insert(hb_cache *c, uint64_t key, int64_t version, const float *dat
     HB_CUDA(cudaMemcpyAsync(ddata, data, c->width * sizeof(float), cudaMemcpyDefault, st));
     PeekResult r = peek(c, key);
     if (r.slot >= 0) {
-        set_line_kernel<<<1, 128, 0, st>>>(c->view, r.slot, version, ddata);
+        HB_LAUNCH(set_line_kernel, 1, 128, 0, st, c->view, r.slot, version, ddata);
         HB_LAUNCHED();
         if (r.state == S_CACHED) {
-            reinsert_touch_kernel<<<1, 1, 0, st>>>(c->view, r.slot);
+            HB_LAUNCH(reinsert_touch_kernel, 1, 1, 0, st, c->view, r.slot);
             HB_LAUNCHED();
         }
     } else {
@@ -2472,24 +2634,24 @@ int hb_cache_insert(hb_cache *c, uint64_t key, int64_t version, const float *dat
         begin_call(c);
         ws.reset_scans(st);
         ws.sorted_valid = false;
-        single_key_kernel<<<1, 1, 0, st>>>(ws.uniq, ws.num_unique, key);
+        HB_LAUNCH(single_key_kernel, 1, 1, 0, st, ws.uniq, ws.num_unique, key);
         HB_LAUNCHED();
         u64 *clk = clk_of(c);
         // bypass=1: resolve as a miss without touching anything, which allocates the fresh line
-        resolve_kernel<<<1, kScanBlock, 0, st>>>(c->view, ws.uniq, ws.num_unique, c->uslot[0],
+        HB_LAUNCH(resolve_kernel, 1, kScanBlock, 0, st, c->view, ws.uniq, ws.num_unique, c->uslot[0],
                                                  c->miss_list[0], 1, ws.next_scan(), 1, clk, clk, 0);
         HB_LAUNCHED();
-        alloc_kernel<<<1, 32, 0, st>>>(c->view, ws.uniq, c->uslot[0], c->miss_list[0], 0, 0);
+        HB_LAUNCH(alloc_kernel, 1, 32, 0, st, c->view, ws.uniq, c->uslot[0], c->miss_list[0], 0, 0);
         HB_LAUNCHED();
         i32 *dslot = nullptr, hslot = -1;
         dmalloc(dslot, 1);
-        read_slot_kernel<<<1, 1, 0, st>>>(c->uslot[0], dslot);
+        HB_LAUNCH(read_slot_kernel, 1, 1, 0, st, c->uslot[0], dslot);
         HB_LAUNCHED();
         HB_CUDA(cudaMemcpyAsync(&hslot, dslot, sizeof(i32), cudaMemcpyDeviceToHost, st));
         HB_CUDA(cudaStreamSynchronize(st));
         dfree(dslot);
         HB_CHECK(hslot >= 0, "no free slot for insert");
-        set_line_kernel<<<1, 128, 0, st>>>(c->view, hslot, version, ddata);
+        HB_LAUNCH(set_line_kernel, 1, 128, 0, st, c->view, hslot, version, ddata);
         HB_LAUNCHED();
         run_insert(c, 1, 0);
         c->pending_upper += 1;

@@ -153,6 +153,13 @@ struct CacheRegs {
     // second batch of a push_pull call
     u32 U2, M2, alloc_base2;
     u32 sel_done; // blocks of sel_hist_kernel that have added their bins (zeroed by plan_insert)
+    // windowed first level of the victim selection (see sel_hist_kernel)
+    u32 sel_done2;    // same for the full-range fallback pass
+    u32 sel_cut;      // persistent: bins the next call's window covers (0 = not known yet)
+    u32 sel_cut_eff;  // window of the running call
+    u32 sel_above;    // class lines at or above the window
+    u32 sel_fallback; // the threshold was not inside the window: run the full-range pass
+    u32 pad1;
 };
 
 // Everything a kernel needs to address the cache (passed by value).
@@ -179,7 +186,7 @@ struct CacheView {
     u32 *victims;    // [capacity]
     u64 *cand_prio;  // [2][capacity] boundary candidates (ping-pong)
     u32 *cand_slot;  // [2][capacity]
-    u32 *sel_hist;   // [kSelBins]
+    u32 *sel_hist;   // [2][kSelBins]: windowed pass, full-range fallback
     CacheRegs *regs;
     // owner shard (same GPU)
     float *trows;
@@ -254,6 +261,7 @@ struct hb_cache {
     bool perf_phases = false;
     // host-side upper bound of index occupancy (refreshed at wait)
     size_t occ_upper = 0;
+    size_t incoming_ring[kRing] = {}; // keys each call could add to the index (per call of the ring)
     size_t pending_upper = 0;
     int key_bits = 64;
     hb::u32 hot_threshold = 64; // segments longer than this take the column-split path

@@ -115,6 +115,7 @@ struct PeerFlags {
 };
 
 __global__ void peer_barrier_kernel(PeerFlags pf, int rank, int world, u64 epoch, u32 *err) {
+    pdl_enter();
     const int r = threadIdx.x;
     if (r >= world)
         return;
@@ -142,7 +143,7 @@ void device_barrier(cudaStream_t st) {
         pf.peer[r] = g_comm.peer_flags[r];
     pf.local = g_comm.flags;
     g_comm.epoch++;
-    peer_barrier_kernel<<<1, 32, 0, st>>>(pf, g_comm.rank, g_comm.world, g_comm.epoch,
+    HB_LAUNCH(peer_barrier_kernel, 1, 32, 0, st, pf, g_comm.rank, g_comm.world, g_comm.epoch,
                                           g_comm.barrier_err);
     HB_LAUNCHED();
 }

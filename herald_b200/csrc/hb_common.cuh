@@ -7,6 +7,7 @@
 #include <atomic>
 #include <stdexcept>
 #include <string>
+#include <utility>
 
 #include "../../include/herald_b200.h"
 
@@ -73,8 +74,40 @@ inline int ceil_div(size_t a, size_t b) {
 
 int sm_count();
 u32 default_hot_threshold();
+bool pdl_enabled(); // $HERALD_PDL != 0 (default on)
 
 #ifdef __CUDACC__
+// ---- launches: programmatic dependent launch (PDL) ----------------------------------------
+// A step is 30+ short kernels on one stream; with plain stream order every boundary costs a full
+// launch latency.  Every kernel of the library is launched with programmatic stream
+// serialization and starts with pdl_enter(): griddepcontrol.wait (block until the previous kernel
+// has COMPLETED and its writes are visible), then griddepcontrol.launch_dependents (the next
+// kernel's CTAs may become resident now and park at their own wait).  No kernel touches memory
+// before its wait, so ordering is exactly stream order; only the launch latency is overlapped,
+// one kernel deep.
+__device__ __forceinline__ void pdl_enter() {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
+template <class... P, class... A>
+inline void launch_kernel(void (*kernel)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                          A &&...args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    HB_CUDA(cudaLaunchKernelEx(&cfg, kernel, static_cast<P>(std::forward<A>(args))...));
+}
+#define HB_LAUNCH(kernel, grid, block, smem, stream, ...) \
+    hb::launch_kernel(kernel, dim3(grid), dim3(block), (size_t)(smem), stream, ##__VA_ARGS__)
+
 // ---- device helpers --------------------------------------------------------
 constexpr unsigned FULL = 0xffffffffu;
 

@@ -284,6 +284,7 @@ __global__ void __launch_bounds__(kRowBlock)
                           const float *__restrict__ param, float *__restrict__ m,
                           float *__restrict__ v, float *__restrict__ update,
                           float *__restrict__ row_sq, size_t n, size_t D, AdamScalars s) {
+    pdl_enter();
     const unsigned lane = lane_id();
     const size_t warp_global = (size_t)blockIdx.x * kRowWarps + (threadIdx.x >> 5);
     const size_t nwarps = (size_t)gridDim.x * kRowWarps;
@@ -319,6 +320,7 @@ __global__ void __launch_bounds__(kRowBlock)
 // norms[0] = ||param[ids]||_2, norms[1] = ||update||_2 (CUDNN_REDUCE_TENSOR_NORM2, :667-699)
 __global__ void __launch_bounds__(1024) lamb_norms_kernel(const float *__restrict__ row_sq, size_t n,
                                                           float *norms) {
+    pdl_enter();
     __shared__ double sh[2][1024];
     double sp = 0.0, su = 0.0;
     for (size_t r = threadIdx.x; r < n; r += 1024) {
@@ -345,6 +347,7 @@ __global__ void __launch_bounds__(kRowBlock)
     lamb_step_kernel(const float *__restrict__ ids, const float *__restrict__ update,
                      float *__restrict__ param, const float *__restrict__ norms, size_t n, size_t D,
                      float lr, float weight_decay) {
+    pdl_enter();
     const unsigned lane = lane_id();
     const size_t warp_global = (size_t)blockIdx.x * kRowWarps + (threadIdx.x >> 5);
     const size_t nwarps = (size_t)gridDim.x * kRowWarps;
@@ -378,6 +381,7 @@ float *float_scratch(cudaStream_t st, size_t count) {
 
 __global__ void momentum_second_phase(float *param, float *veloc, float momentum, bool nesterov,
                                       size_t size) {
+    pdl_enter();
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     size_t stride = (size_t)gridDim.x * blockDim.x;
     for (; i < size; i += stride) {
@@ -394,6 +398,7 @@ __global__ void momentum_second_phase(float *param, float *veloc, float momentum
 
 __global__ void emit_unique_f32(const u64 *uniq, const u32 *inverse, const u32 *num_unique,
                                 size_t n, float *unique_out, float *inverse_out, i64 *count_out) {
+    pdl_enter();
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const u32 U = *num_unique;
     if (i < U)
@@ -416,9 +421,9 @@ void launch_rows(bool v4, size_t n, size_t D, cudaStream_t st, F1 f1, F4 f4) {
         return;
     int grid = row_grid(n);
     if (v4)
-        foreach_row_kernel<4, F4><<<grid, kRowBlock, 0, st>>>(n, nullptr, D, f4);
+        HB_LAUNCH((foreach_row_kernel<4, F4>), grid, kRowBlock, 0, st, n, nullptr, D, f4);
     else
-        foreach_row_kernel<1, F1><<<grid, kRowBlock, 0, st>>>(n, nullptr, D, f1);
+        HB_LAUNCH((foreach_row_kernel<1, F1>), grid, kRowBlock, 0, st, n, nullptr, D, f1);
     HB_LAUNCHED();
 }
 
@@ -452,9 +457,9 @@ int DLGpuEmbeddingLookUp(const DLArrayHandle input, const DLArrayHandle ids, DLA
         IndexFromF32 idx{(const float *)ids->data};
         int grid = row_grid((n + 3) / 4);
         if (vec4_ok(D, {src, dst}))
-            gather_rows_kernel<4, 4, IndexFromF32><<<grid, kRowBlock, 0, st>>>(src, dst, n, D, idx);
+            HB_LAUNCH((gather_rows_kernel<4, 4, IndexFromF32>), grid, kRowBlock, 0, st, src, dst, n, D, idx);
         else
-            gather_rows_kernel<1, 4, IndexFromF32><<<grid, kRowBlock, 0, st>>>(src, dst, n, D, idx);
+            HB_LAUNCH((gather_rows_kernel<1, 4, IndexFromF32>), grid, kRowBlock, 0, st, src, dst, n, D, idx);
         HB_LAUNCHED();
     }
     HB_API_END();
@@ -559,7 +564,7 @@ int MomentumOptimizerSparseUpdate(DLArrayHandle param, const DLArrayHandle grad_
     }
     size_t total = numel(param);
     int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)sm_count() * 16);
-    momentum_second_phase<<<std::max(blocks, 1), 256, 0, st>>>(p, vel, momentum, nesterov, total);
+    HB_LAUNCH(momentum_second_phase, std::max(blocks, 1), 256, 0, st, p, vel, momentum, nesterov, total);
     HB_LAUNCHED();
     HB_API_END();
 }
@@ -625,14 +630,14 @@ int LambOptimizerSparseUpdate(DLArrayHandle param, const DLArrayHandle grad_indi
         float *scratch = float_scratch(st, n * D + 2 * n + 2);
         float *update = scratch, *row_sq = scratch + n * D, *norms = row_sq + 2 * n;
         int grid = row_grid(n);
-        lamb_direction_kernel<<<grid, kRowBlock, 0, st>>>(ids, (const float *)grad_values->data, p,
+        HB_LAUNCH(lamb_direction_kernel, grid, kRowBlock, 0, st, ids, (const float *)grad_values->data, p,
                                                           (float *)expavg->data,
                                                           (float *)expavgsq->data, update, row_sq, n,
                                                           D, s);
         HB_LAUNCHED();
-        lamb_norms_kernel<<<1, 1024, 0, st>>>(row_sq, n, norms);
+        HB_LAUNCH(lamb_norms_kernel, 1, 1024, 0, st, row_sq, n, norms);
         HB_LAUNCHED();
-        lamb_step_kernel<<<grid, kRowBlock, 0, st>>>(ids, update, p, norms, n, D, lr, weight_decay);
+        HB_LAUNCH(lamb_step_kernel, grid, kRowBlock, 0, st, ids, update, p, norms, n, D, lr, weight_decay);
         HB_LAUNCHED();
     }
     HB_API_END();
@@ -647,7 +652,7 @@ int HBUniqueIndexedSlices(const DLArrayHandle ids, DLArrayHandle unique_ids, DLA
     // float32 carries integers exactly only below 2^24, but any float id is < 2^32 in practice
     Segments sg = build_segments((const float *)ids->data, n, 1ull << 32, st);
     int blocks = std::max(1, ceil_div(n, 256));
-    emit_unique_f32<<<blocks, 256, 0, st>>>(sg.ws->uniq, sg.ws->inverse, sg.ws->num_unique, n,
+    HB_LAUNCH(emit_unique_f32, blocks, 256, 0, st, sg.ws->uniq, sg.ws->inverse, sg.ws->num_unique, n,
                                             (float *)unique_ids->data, (float *)inverse->data,
                                             (i64 *)num_unique_dev);
     HB_LAUNCHED();

@@ -83,6 +83,7 @@ template <int VEC, int ROWS, class Index>
 __global__ void __launch_bounds__(kRowBlock)
     gather_rows_kernel(const float *__restrict__ src, float *__restrict__ dst, size_t n, size_t D,
                        Index index) {
+    pdl_enter();
     using V = RowVec<VEC>;
     const unsigned lane = lane_id();
     const size_t warp_global = (size_t)blockIdx.x * kRowWarps + (threadIdx.x >> 5);
@@ -138,9 +139,18 @@ __global__ void __launch_bounds__(kRowBlock)
 //     time: the metadata of all 32 is loaded lane-parallel, then the row / gradient / owner-row
 //     loads of ROWS segments are in flight together (128-bit per lane) before the first add.
 constexpr int kHotTileRows = 128; // occurrences per pipeline stage
-constexpr int kHotStagesDefault = 6; // 6 x 128 x 128 B = 96 KB of dynamic shared memory (x 2 CTAs/SM)
+// 3 x 128 x 128 B = 48 KB (+ 6 KB of indices) of dynamic shared memory per CTA, x 2 CTAs/SM.  Measured
+// on B200 (profiles/r01_segtrace_*.json): the per-occurrence rate of a hot chain does not depend on
+// the ring depth (3 .. 10 stages give 6.8 ns), but every 16 KB stage is taken from the SM's L1, and the
+// cold phase needs L1 lines for its 12 x 512 B loads in flight per warp: 6 stages -> 111 us, 3 -> 89 us.
+constexpr int kHotStagesDefault = 3;
 constexpr int kHotStagesMax = 12;
 constexpr int kHotStageBytes = kHotTileRows * 32 * 4;
+// dynamic shared memory of segment_reduce_kernel: the data ring + the index ring (2 x the ring
+// depth of the 16-column variant = 4 x stages tiles of kHotTileRows u32)
+constexpr size_t hot_smem_bytes(int stages) {
+    return (size_t)stages * kHotStageBytes + (size_t)4 * stages * kHotTileRows * 4;
+}
 constexpr u32 kVeryHot = 1024; // rows above this go first (longest-processing-time-first)
 
 // ring depth of the hot phase ($HERALD_HOT_STAGES, 3 .. 12): the bytes a CTA keeps in flight are
@@ -202,6 +212,7 @@ __device__ __forceinline__ u32 rows_warp_append(u32 *counter, bool pred) {
 static __global__ void __launch_bounds__(256)
     build_hot_lists_kernel(const u32 *__restrict__ seg_start, const u32 *__restrict__ num_unique,
                            u32 hot_threshold, HotLists hl) {
+    pdl_enter();
     const u32 U = *num_unique;
     const u32 stride = gridDim.x * blockDim.x;
     const u32 rounds = (U + stride - 1) / stride;
@@ -250,7 +261,7 @@ __device__ __forceinline__ void cp_async_wait() {
 // instruction.
 template <int W, bool WIDE, class F1>
 __device__ __forceinline__ void hot_chunk(const F1 &f1, const typename F1::Ctx &ctx, float *s_ring,
-                                          u32 S, const u32 *__restrict__ perm,
+                                          u32 *s_perm, u32 S, const u32 *__restrict__ perm,
                                           const float *__restrict__ vals, size_t D, u32 s0, u32 s1,
                                           u32 q) {
     static_assert(WIDE || W == 32, "the 4-byte copy path moves one 32-column chunk per warp");
@@ -270,36 +281,53 @@ __device__ __forceinline__ void hot_chunk(const F1 &f1, const typename F1::Ctx &
     const u32 my_off = WIDE ? (threadIdx.x % TPR) * 4 : lane;         // float offset in the chunk
     const bool cp_active = (size_t)q * W + my_off < D;
     const float *my_src = vals + (size_t)q * W + my_off;
-    u32 pv[CPT];
-    auto load_perm = [&](u32 tile) {
-#pragma unroll
-        for (int j = 0; j < CPT; j++) {
-            const u32 p = s0 + tile * kHotTileRows + my_row + (WIDE ? RPI * j : j);
-            pv[j] = (tile < ntiles && p < s1) ? perm[p] : 0xffffffffu;
-        }
+    // The occurrence indices (perm) travel through their own shared-memory ring of 2S tiles,
+    // copied S - 1 tiles ahead of the data copies that read them and committed in the same
+    // cp.async groups: a data copy never waits for an index load from global memory (with the
+    // indices prefetched one tile ahead in registers, every tile paid one L2/HBM latency:
+    // 10 ns per occurrence instead of the ~2.5 ns of the dependent FADD chain).
+    const u32 PS = 2 * S;
+    const u32 *seg_perm = perm + s0;
+    auto copy_perm = [&](u32 tile, u32 slot) {
+        const u32 i = tile * kHotTileRows + threadIdx.x;
+        if (threadIdx.x < kHotTileRows && i < cnt)
+            cp_async_f32(reinterpret_cast<float *>(s_perm + slot * kHotTileRows + threadIdx.x),
+                         reinterpret_cast<const float *>(seg_perm + i));
     };
     u32 issue_slot = 0; // (next tile to issue) % S, kept without a division
+    u32 pslot_r = 0;    // (next tile to issue) % 2S
+    u32 next_tile = 0;
     auto issue = [&]() {
         float *stage = s_ring + (size_t)issue_slot * kHotTileRows * W;
+        const u32 *pt = s_perm + pslot_r * kHotTileRows;
         issue_slot = issue_slot + 1 == S ? 0 : issue_slot + 1;
+        pslot_r = pslot_r + 1 == PS ? 0 : pslot_r + 1;
+        const u32 base = next_tile * kHotTileRows;
+        next_tile++;
 #pragma unroll
         for (int j = 0; j < CPT; j++) {
             const u32 row = my_row + (WIDE ? RPI * j : j);
-            if (pv[j] != 0xffffffffu && cp_active) {
+            if (base + row < cnt && cp_active) {
+                const u32 pi = pt[row];
                 if (WIDE)
-                    cp_async_16(stage + row * W + my_off, my_src + (size_t)pv[j] * D);
+                    cp_async_16(stage + row * W + my_off, my_src + (size_t)pi * D);
                 else
-                    cp_async_f32(stage + row * W + my_off, my_src + (size_t)pv[j] * D);
+                    cp_async_f32(stage + row * W + my_off, my_src + (size_t)pi * D);
             }
         }
-        cp_async_commit();
     };
+    // prologue: indices of tiles 0 .. 2S-3, then the data of tiles 0 .. S-2
+    for (u32 t = 0; t + 2 < PS && t < ntiles; t++)
+        copy_perm(t, t);
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
 #pragma unroll 1
     for (u32 k = 0; k < S - 1; k++) {
-        load_perm(k);
         issue();
+        cp_async_commit();
     }
-    load_perm(S - 1);
+    u32 pslot_w = PS - 2; // slot of index tile k + 2S - 2
     u32 read_slot = 0;
     for (u32 k = 0; k < ntiles; k++) {
         // groups are committed one per tile, in order: at most S - 2 newer than tile k may still
@@ -327,7 +355,9 @@ __device__ __forceinline__ void hot_chunk(const F1 &f1, const typename F1::Ctx &
             cp_async_wait<1>();
         __syncthreads(); // ... everyone's has; and stage k-1 has been consumed
         issue();         // tile k + S - 1 into the slot tile k - 1 occupied
-        load_perm(k + S);
+        copy_perm(k + PS - 2, pslot_w); // its slot held tile k - 2, last read S + 1 iterations ago
+        pslot_w = pslot_w + 1 == PS ? 0 : pslot_w + 1;
+        cp_async_commit();
         if (warp == 0 && active) {
             const float *stage = s_ring + (size_t)read_slot * kHotTileRows * W + lane;
             const u32 rows = min((u32)kHotTileRows, cnt - k * kHotTileRows);
@@ -370,9 +400,11 @@ __global__ void __launch_bounds__(kRowBlock, 2)
     segment_reduce_kernel(const u32 *__restrict__ seg_start, const u32 *__restrict__ perm,
                           const u32 *__restrict__ num_unique, const float *__restrict__ vals,
                           size_t D, u32 hot_threshold, HotLists hl, FV fv, F1 f1) {
-    extern __shared__ __align__(16) float s_ring[]; // [stages][kHotTileRows][32]
+    pdl_enter();
+    extern __shared__ __align__(16) float s_ring[]; // [stages][kHotTileRows][32], then the index ring
     __shared__ u32 s_item;
     const u32 S = (u32)hl.stages;
+    u32 *const s_perm = reinterpret_cast<u32 *>(s_ring + (size_t)S * kHotTileRows * 32); // [4S][kHotTileRows]
     u64 *const trace = hl.trace;
     u32 items_taken = 0;
     if (trace && threadIdx.x == 0 && blockIdx.x < kTraceCtas) {
@@ -386,6 +418,10 @@ __global__ void __launch_bounds__(kRowBlock, 2)
     const u32 U = *num_unique;
     fv.kernel_begin();
 
+    // Every CTA runs the hot items first, then the cold tickets.  (Measured alternative: letting one
+    // CTA of every SM start with the cold tickets makes the chains 2.5x slower — a hot chain's copies
+    // queue behind the cold neighbour's loads for the whole run instead of the second half — and
+    // the kernel went from 89 us to 200 us.)
     // ------------------------------- hot phase -------------------------------------------
     if (hot_threshold != 0xffffffffu) {
         // very hot rows are cut into 16-column chunks when the rows allow 16 B copies: half the
@@ -419,11 +455,11 @@ __global__ void __launch_bounds__(kRowBlock, 2)
             if (ok) {
                 if constexpr (WIDE) {
                     if (very)
-                        hot_chunk<16, true>(f1, ctx, s_ring, S * 2, perm, vals, D, s0, s1, q);
+                        hot_chunk<16, true>(f1, ctx, s_ring, s_perm, S * 2, perm, vals, D, s0, s1, q);
                     else
-                        hot_chunk<32, true>(f1, ctx, s_ring, S, perm, vals, D, s0, s1, q);
+                        hot_chunk<32, true>(f1, ctx, s_ring, s_perm, S, perm, vals, D, s0, s1, q);
                 } else {
-                    hot_chunk<32, false>(f1, ctx, s_ring, S, perm, vals, D, s0, s1, q);
+                    hot_chunk<32, false>(f1, ctx, s_ring, s_perm, S, perm, vals, D, s0, s1, q);
                 }
             }
             // the CTA that completes the row's last chunk applies the per-row scalars
@@ -552,6 +588,7 @@ __global__ void __launch_bounds__(kRowBlock, 2)
 template <int VEC, class F>
 __global__ void __launch_bounds__(kRowBlock)
     foreach_row_kernel(size_t nrows, const u32 *__restrict__ nrows_dev, size_t D, F f) {
+    pdl_enter();
     const unsigned lane = lane_id();
     const size_t warp_global = (size_t)blockIdx.x * kRowWarps + (threadIdx.x >> 5);
     const size_t nwarps = (size_t)gridDim.x * kRowWarps;

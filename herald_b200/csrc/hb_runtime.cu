@@ -57,7 +57,17 @@ int sm_count() {
     return sms;
 }
 
+bool pdl_enabled() {
+    static int on = -1;
+    if (on < 0) {
+        const char *e = getenv("HERALD_PDL");
+        on = (e && e[0] == '0') ? 0 : 1;
+    }
+    return on == 1;
+}
+
 __global__ void fill_kernel(float *out, float value, size_t n) {
+    pdl_enter();
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     size_t stride = (size_t)gridDim.x * blockDim.x;
     // 128-bit stores on the aligned body, scalar tail
@@ -263,7 +273,7 @@ int DLGpuArraySet(DLArrayHandle arr, float value, DLStreamHandle stream_handle) 
             HB_CUDA(cudaMemsetAsync(arr->data, 0, n * sizeof(float), st));
         } else {
             int blocks = std::min<size_t>((n / 4 + 255) / 256 + 1, (size_t)sm_count() * 8);
-            fill_kernel<<<blocks, 256, 0, st>>>((float *)arr->data, value, n);
+            HB_LAUNCH(fill_kernel, blocks, 256, 0, st, (float *)arr->data, value, n);
             HB_LAUNCHED();
         }
     }

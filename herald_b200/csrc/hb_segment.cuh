@@ -39,11 +39,11 @@ template <int VEC, int ROWS, class FV, class F1>
 void launch_segment_reduce(KeyWorkspace &ws, const u32 *perm, const float *vals, size_t D, size_t n,
                            bool hot, u32 thr, const HotLists &hl, cudaStream_t st, FV fv, F1 f1) {
     auto k = segment_reduce_kernel<VEC, ROWS, FV, F1>;
-    const size_t smem = (size_t)hot_stages() * kHotStageBytes;
+    const size_t smem = hot_smem_bytes(hot_stages());
     static const int full = persistent_grid(k, smem);
     const size_t chunks = (n + 31) / 32; // upper bound of the cold tickets
     int grid = (int)std::max<size_t>(1, std::min<size_t>(full, (chunks + kRowWarps - 1) / kRowWarps));
-    k<<<hot ? full : grid, kRowBlock, smem, st>>>(ws.seg_start, perm, ws.num_unique, vals, D, thr, hl,
+    HB_LAUNCH(k, hot ? full : grid, kRowBlock, smem, st, ws.seg_start, perm, ws.num_unique, vals, D, thr, hl,
                                                   fv, f1);
     HB_LAUNCHED();
 }
@@ -58,7 +58,7 @@ void run_segment_reduce(KeyWorkspace &ws, const u32 *perm, const float *vals, si
                 hot_stages()};
     if (hot) {
         int g = (int)std::min<size_t>((n + 255) / 256, (size_t)sm_count() * 4);
-        build_hot_lists_kernel<<<std::max(g, 1), 256, 0, st>>>(ws.seg_start, ws.num_unique,
+        HB_LAUNCH(build_hot_lists_kernel, std::max(g, 1), 256, 0, st, ws.seg_start, ws.num_unique,
                                                              hot_threshold, hl);
         HB_LAUNCHED();
     }

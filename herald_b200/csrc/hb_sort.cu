@@ -17,7 +17,7 @@ namespace {
 
 constexpr int RB = kSortRadixBits;
 constexpr int RADIX = kSortRadix;
-constexpr int SORT_THREADS = 256;
+constexpr int SORT_THREADS = 512; // 52 tiles at N = 212,992: the look-back chain is what a pass costs
 constexpr int SORT_WARPS = SORT_THREADS / 32;
 constexpr int SORT_ITEMS = 8;
 constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS; // 2048 keys per block
@@ -67,6 +67,7 @@ __device__ __forceinline__ void rank_tile(int shift, u32 (*s_cnt)[RADIX], const 
 template <int KIND>
 __global__ void __launch_bounds__(SORT_THREADS)
     sort_hist_all_kernel(const void *kin, size_t n, int passes, u32 *totals, const u32 *mismatch) {
+    pdl_enter();
     __shared__ u32 sh[kMaxSortPasses * RADIX];
     if (mismatch && *mismatch == 0)
         return; // same keys as the batch this workspace already holds sorted
@@ -103,6 +104,7 @@ __global__ void __launch_bounds__(SORT_THREADS)
     sort_pass_kernel(const void *kin, const u32 *vin, u64 *kout, u32 *vout, size_t n, int shift,
                      const u32 *__restrict__ totals, u64 *status, u32 *ticket, u32 epoch,
                      const u32 *mismatch) {
+    pdl_enter();
     __shared__ u32 s_cnt[SORT_WARPS][RADIX];
     if (mismatch && *mismatch == 0)
         return;
@@ -229,6 +231,7 @@ constexpr int UNIQ_TILE = kScanBlock * UNIQ_ITEMS;
 __global__ void __launch_bounds__(kScanBlock)
     unique_kernel(const u64 *sk, const u32 *perm, size_t n, u64 *uniq, u32 *inverse,
                   u32 *seg_start, u32 *num_unique, ScanState st, u32 ntiles, const u32 *mismatch) {
+    pdl_enter();
     if (mismatch && *mismatch == 0)
         return;
     const u32 tile = take_ticket(st.ticket);
@@ -279,6 +282,7 @@ __global__ void __launch_bounds__(256)
     same_keys_kernel(const void *kin, size_t n, const u64 *__restrict__ uniq,
                      const u32 *__restrict__ inverse, const u32 *__restrict__ num_unique,
                      u32 *mismatch) {
+    pdl_enter();
     const u32 U = *num_unique;
     bool bad = false;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
@@ -291,6 +295,7 @@ __global__ void __launch_bounds__(256)
 }
 
 __global__ void set_zero_unique(u32 *num_unique, u32 *seg_start) {
+    pdl_enter();
     *num_unique = 0;
     seg_start[0] = 0;
 }
@@ -315,10 +320,10 @@ const u32 *check_same_keys(KeyWorkspace &ws, const void *keys_in, int key_kind, 
     u32 *mismatch = ws.reuse_mismatch();
     int grid = std::min(ceil_div(n, 256 * 4), sm_count() * 4);
     if (key_kind == HB_KEYS_F32)
-        same_keys_kernel<HB_KEYS_F32><<<grid, 256, 0, st>>>(keys_in, n, ws.uniq, ws.inverse,
+        HB_LAUNCH(same_keys_kernel<HB_KEYS_F32>, grid, 256, 0, st, keys_in, n, ws.uniq, ws.inverse,
                                                            ws.num_unique, mismatch);
     else
-        same_keys_kernel<HB_KEYS_U64><<<grid, 256, 0, st>>>(keys_in, n, ws.uniq, ws.inverse,
+        HB_LAUNCH(same_keys_kernel<HB_KEYS_U64>, grid, 256, 0, st, keys_in, n, ws.uniq, ws.inverse,
                                                            ws.num_unique, mismatch);
     HB_LAUNCHED();
     return mismatch;
@@ -402,9 +407,9 @@ SortedKeys radix_sort_keys(KeyWorkspace &ws, const void *keys_in, int key_kind, 
     u32 *totals = ws.sort_totals();
     int hgrid = std::max(1, std::min(ceil_div(n, 1024), sm_count() * 2));
     if (key_kind == HB_KEYS_F32)
-        sort_hist_all_kernel<HB_KEYS_F32><<<hgrid, SORT_THREADS, 0, st>>>(keys_in, n, passes, totals, mismatch);
+        HB_LAUNCH(sort_hist_all_kernel<HB_KEYS_F32>, hgrid, SORT_THREADS, 0, st, keys_in, n, passes, totals, mismatch);
     else
-        sort_hist_all_kernel<HB_KEYS_U64><<<hgrid, SORT_THREADS, 0, st>>>(keys_in, n, passes, totals, mismatch);
+        HB_LAUNCH(sort_hist_all_kernel<HB_KEYS_U64>, hgrid, SORT_THREADS, 0, st, keys_in, n, passes, totals, mismatch);
     HB_LAUNCHED();
     const void *kin = keys_in;
     const u32 *vin = nullptr;
@@ -420,7 +425,7 @@ SortedKeys radix_sort_keys(KeyWorkspace &ws, const void *keys_in, int key_kind, 
         const bool packed = key_bits <= 32 && passes > 1;
         const bool pin = packed && !first, pout = packed && p + 1 < passes;
 #define HB_SORT_PASS(KIND, F, PI, PO)                                                             \
-    sort_pass_kernel<KIND, F, PI, PO><<<nblk, SORT_THREADS, 0, st>>>(                            \
+    HB_LAUNCH((sort_pass_kernel<KIND, F, PI, PO>), nblk, SORT_THREADS, 0, st, \
         kin, vin, ws.keys[out], ws.vals[out], n, shift, tp, ws.sort_status, ticket, epoch, mismatch)
         if (f32 && pout)
             HB_SORT_PASS(HB_KEYS_F32, true, false, true);
@@ -451,12 +456,12 @@ SortedKeys radix_sort_keys(KeyWorkspace &ws, const void *keys_in, int key_kind, 
 void unique_from_sorted(KeyWorkspace &ws, const SortedKeys &sk, size_t n, cudaStream_t st,
                         const u32 *mismatch) {
     if (n == 0) {
-        set_zero_unique<<<1, 1, 0, st>>>(ws.num_unique, ws.seg_start);
+        HB_LAUNCH(set_zero_unique, 1, 1, 0, st, ws.num_unique, ws.seg_start);
         HB_LAUNCHED();
         return;
     }
     u32 ntiles = (u32)ceil_div(n, UNIQ_TILE);
-    unique_kernel<<<ntiles, kScanBlock, 0, st>>>(sk.keys, sk.perm, n, ws.uniq, ws.inverse,
+    HB_LAUNCH(unique_kernel, ntiles, kScanBlock, 0, st, sk.keys, sk.perm, n, ws.uniq, ws.inverse,
                                                  ws.seg_start, ws.num_unique, ws.next_scan(),
                                                  ntiles, mismatch);
     HB_LAUNCHED();
