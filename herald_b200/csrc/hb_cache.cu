@@ -180,6 +180,8 @@ __global__ void op_end_kernel(CacheView c, const u64 *clk, int last_stage, PerfR
     rec->ht_occupied = r->ht_occupied;
     rec->pending = r->pending;
     rec->limit_full = r->size == c.limit;
+    rec->clock = r->clock;
+    rec->floor = r->floor;
 }
 
 // =====================================================================================
@@ -216,6 +218,7 @@ __global__ void __launch_bounds__(kScanBlock)
             atomicMax(&c.regs->error, (u32)E_KEY_RANGE);
         if (s >= 0) {
             const u64 stamp = base + i;
+            c.stamp_log[stamp & c.log_mask] = (u32)s;
             switch (c.policy) {
             case HB_POLICY_LRU: // lru_cache.cc:27-39: move to the front
                 c.slot_prio[s] = make_prio(0, stamp);
@@ -405,48 +408,138 @@ struct IndexFromSlots {
 // =====================================================================================
 // batched insert: plan, select victims, evict, insert  (cache.cc:28-35 + policy insert())
 // =====================================================================================
+constexpr int kSelUnroll = 4; // slot priorities a thread loads before it uses the first
+constexpr int kLogBlock = 512, kLogItems = 8;
+constexpr int kLogTile = kLogBlock * kLogItems; // stamps one tile of the log walk covers
+
 __global__ void __launch_bounds__(256)
     plan_insert_kernel(CacheView c, int bypass, const u64 *clk_in, u64 *clk_out) {
     pdl_enter();
+    __shared__ u32 s_log_tiles;
     for (int b = threadIdx.x; b < 2 * kSelBins; b += blockDim.x)
         c.sel_hist[b] = 0;
-    if (threadIdx.x != 0)
-        return;
-    CacheRegs *r = c.regs;
-    r->sel_done2 = 0;
-    r->sel_above = 0;
-    r->sel_fallback = 0;
-    r->sel_cut_eff = r->sel_cut ? r->sel_cut : (u32)kSelBins;
-    const u32 M = r->M, size_old = r->size, limit = c.limit;
-    u32 E = 0;
-    if (!bypass) {
-        if (c.policy == HB_POLICY_LRU) { // insert, then evict while over limit (lru_cache.cc:9-25)
-            u64 tot = (u64)size_old + M;
-            E = tot > limit ? (u32)(tot - limit) : 0;
-        } else { // evict before insert when full (lfu_cache.cc:9-20, lfuopt_cache.cc:9-26)
-            u32 F = limit > size_old ? limit - size_old : 0;
-            E = M > F ? M - F : 0;
+    if (threadIdx.x == 0) {
+        CacheRegs *r = c.regs;
+        r->sel_done2 = 0;
+        r->sel_above = 0;
+        r->sel_fallback = 0;
+        r->sel_cut_eff = r->sel_cut ? r->sel_cut : (u32)kSelBins;
+        const u32 M = r->M, size_old = r->size, limit = c.limit;
+        u32 E = 0;
+        if (!bypass) {
+            if (c.policy == HB_POLICY_LRU) { // insert, then evict while over limit (lru_cache.cc:9-25)
+                u64 tot = (u64)size_old + M;
+                E = tot > limit ? (u32)(tot - limit) : 0;
+            } else { // evict before insert when full (lfu_cache.cc:9-20, lfuopt_cache.cc:9-26)
+                u32 F = limit > size_old ? limit - size_old : 0;
+                E = M > F ? M - F : 0;
+            }
         }
+        r->E = E;
+        r->k_old = 0;
+        r->n_drop = bypass ? M : 0;
+        r->need_min = 0;
+        r->nv = 0;
+        r->nc = 0;
+        r->sel_done = 0;
+        r->min_use = 0xffffffffu;
+        r->min_prio = ~0ull;
+        const u64 now = *clk_in;
+        r->ins_clock0 = now;
+        *clk_out = now + M;
+        // bins cover [floor, now): (stamp - floor) >> shift < kSelBins
+        const u64 span = now > r->floor ? now - r->floor : 1; // stamp offsets 0 .. span-1
+        const int bits = span > 1 ? 64 - __clzll((long long)(span - 1)) : 0;
+        r->sel_shift = bits > kSelBits ? (u32)(bits - kSelBits) : 0;
+        // LRU: every stamp of [floor, now) still has its own entry in the stamp log
+        const bool use_log = c.policy == HB_POLICY_LRU && E > 0 && now > r->floor &&
+                             now - r->floor <= (u64)c.log_mask + 1;
+        r->sel_use_log = use_log ? 1u : 0u;
+        r->sel_floor0 = r->floor;
+        s_log_tiles = use_log ? (u32)((now - r->floor + kLogTile - 1) / kLogTile) : 0;
     }
-    r->E = E;
-    r->k_old = 0;
-    r->n_drop = bypass ? M : 0;
-    r->need_min = 0;
-    r->nv = 0;
-    r->nc = 0;
-    r->sel_done = 0;
-    r->min_use = 0xffffffffu;
-    r->min_prio = ~0ull;
-    const u64 now = *clk_in;
-    r->ins_clock0 = now;
-    *clk_out = now + M;
-    // bins cover [floor, now): (stamp - floor) >> shift < kSelBins
-    const u64 span = now > r->floor ? now - r->floor : 1; // stamp offsets 0 .. span-1
-    const int bits = span > 1 ? 64 - __clzll((long long)(span - 1)) : 0;
-    r->sel_shift = bits > kSelBits ? (u32)(bits - kSelBits) : 0;
+    __syncthreads();
+    // scan state of the log walk: ticket + one status word per tile
+    for (u32 w = threadIdx.x; w < s_log_tiles + 2; w += blockDim.x)
+        c.sel_scan[w] = 0;
 }
 
-constexpr int kSelUnroll = 4; // slot priorities a thread loads before it uses the first
+// LRU victim selection by walking the stamp log.  Every policy touch and insert takes the next
+// tick of the replacement clock and records `stamp_log[t & mask] = slot`, so the resident lines in
+// recency order are the entries of [floor, now) whose slot still carries that stamp.  The E oldest
+// lines are found by walking the log from `floor`: tiles of kLogTile stamps, taken in order from a
+// ticket, count their live entries and rank them with the grid scan; the tile in which the count
+// reaches E writes the plan and stops the walk.  Work is proportional to the stamps issued since
+// the victims were last touched (~4 stamps per victim in the WDL steady state) instead of two
+// sweeps over the priorities of every slot of the cache.
+__global__ void __launch_bounds__(kLogBlock) sel_log_kernel(CacheView c) {
+    pdl_enter();
+    CacheRegs *r = c.regs;
+    if (!r->sel_use_log)
+        return;
+    __shared__ u32 s_tile;
+    __shared__ u32 s_stop;
+    const u32 E = r->E;
+    const u64 floor = r->sel_floor0, now = r->ins_clock0;
+    const u32 ntiles = (u32)((now - floor + kLogTile - 1) / kLogTile);
+    ScanState st;
+    st.ticket = reinterpret_cast<u32 *>(c.sel_scan);
+    st.status = c.sel_scan + 1;
+    while (true) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            s_stop = *reinterpret_cast<volatile u32 *>(&r->sel_done);
+            s_tile = s_stop ? 0u : atomicAdd(st.ticket, 1u);
+        }
+        __syncthreads();
+        if (s_stop)
+            break;
+        const u32 tile = s_tile;
+        if (tile >= ntiles)
+            break;
+        const u64 t0 = floor + (u64)tile * kLogTile + (u64)threadIdx.x * kLogItems;
+        u32 slot[kLogItems];
+        bool live[kLogItems];
+#pragma unroll
+        for (int j = 0; j < kLogItems; j++)
+            slot[j] = t0 + j < now ? c.stamp_log[(t0 + j) & c.log_mask] : 0xffffffffu;
+        u64 prio[kLogItems];
+#pragma unroll
+        for (int j = 0; j < kLogItems; j++)
+            prio[j] = slot[j] < c.capacity ? c.slot_prio[slot[j]] : PRIO_NONE;
+        u32 cnt = 0;
+#pragma unroll
+        for (int j = 0; j < kLogItems; j++) {
+            live[j] = prio[j] == make_prio(0, t0 + j);
+            cnt += live[j];
+        }
+        const ScanResult sr = grid_exclusive_scan<kLogBlock>(st, cnt, tile);
+        u32 rank = sr.excl;
+#pragma unroll
+        for (int j = 0; j < kLogItems; j++) {
+            if (live[j]) {
+                if (rank < E)
+                    c.victims[rank] = slot[j];
+                if (rank == E - 1)
+                    r->floor = t0 + j + 1; // every line below has just been selected
+                rank++;
+            }
+        }
+        const u32 incl = sr.tile_prefix + sr.tile_total;
+        const bool completes = (sr.tile_prefix < E && incl >= E) || (tile == ntiles - 1 && incl < E);
+        if (completes && threadIdx.x == 0) {
+            const u32 k_old = min(E, incl);
+            r->k_old = k_old;
+            r->nv = k_old;
+            r->n_drop = E - k_old; // the oldest new lines fall off the tail themselves
+            r->need_min = 0;
+            if (incl < E)
+                r->floor = now;
+            __threadfence();
+            atomicExch(&r->sel_done, 1u);
+        }
+    }
+}
 
 // Block-wide: exclusive prefix of sh[0..kSelBins) in place; returns total.  blockDim.x is a
 // multiple of 256 (the first 256 threads do the work, every thread must call it).
@@ -500,7 +593,7 @@ __global__ void __launch_bounds__(1024) sel_hist_kernel(CacheView c, int level) 
     pdl_enter();
     CacheRegs *r = c.regs;
     const u32 E = r->E;
-    if (E == 0)
+    if (E == 0 || r->sel_use_log)
         return;
     if (level == 1 && !r->sel_fallback)
         return;
@@ -627,7 +720,7 @@ constexpr int kCollectCap = 2048;
 __global__ void __launch_bounds__(256) sel_collect_kernel(CacheView c) {
     pdl_enter();
     CacheRegs *r = c.regs;
-    if (r->E == 0 || r->k_old == 0)
+    if (r->E == 0 || r->k_old == 0 || r->sel_use_log)
         return;
     __shared__ u32 s_vic[kCollectCap];
     __shared__ u32 s_cslot[kCollectCap];
@@ -702,7 +795,7 @@ __global__ void __launch_bounds__(256) sel_collect_kernel(CacheView c) {
 __global__ void __launch_bounds__(1024) sel_refine_kernel(CacheView c) {
     pdl_enter();
     CacheRegs *r = c.regs;
-    if (r->E == 0 || r->k_old == 0)
+    if (r->E == 0 || r->k_old == 0 || r->sel_use_log)
         return;
     __shared__ u32 sh[kSelBins];
     __shared__ u32 s_part[1024];
@@ -900,6 +993,7 @@ __global__ void insert_new_kernel(CacheView c, const i32 *uslot, const u32 *miss
             atomicMax(&r->error, (u32)E_INDEX_FULL);
         c.slot_use[s] = use0;
         c.slot_prio[s] = make_prio(use0, clock0 + j);
+        c.stamp_log[(clock0 + j) & c.log_mask] = s;
         c.slot_state[s] = S_CACHED;
     }
     add_occupied(&r->ht_occupied, fresh);
@@ -1420,6 +1514,7 @@ __global__ void reinsert_touch_kernel(CacheView c, i32 s) {
     pdl_enter();
     CacheRegs *r = c.regs;
     const u64 stamp = r->clock;
+    c.stamp_log[stamp & c.log_mask] = (u32)s;
     if (c.policy == HB_POLICY_LRU) {
         c.slot_prio[s] = make_prio(0, stamp);
         r->clock = stamp + 1;
@@ -1666,6 +1761,8 @@ void end_call(hb_cache *c, int last_stage, u32 kind, size_t n, bool inserted) {
     HB_CUDA(cudaMemcpyAsync(&c->ring[idx], c->dev_record, sizeof(PerfRecord), cudaMemcpyDeviceToHost,
                             c->stream));
     HB_CUDA(cudaEventRecord(c->ev_end[idx], c->stream));
+    c->ticks_ring[idx] = c->cur_ticks + 4; // + the single-line paths (reinsert touch)
+    c->cur_ticks = 0;
     c->calls++;
     c->incoming_ring[c->calls % hb_cache::kRing] = 0;
 }
@@ -1675,6 +1772,7 @@ void resolve_batch(hb_cache *c, const void *dev_keys, int kind, size_t n, int ba
                    int clk_stage, bool marks = true) {
     KeyWorkspace &ws = c->ws[batch];
     cudaStream_t st = c->stream;
+    c->cur_ticks += n;
     ws.reset_scans(st);
     SortedKeys sk{nullptr, nullptr};
     const u32 *same = check_same_keys(ws, dev_keys, kind, n, st);
@@ -1740,16 +1838,41 @@ void run_insert(hb_cache *c, size_t n, int clk_stage) {
     if (!n)
         return;
     int sgrid = lin_grid(c->view.capacity);
-    // few fat CTAs: every CTA ends with one global atomic per non-empty bin of its histogram
-    const int hgrid = sm_count() * 2;
-    HB_LAUNCH(sel_hist_kernel, hgrid, 1024, 0, st, c->view, 0);
-    HB_LAUNCHED();
-    HB_LAUNCH(sel_hist_kernel, hgrid, 1024, 0, st, c->view, 1);
-    HB_LAUNCHED();
-    HB_LAUNCH(sel_collect_kernel, sgrid, 256, 0, st, c->view);
-    HB_LAUNCHED();
-    HB_LAUNCH(sel_refine_kernel, 1, 1024, 0, st, c->view);
-    HB_LAUNCHED();
+    c->cur_ticks += n;
+    // LRU walks the stamp log (sel_log_kernel) as long as [floor, now) fits the log; the device
+    // decides (plan_insert_kernel), the histogram kernels below are its fallback.  They are not
+    // even launched when the host can prove the span fits: newest finished call's clock - floor
+    // plus an upper bound of the ticks taken since.
+    bool log_certain = false;
+    if (c->policy == HB_POLICY_LRU) {
+        for (uint64_t back = 1; back <= std::min<uint64_t>(c->calls, 64); back++) {
+            const uint64_t call = c->calls - back;
+            const int idx = (int)(call % hb_cache::kRing);
+            if (cudaEventQuery(c->ev_end[idx]) != cudaSuccess)
+                continue;
+            const PerfRecord &rec = c->ring[idx];
+            uint64_t span = rec.clock - rec.floor + c->cur_ticks;
+            for (uint64_t k = call + 1; k < c->calls; k++)
+                span += c->ticks_ring[k % hb_cache::kRing];
+            log_certain = span <= (uint64_t)c->view.log_mask + 1;
+            break;
+        }
+        (void)cudaGetLastError(); // cudaErrorNotReady of the queries is not an error
+        HB_LAUNCH(sel_log_kernel, sm_count(), kLogBlock, 0, st, c->view);
+        HB_LAUNCHED();
+    }
+    if (!log_certain) {
+        // few fat CTAs: every CTA ends with one global atomic per non-empty bin of its histogram
+        const int hgrid = sm_count() * 2;
+        HB_LAUNCH(sel_hist_kernel, hgrid, 1024, 0, st, c->view, 0);
+        HB_LAUNCHED();
+        HB_LAUNCH(sel_hist_kernel, hgrid, 1024, 0, st, c->view, 1);
+        HB_LAUNCHED();
+        HB_LAUNCH(sel_collect_kernel, sgrid, 256, 0, st, c->view);
+        HB_LAUNCHED();
+        HB_LAUNCH(sel_refine_kernel, 1, 1024, 0, st, c->view);
+        HB_LAUNCHED();
+    }
     if (c->policy != HB_POLICY_LRU) {
         HB_LAUNCH(min_use_kernel, sgrid, 256, 0, st, c->view);
         HB_LAUNCHED();
@@ -2085,6 +2208,16 @@ int hb_cache_create(int policy, size_t limit, size_t length, size_t width, int n
     dmalloc(v.cand_prio, 2 * cap);
     dmalloc(v.cand_slot, 2 * cap);
     dmalloc(v.sel_hist, 2 * kSelBins);
+    {   // stamp log: >= 4 entries per slot (the span of live stamps of an LRU cache in steady state
+        // is a few ticks per resident line)
+        size_t ls = 1 << 16;
+        while (ls < 4 * cap)
+            ls <<= 1;
+        v.log_mask = (u32)(ls - 1);
+        dmalloc(v.stamp_log, ls);
+        HB_CUDA(cudaMemset(v.stamp_log, 0xff, ls * sizeof(u32)));
+        dmalloc(v.sel_scan, ls / kLogTile + 4);
+    }
     dmalloc(v.regs, 1);
     v.trows = t->rows;
     v.tver = t->ver;
@@ -2165,6 +2298,8 @@ int hb_cache_destroy(hb_cache *c) {
         dfree(v.cand_prio);
         dfree(v.cand_slot);
         dfree(v.sel_hist);
+        dfree(v.stamp_log);
+        dfree(v.sel_scan);
         dfree(v.regs);
         dfree(v.pv.lo);
         dfree(v.pv.fl_count);

@@ -159,7 +159,8 @@ struct CacheRegs {
     u32 sel_cut_eff;  // window of the running call
     u32 sel_above;    // class lines at or above the window
     u32 sel_fallback; // the threshold was not inside the window: run the full-range pass
-    u32 pad1;
+    u32 sel_use_log;  // LRU: this call selects its victims by walking the stamp log
+    u64 sel_floor0;   // floor at the start of the selection (the log walk moves `floor` itself)
 };
 
 // Everything a kernel needs to address the cache (passed by value).
@@ -187,6 +188,9 @@ struct CacheView {
     u64 *cand_prio;  // [2][capacity] boundary candidates (ping-pong)
     u32 *cand_slot;  // [2][capacity]
     u32 *sel_hist;   // [2][kSelBins]: windowed pass, full-range fallback
+    u32 *stamp_log;  // [log_mask + 1]: slot that was given stamp t, at t & log_mask (see sel_log_kernel)
+    u64 *sel_scan;   // ticket + tile status words of the log walk's grid scan
+    u32 log_mask;
     CacheRegs *regs;
     // owner shard (same GPU)
     float *trows;
@@ -220,6 +224,7 @@ struct PerfRecord {
     u32 num_all, num_unique, num_miss, num_evict, num_transfered;
     u32 size, error, ht_occupied, pending, limit_full;
     u32 pad;
+    u64 clock, floor; // replacement clock and victim-class floor after the call
 };
 
 } // namespace hb
@@ -262,6 +267,8 @@ struct hb_cache {
     // host-side upper bound of index occupancy (refreshed at wait)
     size_t occ_upper = 0;
     size_t incoming_ring[kRing] = {}; // keys each call could add to the index (per call of the ring)
+    size_t ticks_ring[kRing] = {};    // most replacement-clock ticks each call could take
+    size_t cur_ticks = 0;             // ... the call being enqueued
     size_t pending_upper = 0;
     int key_bits = 64;
     hb::u32 hot_threshold = 64; // segments longer than this take the column-split path
