@@ -343,7 +343,7 @@ __global__ void __launch_bounds__(kRowBlock)
             }
             if (s >= 0 && have) {
                 const i64 v = c.slot_version[s];
-                srv = c.pv.ver[owner][trow];
+                srv = __ldg(&c.pv.ver[owner][trow]);
                 need = v == -1 || srv - v > pull_bound;
                 if (need) {
                     addup = c.slot_flags[s] & F_GRAD; // Line::addup (embedding.h:92-96)
@@ -377,7 +377,11 @@ __global__ void __launch_bounds__(kRowBlock)
 #pragma unroll
                 for (int r = 0; r < ROWS; r++)
                     if (src[r] >= 0) {
-                        x[r] = V::ld(rbase[r] + rt[r] * D + k * VEC);
+                        // read-only for the whole kernel (pushes reach a shard only between the
+                        // barriers of an update), and possibly a PEER's memory: the non-coherent
+                        // path fetches whole lines over NVLink; a plain ld.global of peer memory
+                        // ran 10x slower (660 us for 52k remote rows against 60 us)
+                        x[r] = V::ld_nc(rbase[r] + rt[r] * D + k * VEC);
                         g[r] = rg[r] ? V::ld(c.grad + (size_t)rs[r] * D + k * VEC) : V::zero();
                     }
 #pragma unroll
@@ -1593,6 +1597,18 @@ template <typename T>
 void dmalloc(T *&p, size_t count) {
     HB_CUDA(cudaMalloc((void **)&p, std::max<size_t>(count, 1) * sizeof(T)));
 }
+// Memory other ranks map through CUDA IPC (shards, versions, mailboxes): the size is rounded up to
+// a multiple of 2 MiB.  Measured on 2 x B200 (scripts/ipcbench.cu, profiles/r01_ipcbench.txt): a
+// peer's mapping of an 8.64 GB cudaMalloc whose size is NOT a multiple of 2 MiB serves random 512 B
+// row reads at 38 GB/s (small pages on the importer's side), the same allocation rounded up at
+// 431 GB/s.
+template <typename T>
+void dmalloc_shared(T *&p, size_t count) {
+    const size_t two_mb = (size_t)2 << 20;
+    size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
+    bytes = (bytes + two_mb - 1) / two_mb * two_mb;
+    HB_CUDA(cudaMalloc((void **)&p, bytes));
+}
 template <typename T>
 void dfree(T *&p) {
     if (p)
@@ -1633,7 +1649,7 @@ void setup_mailbox(hb_cache *c, size_t rows) {
     }
     pv.cap = (u32)rows;
     pv.region_bytes = mailbox_region_bytes(rows, c->width);
-    HB_CUDA(cudaMalloc((void **)&c->mailbox, pv.region_bytes * pv.world));
+    dmalloc_shared(c->mailbox, pv.region_bytes * pv.world);
     HB_CUDA(cudaMemset(c->mailbox, 0, pv.region_bytes * pv.world));
     c->mailbox_cap = rows;
     ipc_share(c->mailbox, reinterpret_cast<void **>(c->peer_mailbox));
@@ -2041,8 +2057,8 @@ int hb_table_create(int node_id, size_t length, size_t width, int device, hb_tab
     size_t per = length / world, rem = length % world;
     t->row_begin = (size_t)rank * per + std::min<size_t>(rank, rem);
     t->nrows = per + ((size_t)rank < rem ? 1 : 0);
-    dmalloc(t->rows, t->nrows * width);
-    dmalloc(t->ver, t->nrows);
+    dmalloc_shared(t->rows, t->nrows * width);
+    dmalloc_shared(t->ver, t->nrows);
     HB_CUDA(cudaMemset(t->rows, 0, std::max<size_t>(t->nrows * width, 1) * sizeof(float)));
     HB_CUDA(cudaMemset(t->ver, 0, std::max<size_t>(t->nrows, 1) * sizeof(i64)));
     t->rank = rank;
