@@ -52,19 +52,56 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-steps", type=int, default=8)
+    ap.add_argument("--ids", default="permuted", choices=["permuted", "folded"],
+                    help="Zipf rank -> row: fixed permutation (default, SURVEY 8d) or rank == row")
     ap.add_argument("--seg-trace", default=None,
                     help="diagnostics: write the per-CTA timeline of one segment_reduce launch here")
-    return ap.parse_args()
+    args = ap.parse_args()
+    global _IDS_MODE
+    _IDS_MODE = args.ids
+    return args
 
 
 # ----------------------------------------------------------------------------------------------
 # synthetic Criteo-shaped ids: unified Zipf(1.05) over the single [V, D] table, carried as float32
 # exactly like Hetu's dataloader (python/hetu/dataloader.py:14) — ids above 2^24 round.
 # ----------------------------------------------------------------------------------------------
+_IDS_MODE = "permuted"
+
+
+def _spread_multiplier(vocab):
+    """A multiplier coprime with `vocab` near the golden-ratio point: rank -> (rank * m) % vocab is a
+    fixed permutation of [0, vocab) that sends neighbouring popularity ranks far apart."""
+    import math
+    m = int(0.6180339887498949 * vocab) | 1
+    while math.gcd(m, vocab) != 1:
+        m += 2
+    return m
+
+
+def rank_to_id(ranks, vocab):
+    """Popularity rank (0 = hottest) -> table row.  SURVEY 8(d) flavour (i): the Zipf rank is mapped
+    through a fixed permutation of [0, V), as label-encoded Criteo ids are not sorted by
+    popularity (examples/ctr/models/load_data.py:193-205 offsets 26 per-field encodings);
+    `--ids folded` keeps rank == row (every hot row in the first shard)."""
+    ranks = np.asarray(ranks, dtype=np.int64) % vocab
+    if _IDS_MODE == "folded":
+        return ranks
+    return (ranks * _spread_multiplier(vocab)) % vocab
+
+
 def make_ids(step, batch, vocab, rank=0):
     rng = np.random.default_rng(1234 + step + 100003 * rank)
     z = rng.zipf(ZIPF_A, (batch, FIELDS))
-    return ((z - 1) % vocab).astype(np.float32)
+    return rank_to_id(z - 1, vocab).astype(np.float32)
+
+
+def hottest_ids(lo, hi, vocab, dtype):
+    """Rows of the popularity ranks [lo, hi) as the cache would see them (float32-carried ids round
+    above 2^24: duplicates after rounding are dropped, order kept)."""
+    ids = rank_to_id(np.arange(lo, hi), vocab).astype(np.float32)
+    _, first = np.unique(ids, return_index=True)
+    return ids[np.sort(first)].astype(dtype)
 
 
 def cache_limit(vocab, ratio):
@@ -170,7 +207,7 @@ def run_cpu_reference(args, steps, warmup):
     t0 = time.perf_counter()
     chunk = 1 << 20
     for lo in range(0, limit, chunk):
-        cache.embedding_lookup(np.arange(lo, min(lo + chunk, limit), dtype=np.uint64))
+        cache.embedding_lookup(hottest_ids(lo, min(lo + chunk, limit), vocab, np.uint64))
     fill_s = time.perf_counter() - t0
     N = B * FIELDS
     grads = (np.random.default_rng(7).normal(0, 1e-3, (N, D)) * 1e-2).astype(np.float32)
@@ -219,7 +256,7 @@ def workload_config(args, vocab=None):
                         "%s cache ratio %.2f, bound %d" % (args.policy.upper(), args.ratio, args.bound),
             "batch_per_gpu": args.batch, "fields": FIELDS, "emb_dim": args.dim,
             "table_rows": vocab or args.vocab, "cache_limit": cache_limit(vocab or args.vocab, args.ratio),
-            "ids": "Zipf(%.2f) unified, float32-carried" % ZIPF_A,
+            "ids": "Zipf(%.2f) unified, %s, float32-carried" % (ZIPF_A, "rank -> row by a fixed permutation" if _IDS_MODE == "permuted" else "rank == row"),
             "l2": "inputs larger than L2: 3 rotating grads/dest buffer pairs of 2x%.0f MB, "
                   "17 GB table" % (args.batch * FIELDS * args.dim * 4 / 1e6),
             "parallelism": "dp%d row-sharded" % args.gpus}
@@ -315,8 +352,8 @@ def herald_main(args, rank, world, local_rank):
     chunk = 1 << 20
     for lo in range(0, limit, chunk):
         n = min(chunk, limit - lo)
-        k = hb.array(np.arange(lo, lo + n, dtype=np.float32), dev)
-        d = hb.empty((n, D), dev)
+        k = hb.array(hottest_ids(lo, lo + n, V, np.float32), dev)
+        d = hb.empty((k.shape[0], D), dev)
         cst.embedding_lookup(k, d, sync=True)
         del k, d
     cst.embedding_lookup(ids_dev[0], dest_dev[0], sync=True)
@@ -405,7 +442,7 @@ def herald_main(args, rank, world, local_rank):
         kernels = {
             "gather_rows_kernel": {"ms": t_gather, "algorithmic_bytes": gather_bytes,
                                    "gbs": gather_bytes / t_gather / 1e6 if t_gather else None},
-            "segment_rows_kernel<AccumulatePush>": {
+            "segment_reduce_kernel<AccumulatePush>": {
                 "ms": t_accum, "algorithmic_bytes": accum_bytes,
                 "gbs": accum_bytes / t_accum / 1e6 if t_accum else None,
                 "algorithmic_bytes_with_owner_row_rmw": accum_bytes_owner,
