@@ -285,6 +285,42 @@ int hb_comm_rank(int *rank, int *world);
 int hb_comm_barrier(void); /* BarrierWorker (python/hetu/cstable.py:36) */
 int hb_comm_finalize(void);
 
+/* ------------------------------------------------------------------------- */
+/* Laia / Herald embedding scheduler (host side) — replaces the pybind module    */
+/* `laia_cache` (laia/src/python_binding.cc:8-16: LaiaScheduler.start / pop /    */
+/* length) and the Cython planner python/hetu/laia/laia.pyx.  Every worker runs  */
+/* the same planner; the plan of a worker is the `push_keys` argument of         */
+/* hb_cache_update_with_push_keys.                                               */
+/* ------------------------------------------------------------------------- */
+typedef struct hb_laia hb_laia;
+/* LaiaScheduler::start (laia/src/laia_scheduler.cc:30-88): sample_embs is the [num_sample,
+ * num_table] matrix of embedding ids, copied.  A global batch is mini_batch_size * nrank samples. */
+int hb_laia_create(hb_laia **out, const uint64_t *sample_embs, size_t num_sample, size_t num_table,
+                   size_t epoch_num, size_t mini_batch_size, size_t batch_num, size_t nrank, size_t rank,
+                   size_t cache_size, size_t num_threads);
+int hb_laia_destroy(hb_laia *s);
+/* Plan the next global batch (laia_scheduler.cc:115-169 one iteration: get_dist :171-271, then the
+ * snapshot update :146-161).  *done = 1 when the sequence (epochs x batches, one more batch in the
+ * last epoch) is over — the reference then pushes the terminator {0}. */
+int hb_laia_next(hb_laia *s, int *done);
+/* Results of the most recent hb_laia_next, for any worker (the reference hands out `rank`'s):
+ * the communication plan (ascending unique keys) and the mini_batch_size sample positions. */
+int hb_laia_plan_size(hb_laia *s, size_t worker, size_t *n);
+int hb_laia_plan(hb_laia *s, size_t worker, uint64_t *keys, size_t cap);
+int hb_laia_dist(hb_laia *s, size_t worker, uint64_t *sample_idx);
+/* MiniLRUCache::get_keys of a worker's snapshot: valid keys, ascending (keys may be NULL: count) */
+int hb_laia_snapshot_keys(hb_laia *s, size_t worker, uint64_t *keys, size_t cap, size_t *n);
+/* The snapshot cache alone (laia/include/mini_lru_cache.h:14-137).  get returns -1 hit, -2 stale
+ * hit, 0 miss, 1 miss that evicted a valid line (:69-105). */
+typedef struct hb_minilru hb_minilru;
+int hb_minilru_create(hb_minilru **out, size_t capacity);
+int hb_minilru_destroy(hb_minilru *m);
+int hb_minilru_get(hb_minilru *m, uint64_t key);
+int hb_minilru_check(hb_minilru *m, uint64_t key);
+int hb_minilru_outdate(hb_minilru *m, uint64_t key);
+int hb_minilru_evict(hb_minilru *m, uint64_t key);
+int hb_minilru_keys(hb_minilru *m, uint64_t *keys, size_t cap, size_t *n);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,167 @@
+"""Laia / Herald embedding scheduler: the C++ planner in
+libherald_b200.so (csrc/hb_laia.cu, through herald_b200.laia) against
+  * the golden vectors produced by the reference's own planner (python/hetu/laia/laia.pyx,
+    tests/golden/make_golden_laia.py),
+  * the pure-Python restatement oracle/laia_port.py (itself checked against the same vectors),
+  * the reference planner run live when oracle/_ref/laia*.so is present.
+Integer work: every plan and distribution must be identical.  Host code: no GPU needed."""
+import os
+
+import numpy as np
+import pytest
+
+from herald_b200.laia import LaiaScheduler, MiniLRUCache
+from oracle import laia_port, laia_ref
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "laia_cases.npz")
+
+
+def golden_cases():
+    z = np.load(GOLDEN)
+    for c in range(int(z["ncases"])):
+        W, mini, T, nb, cap, ep = (int(x) for x in z["c%d_params" % c])
+        emb, plan, off, dist = z["c%d_emb" % c], z["c%d_plan" % c], z["c%d_plan_off" % c], z["c%d_dist" % c]
+        batches = []
+        for b in range(dist.shape[0]):
+            plans = [plan[off[b * W + w]:off[b * W + w + 1]].tolist() for w in range(W)]
+            batches.append((plans, dist[b].tolist()))
+        yield c, dict(W=W, mini=mini, T=T, nb=nb, cap=cap, ep=ep, emb=emb), batches
+
+
+CASES = list(golden_cases())
+
+
+def run_ours(p, threads=3):
+    """Every rank runs its own scheduler and reports its own part -> per batch (plans, dist)."""
+    S = p["emb"].shape[0]
+    scheds = []
+    for rank in range(p["W"]):
+        s = LaiaScheduler()
+        s.start(p["emb"], S, p["T"], p["ep"], p["mini"], p["nb"], p["W"], rank, p["cap"], threads)
+        scheds.append(s)
+    out = []
+    while True:
+        more = [s.step() for s in scheds]
+        assert all(m == more[0] for m in more)
+        if not more[0]:
+            break
+        # (not through pop(): a plan that is exactly [0] reads as the terminator on the reference's
+        # wire, laia_dataloader.py:137-139)
+        out.append(([s.plan_of(s.rank).tolist() for s in scheds], [s.dist_of(s.rank).tolist() for s in scheds]))
+    return out, scheds
+
+
+@pytest.mark.parametrize("case", [c[0] for c in CASES])
+def test_port_matches_reference_golden(case):
+    _, p, expected = CASES[case]
+    planner = laia_port.LaiaPlanner(p["emb"], p["mini"], p["W"], p["cap"], p["ep"], p["nb"])
+    for b, (plans, dist) in enumerate(expected):
+        got = planner.next_all()
+        assert got is not None, "port stopped early at batch %d" % b
+        assert got[0] == plans, "communication plan, batch %d" % b
+        assert got[1] == dist, "sample distribution, batch %d" % b
+    assert planner.next_all() is None
+
+
+@pytest.mark.parametrize("case", [c[0] for c in CASES])
+def test_planner_matches_reference_golden(case):
+    _, p, expected = CASES[case]
+    got, scheds = run_ours(p)
+    assert len(got) == len(expected)
+    for b, ((plans, dist), (eplans, edist)) in enumerate(zip(got, expected)):
+        assert plans == eplans, "communication plan, batch %d" % b
+        assert dist == edist, "sample distribution, batch %d" % b
+    # every rank plans the whole group: any rank can report any worker's part
+    assert scheds[0].plan_of(p["W"] - 1).tolist() == expected[-1][0][p["W"] - 1]
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_planner_matches_port_random(seed):
+    rng = np.random.default_rng(seed)
+    W, mini, T = int(rng.integers(1, 7)), int(rng.integers(1, 10)), int(rng.integers(1, 8))
+    nb, cap, ep = int(rng.integers(1, 5)), int(rng.integers(0, 50)), int(rng.integers(1, 4))
+    S = W * mini * nb + int(rng.integers(0, 3)) * W * mini        # more samples than one epoch uses
+    emb = ((rng.zipf(1.3, (S, T)) - 1) % 90).astype(np.uint64)
+    p = dict(W=W, mini=mini, T=T, nb=nb, cap=cap, ep=ep, emb=emb)
+    got, scheds = run_ours(p, threads=int(rng.integers(1, 5)))
+    planner = laia_port.LaiaPlanner(emb, mini, W, cap, ep, nb)
+    for b, (plans, dist) in enumerate(got):
+        eplans, edist = planner.next_all()
+        assert plans == eplans and dist == edist, "batch %d" % b
+    assert planner.next_all() is None
+    for w in range(W):                                            # simulated caches agree at the end
+        assert scheds[0].snapshot_keys(w).tolist() == planner.snaps[w].get_keys()
+
+
+@pytest.mark.skipif(not laia_ref.available(), reason="oracle/_ref/laia*.so not built")
+@pytest.mark.parametrize("seed", range(4))
+def test_planner_matches_live_reference(seed):
+    rng = np.random.default_rng(50 + seed)
+    W, mini, T = int(rng.integers(1, 6)), int(rng.integers(2, 12)), int(rng.integers(1, 6))
+    while W * mini < 8:
+        mini += 1
+    nb, cap, ep = int(rng.integers(1, 5)), int(rng.integers(1, 60)), int(rng.integers(1, 3))
+    emb = ((rng.zipf(1.3, (W * mini * nb, T)) - 1) % 80).astype(np.int32)
+    expected = laia_ref.run(emb, ep, mini, nb, W, cap)
+    got, _ = run_ours(dict(W=W, mini=mini, T=T, nb=nb, cap=cap, ep=ep, emb=emb))
+    assert [(pl, d) for pl, d in got] == [(pl, d) for pl, d in expected]
+
+
+def test_wire_format():
+    """laia_dataloader.py:122-143: plan then indices per batch, [0] at the end, length() >= 2
+    while batches remain."""
+    emb = np.arange(48, dtype=np.uint64).reshape(16, 3) % 7
+    s = LaiaScheduler()
+    s.start(emb, 16, 3, 1, 4, 1, 2, 1, 5)
+    assert s.length() >= 2
+    msgs = []
+    while True:
+        m = s.pop()
+        assert isinstance(m, list)
+        msgs.append(m)
+        if m == [0]:
+            break
+    assert len(msgs) == 2 * 2 + 1                                 # batch_num + 1 batches in the last epoch
+    assert all(len(msgs[i]) == 4 for i in (1, 3))
+    assert s.length() == 0
+    with pytest.raises(RuntimeError):
+        s.pop()
+    with pytest.raises(RuntimeError):
+        LaiaScheduler().start(np.zeros(4, np.uint64), 4, 1, 1, 1, 1, 1, 0, 1)
+
+
+def test_mini_lru_return_codes():
+    """laia/include/mini_lru_cache.h:69-105: -1 hit, -2 stale hit, 0 miss, 1 miss + valid victim."""
+    for impl in (MiniLRUCache, laia_port.MiniLRUCache):
+        c = impl(2)
+        assert c.get(5) == 0 and c.get(7) == 0                    # misses, room left
+        assert c.get(5) == -1                                     # hit
+        c.outdate(7)
+        assert not c.check(7) and c.check(5)
+        assert c.get(7) == -2                                     # stale hit: valid again, most recent
+        assert c.check(7)
+        assert c.get(9) == 1                                      # evicts 5 (valid)
+        assert list(c.get_keys()) == [7, 9]
+        c.outdate(7)
+        assert c.get(11) == 0                                     # evicts 7 (outdated)
+        assert list(c.get_keys()) == [9, 11]
+        c.evict(9)
+        assert list(c.get_keys()) == [11] and not c.check(9)
+        z = impl(0)                                               # capacity 0: nothing stays
+        assert z.get(3) == 1 and not z.check(3)
+
+
+def test_mini_lru_random_against_port():
+    rng = np.random.default_rng(3)
+    a, b = MiniLRUCache(17), laia_port.MiniLRUCache(17)
+    for _ in range(5000):
+        k, op = int(rng.integers(0, 60)), int(rng.integers(0, 10))
+        if op < 6:
+            assert a.get(k) == b.get(k)
+        elif op < 8:
+            a.outdate(k), b.outdate(k)
+        elif op < 9:
+            a.evict(k), b.evict(k)
+        else:
+            assert a.check(k) == b.check(k)
+    assert list(a.get_keys()) == b.get_keys()
