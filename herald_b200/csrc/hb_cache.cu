@@ -1060,9 +1060,21 @@ struct AccumulatePush {
     __device__ MailboxSection outbox(int owner) const {
         return mailbox_section(c.pv.out[owner], 0, c.pv.cap, c.width);
     }
+    // the two loads every row starts with, issued by the cold phase together with the segment
+    // bounds (one dependent-load level less per ticket)
+    struct Pre {
+        i32 s;
+        u64 key;
+    };
+    __device__ Pre peek(size_t u) const {
+        return Pre{uslot[u], uniq[u]};
+    }
     __device__ bool begin(size_t u, u32 cnt, Ctx &x) const {
-        x.s = uslot[u];
-        const u64 key = uniq[u];
+        return begin(peek(u), u, cnt, x);
+    }
+    __device__ bool begin(const Pre &pre, size_t u, u32 cnt, Ctx &x) const {
+        x.s = pre.s;
+        const u64 key = pre.key;
         x.owner = 0;
         x.mpos = 0;
         if (c.pv.world > 1) { // every line goes through the owner's mailbox, the local ones too:
@@ -1086,6 +1098,8 @@ struct AccumulatePush {
             x.trow = key - c.row_begin;
             x.local = x.trow < c.nrows_local;
         }
+        // owner version read ahead of the push decision (same load level as the line's scalars)
+        const i64 tv = x.local ? c.tver[x.trow] : 0;
         x.upd0 = c.slot_updates[x.s];
         x.flags = c.slot_flags[x.s];
         x.version = c.slot_version[x.s];
@@ -1095,15 +1109,15 @@ struct AccumulatePush {
             x.pushed = !x.dataless && in_plan(key); // cache.cc:296
         else
             x.pushed = (i64)x.upd > push_bound || x.dataless; // cache.cc:157
-        x.tver = (x.pushed && x.local) ? c.tver[x.trow] : 0;
+        x.tver = tv;
         return true;
     }
     __device__ Acc load(const Ctx &x, size_t k) const {
         Acc a;
         const size_t o = (size_t)x.s * c.width + k * VEC;
-        a.d = x.dataless ? V::zero() : V::ld(c.data + o);
-        a.g = x.upd0 != 0 ? V::ld(c.grad + o) : V::zero();
-        a.t = (x.pushed && x.local) ? V::ld(c.trows + x.trow * c.width + k * VEC) : V::zero();
+        a.d = x.dataless ? V::zero() : V::ld_rmw(c.data + o);
+        a.g = x.upd0 != 0 ? V::ld_rmw(c.grad + o) : V::zero();
+        a.t = (x.pushed && x.local) ? V::ld_rmw(c.trows + x.trow * c.width + k * VEC) : V::zero();
         return a;
     }
     __device__ Acc step(const Acc &a, const typename V::T &g) const {
@@ -1754,7 +1768,9 @@ void maybe_rebuild_index(hb_cache *c, size_t incoming) {
 
 // phase boundary k of the running call (only when perf is enabled: cache.cc:89-106 timings)
 void mark(hb_cache *c, int k) {
-    if (!c->perf_phases)
+    // an event between two kernels costs their launch overlap (PDL): with sampling, only every
+    // perf_every-th update/lookup pair carries the phase events (the counters are always recorded)
+    if (!c->perf_phases || (c->perf_every > 1 && (c->calls / 2) % c->perf_every != 0))
         return;
     int idx = (int)(c->calls % hb_cache::kRing);
     HB_CUDA(cudaEventRecord(c->ev_phase[idx * hb_cache::kPhases + k], c->stream));
@@ -2371,6 +2387,12 @@ int hb_cache_set_bypass(hb_cache *c, int on) {
 int hb_cache_set_perf(hb_cache *c, int on) {
     HB_API_BEGIN();
     c->perf_phases = on != 0;
+    HB_API_END();
+}
+
+int hb_cache_set_perf_sampling(hb_cache *c, unsigned every) {
+    HB_API_BEGIN();
+    c->perf_every = every ? every : 1;
     HB_API_END();
 }
 

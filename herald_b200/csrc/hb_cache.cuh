@@ -264,6 +264,7 @@ struct hb_cache {
     std::vector<cudaEvent_t> ev_phase; // [kRing][kPhases] phase boundaries (perf enabled only)
     std::vector<uint32_t> phase_mask;
     bool perf_phases = false;
+    unsigned perf_every = 1; // phase events on every perf_every-th pair of calls
     // host-side upper bound of index occupancy (refreshed at wait)
     size_t occ_upper = 0;
     size_t incoming_ring[kRing] = {}; // keys each call could add to the index (per call of the ring)

@@ -133,9 +133,15 @@ __device__ __forceinline__ void st_stream(float4 *p, const float4 &v) {
                  "f"(v.y), "f"(v.z), "f"(v.w)
                  : "memory");
 }
-// plain (coherent) 128-bit accesses for rows that are read and written in one step
+// coherent 128-bit load that does not allocate in L1 (rows that are read, modified and written once:
+// an L1 line would only displace the per-row metadata other warps are about to read)
 __device__ __forceinline__ float4 ld_row(const float4 *p) {
-    return *p;
+    float4 v;
+    asm volatile("ld.global.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "l"(p)
+                 : "memory");
+    return v;
 }
 __device__ __forceinline__ void st_row(float4 *p, const float4 &v) {
     *p = v;

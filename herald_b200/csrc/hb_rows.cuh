@@ -30,6 +30,9 @@ struct RowVec<4> {
     static __device__ __forceinline__ T ld(const float *p) {
         return *reinterpret_cast<const float4 *>(p);
     }
+    static __device__ __forceinline__ T ld_rmw(const float *p) { // row read once, then overwritten
+        return ld_row(reinterpret_cast<const float4 *>(p));
+    }
     static __device__ __forceinline__ void st(float *p, const T &v) {
         *reinterpret_cast<float4 *>(p) = v;
     }
@@ -54,6 +57,9 @@ struct RowVec<1> {
         *p = v;
     }
     static __device__ __forceinline__ T ld(const float *p) {
+        return *p;
+    }
+    static __device__ __forceinline__ T ld_rmw(const float *p) {
         return *p;
     }
     static __device__ __forceinline__ void st(float *p, const T &v) {
@@ -156,6 +162,8 @@ constexpr u32 kVeryHot = 1024; // rows above this go first (longest-processing-t
 // ring depth of the hot phase ($HERALD_HOT_STAGES, 3 .. 12): the bytes a CTA keeps in flight are
 // (stages - 1) x 16 KB, which is what hides HBM latency under the dependent add chain
 int hot_stages();
+// uniques per cold-phase ticket ($HERALD_TICKET_ROWS, 4 .. 32)
+u32 ticket_rows();
 
 // optional per-CTA timeline of the last segment_reduce launch (diagnostics, HBSegTraceEnable):
 // [0] = grid, [1] = hot items; then 4 words per CTA {start, hot phase end, end, items taken};
@@ -186,6 +194,27 @@ __device__ __forceinline__ T shfl_pod(const T &v, int src) {
     return out.t;
 }
 
+// optional two-step row opening: F::peek(u) (loads that depend on nothing but u) + F::begin(pre, u,
+// cnt, ctx); functors without peek keep the one-step begin(u, cnt, ctx)
+template <class F>
+__device__ __forceinline__ auto seg_peek(const F &f, size_t u, int) -> decltype(f.peek(u)) {
+    return f.peek(u);
+}
+template <class F>
+__device__ __forceinline__ int seg_peek(const F &, size_t, long) {
+    return 0;
+}
+template <class F, class P>
+__device__ __forceinline__ auto seg_begin(const F &f, const P &pre, size_t u, u32 cnt,
+                                          typename F::Ctx &x, int) -> decltype(f.begin(pre, u, cnt, x)) {
+    return f.begin(pre, u, cnt, x);
+}
+template <class F, class P>
+__device__ __forceinline__ bool seg_begin(const F &f, const P &, size_t u, u32 cnt, typename F::Ctx &x,
+                                          long) {
+    return f.begin(u, cnt, x);
+}
+
 struct HotLists {
     u32 *very_hot; // [cap] unique indices with count > kVeryHot
     u32 *hot;      // [cap] unique indices with hot_threshold < count <= kVeryHot
@@ -195,6 +224,7 @@ struct HotLists {
                    // the scan arena)
     u64 *trace;    // diagnostics timeline or null
     int stages;    // ring depth of the hot phase
+    u32 ticket_rows; // uniques per cold ticket (<= 32; $HERALD_TICKET_ROWS)
 };
 
 __device__ __forceinline__ u32 rows_warp_append(u32 *counter, bool pred) {
@@ -493,7 +523,8 @@ __global__ void __launch_bounds__(kRowBlock, 2)
     // Ticket t covers the uniques t, t + T, t + 2T, ... (T tickets): ids that are hot tend to be
     // neighbours in key order, a strided ticket spreads their longer segments over many warps.
     const size_t nvec = D / VEC;
-    const u32 T = (U + 31) / 32;
+    const u32 TK = hl.ticket_rows;
+    const u32 T = (U + TK - 1) / TK;
     while (true) {
         u32 t = 0;
         if (lane == 0)
@@ -503,7 +534,8 @@ __global__ void __launch_bounds__(kRowBlock, 2)
             break;
         // lane-parallel metadata of the 32 uniques of this ticket
         const u32 my_u = t + lane * T;
-        const bool mine = my_u < U;
+        const bool mine = lane < TK && my_u < U;
+        const auto my_pre = seg_peek(fv, mine ? my_u : 0u, 0);
         const u32 my_s0 = mine ? seg_start[my_u] : 0;
         const u32 my_cnt = mine ? seg_start[my_u + 1] - my_s0 : 0;
         const bool my_cold = my_cnt > 0 && my_cnt <= hot_threshold;
@@ -511,7 +543,7 @@ __global__ void __launch_bounds__(kRowBlock, 2)
         const int nrows = __popc(__ballot_sync(FULL, mine)); // valid lanes are 0 .. nrows-1
         // every lane opens its own row: the dependent scalar loads of 32 rows overlap
         typename FV::Ctx my_ctx;
-        const bool my_ok = my_cold && fv.begin(my_u, my_cnt, my_ctx);
+        const bool my_ok = my_cold && seg_begin(fv, my_pre, my_u, my_cnt, my_ctx, 0);
 #pragma unroll 1
         for (int g0 = 0; g0 < nrows; g0 += ROWS) {
             typename FV::Ctx ctx[ROWS];

@@ -39,6 +39,15 @@ int hot_stages() {
     return stages;
 }
 
+u32 ticket_rows() {
+    static const u32 rows = [] {
+        const char *e = getenv("HERALD_TICKET_ROWS");
+        int v = e ? atoi(e) : 32;
+        return (u32)std::min(std::max(v, 4), 32);
+    }();
+    return rows;
+}
+
 static std::atomic<u64 *> g_seg_trace{nullptr};
 
 u64 *seg_trace_buffer() {

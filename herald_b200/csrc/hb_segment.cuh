@@ -41,7 +41,7 @@ void launch_segment_reduce(KeyWorkspace &ws, const u32 *perm, const float *vals,
     auto k = segment_reduce_kernel<VEC, ROWS, FV, F1>;
     const size_t smem = hot_smem_bytes(hot_stages());
     static const int full = persistent_grid(k, smem);
-    const size_t chunks = (n + 31) / 32; // upper bound of the cold tickets
+    const size_t chunks = (n + ticket_rows() - 1) / ticket_rows(); // upper bound of the cold tickets
     int grid = (int)std::max<size_t>(1, std::min<size_t>(full, (chunks + kRowWarps - 1) / kRowWarps));
     HB_LAUNCH(k, hot ? full : grid, kRowBlock, smem, st, ws.seg_start, perm, ws.num_unique, vals, D, thr, hl,
                                                   fv, f1);
@@ -55,7 +55,7 @@ void run_segment_reduce(KeyWorkspace &ws, const u32 *perm, const float *vals, si
         return;
     const bool hot = n > hot_threshold;
     HotLists hl{ws.hot_a, ws.hot_b, ws.hot_done_a, ws.hot_done_b, ws.hot_ctrl(), seg_trace_buffer(),
-                hot_stages()};
+                hot_stages(), ticket_rows()};
     if (hot) {
         int g = (int)std::min<size_t>((n + 255) / 256, (size_t)sm_count() * 4);
         HB_LAUNCH(build_hot_lists_kernel, std::max(g, 1), 256, 0, st, ws.seg_start, ws.num_unique,

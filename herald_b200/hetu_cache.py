@@ -39,6 +39,7 @@ def _proto():
                                       ctypes.POINTER(ctypes.c_int64)]
     L.hb_cache_set_bypass.argtypes = [_vp, ctypes.c_int]
     L.hb_cache_set_perf.argtypes = [_vp, ctypes.c_int]
+    L.hb_cache_set_perf_sampling.argtypes = [_vp, ctypes.c_uint]
     L.hb_cache_reserve.argtypes = [_vp, _sz]
     L.hb_cache_stream.argtypes = [_vp, ctypes.POINTER(_vp)]
     L.hb_cache_flush.argtypes = [_vp]
@@ -145,6 +146,10 @@ class CacheBase(object):
     @property
     def perf_enabled(self):
         return self._perf_enabled
+
+    def set_perf_sampling(self, every):
+        """Phase timings on every `every`-th update/lookup pair only (herald_b200 extension)."""
+        check_call(_LIB.hb_cache_set_perf_sampling(self._h, int(every)))
 
     @perf_enabled.setter
     def perf_enabled(self, value):

@@ -230,6 +230,10 @@ int hb_cache_set_bypass(hb_cache *c, int on);                   /* cache.cc:15-3
 /* perf_enabled (python_api.cc:40-41): also records the per-phase CUDA events behind
  * hb_perf.sort_ms / lookup_ms / transfer_ms / copy_ms / insert_ms. */
 int hb_cache_set_perf(hb_cache *c, int on);
+/* Phase events (sort / lookup / transfer / copy / insert times) only on every `every`-th pair of
+ * calls: an event between two kernels costs their launch overlap.  Counters are always recorded;
+ * an unsampled call reports zero phase times.  Default 1 (every call, as the reference). */
+int hb_cache_set_perf_sampling(hb_cache *c, unsigned every);
 /* Reserve workspace for calls of up to max_keys keys (grows on demand otherwise). */
 int hb_cache_reserve(hb_cache *c, size_t max_keys);
 /* The CUDA stream (cudaStream_t) all of this cache's work is ordered on. */
