@@ -1777,9 +1777,14 @@ void mark(hb_cache *c, int k) {
     c->phase_mask[idx] |= 1u << k;
 }
 
-void begin_call(hb_cache *c, bool flush = false) {
+void begin_call(hb_cache *c, bool flush = false, int batches = 1) {
     int idx = (int)(c->calls % hb_cache::kRing);
     c->phase_mask[idx] = 0;
+    // the scan arenas of the workspaces this call uses are zeroed here, next to the other
+    // non-kernel stream operations of a call boundary: a memset between two kernels would cost
+    // their launch overlap
+    for (int b = 0; b < batches; b++)
+        c->ws[b].reset_scans(c->stream);
     HB_CUDA(cudaEventRecord(c->ev_begin[idx], c->stream));
     HB_LAUNCH(op_begin_kernel, 1, 1, 0, c->stream, c->view.regs, clk_of(c), flush ? 1 : 0);
     HB_LAUNCHED();
@@ -1805,7 +1810,6 @@ void resolve_batch(hb_cache *c, const void *dev_keys, int kind, size_t n, int ba
     KeyWorkspace &ws = c->ws[batch];
     cudaStream_t st = c->stream;
     c->cur_ticks += n;
-    ws.reset_scans(st);
     SortedKeys sk{nullptr, nullptr};
     const u32 *same = check_same_keys(ws, dev_keys, kind, n, st);
     if (n)
@@ -2245,6 +2249,11 @@ int hb_cache_create(int policy, size_t limit, size_t length, size_t width, int n
         size_t ls = 1 << 16;
         while (ls < 4 * cap)
             ls <<= 1;
+        if (const char *e = getenv("HERALD_STAMP_LOG_SLOTS")) { // tests: a tiny log forces the fallback
+            ls = 16;
+            while (ls < (size_t)std::max(atoi(e), 16))
+                ls <<= 1;
+        }
         v.log_mask = (u32)(ls - 1);
         dmalloc(v.stamp_log, ls);
         HB_CUDA(cudaMemset(v.stamp_log, 0xff, ls * sizeof(u32)));
@@ -2474,7 +2483,7 @@ int hb_cache_push_pull(hb_cache *c, const void *pull_keys, int pull_kind, size_t
                                 cudaMemcpyHostToDevice, st));
         dgrads = stage;
     }
-    begin_call(c, /*flush=*/true);
+    begin_call(c, /*flush=*/true, /*batches=*/2);
     // cache.cc:360-391: pull-side lookup, then push-side lookup + accumulate
     resolve_batch(c, dpull, pull_kind, n_pull, 0, /*dataless=*/false, 0, false);
     resolve_batch(c, dpush, push_kind, n_push, 1, /*dataless=*/true, 1, false);
@@ -2757,7 +2766,6 @@ int hb_cache_touch(hb_cache *c, uint64_t key, int *found, int64_t *version, floa
     KeyWorkspace &ws = c->ws[0];
     // a batched lookup of one key without the insert/sync half: CacheBase::lookup via python
     begin_call(c);
-    ws.reset_scans(st);
     ws.sorted_valid = false;
     HB_LAUNCH(single_key_kernel, 1, 1, 0, st, ws.uniq, ws.num_unique, key);
     HB_LAUNCHED();
@@ -2805,7 +2813,6 @@ int hb_cache_insert(hb_cache *c, uint64_t key, int64_t version, const float *dat
     } else {
         KeyWorkspace &ws = c->ws[0];
         begin_call(c);
-        ws.reset_scans(st);
         ws.sorted_valid = false;
         HB_LAUNCH(single_key_kernel, 1, 1, 0, st, ws.uniq, ws.num_unique, key);
         HB_LAUNCHED();

@@ -355,3 +355,33 @@ def test_flush_then_save_load_roundtrip(tmp_path, policy):
         assert np.array_equal(h.table.read_versions(), vers)
     finally:
         h.close()
+
+
+@pytest.mark.parametrize("slots", [16, 256, 4096])
+@pytest.mark.parametrize("limit,bound,mode", [(5, 0, "plain"), (30, 2, "plain"), (150, 0, "plan"),
+                                               (30, 0, "pushpull"), (400, 10, "plain")])
+def test_lru_stamp_log_fallback(oracle_impl, monkeypatch, slots, limit, bound, mode):
+    """LRU victims come from the stamp-log walk while [floor, now) fits the log and from the
+    histogram select otherwise (the device decides per call).  A tiny log makes calls alternate
+    between the two paths; hit/miss/evict sets and rows must stay those of the reference."""
+    monkeypatch.setenv("HERALD_STAMP_LOG_SLOTS", str(slots))
+    _run_sequence(oracle_impl, "lru", limit, bound, seed=7 * slots + limit, steps=80,
+                  push_keys=mode == "plan", push_pull=mode == "pushpull")
+
+
+def test_perf_sampling(oracle_impl):
+    """hb_cache_set_perf_sampling: phase times only on every n-th pair of calls, counters always."""
+    rng = np.random.default_rng(5)
+    h = GpuHarness(oracle_impl, "lru", 50, 0, _rows(rng, 300, 8))
+    try:
+        h.gc.set_perf_sampling(4)
+        for t in range(16):
+            keys = zipf_keys(rng, 40, 300, 1.3)
+            h.lookup(keys, "step %d" % t)
+            h.update(keys, rng.normal(0, 1e-3, (len(keys), 8)).astype(np.float32), None, "step %d" % t)
+        perf = list(h.gc.perf)[-32:]
+        timed = [p for p in perf if p["lookup_time"] > 0]
+        assert 0 < len(timed) < len(perf)
+        assert all(p["num_all"] == 40 and p["time"] > 0 for p in perf)
+    finally:
+        h.close()
