@@ -125,7 +125,7 @@ class ClockSampler(threading.Thread):
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + self.Q,
-                 "--format=csv,noheader,nounits", "-lms", "100"],
+                 "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             for line in self.proc.stdout:
                 self.rows.append([x.strip() for x in line.split(",")])
@@ -400,7 +400,6 @@ def herald_main(args, rank, world, local_rank):
             print(json.dumps({"diag": "phase events off", "ms_per_step": ms / K}), flush=True)
         os._exit(0)
     perf = list(cst.perf)[-2 * K:]
-    clocks = sampler.stop() if rank == 0 else None
 
     if args.seg_trace and rank == 0:
         seg_trace(args.seg_trace, lambda: step(W + K - 1, ids_dev, grads_dev, dest_dev, True))
@@ -425,6 +424,8 @@ def herald_main(args, rank, world, local_rank):
         e2e_ms = ev[3].time_since(ev[2])
         checksum = float(dest_host[0].asnumpy()[0, 0, 0])       # the result is read on the host
         e2e = {"ms": e2e_ms, "steps": Ke - 1, "checksum": checksum}
+
+    clocks = sampler.stop() if rank == 0 else None   # sampled over both timed regions (device-resident, e2e)
 
     # ---- max over ranks ----
     if dist is not None:

@@ -948,12 +948,11 @@ __global__ void min_pick_kernel(CacheView c) {
 
 // Remove the victims from the index; dirty ones wait for the next push (evict_), clean ones
 // are freed (lru_cache.cc:17-24).
-__global__ void evict_apply_kernel(CacheView c) {
-    pdl_enter();
+__device__ __forceinline__ void evict_apply(const CacheView &c, u32 block, u32 nblocks) {
     CacheRegs *r = c.regs;
     const u32 nv = r->nv;
-    const u32 stride = gridDim.x * blockDim.x;
-    for (u32 v0 = blockIdx.x * blockDim.x; v0 < nv; v0 += stride) { // block-uniform trip count
+    const u32 stride = nblocks * blockDim.x;
+    for (u32 v0 = block * blockDim.x; v0 < nv; v0 += stride) { // block-uniform trip count
         const u32 v = v0 + threadIdx.x;
         const bool act = v < nv;
         u32 s = 0;
@@ -979,14 +978,14 @@ __global__ void evict_apply_kernel(CacheView c) {
     }
 }
 
-__global__ void insert_new_kernel(CacheView c, const i32 *uslot, const u32 *miss_list) {
-    pdl_enter();
+__device__ __forceinline__ void insert_new(const CacheView &c, const i32 *uslot, const u32 *miss_list,
+                                           u32 block, u32 nblocks) {
     CacheRegs *r = c.regs;
     const u32 M = r->M, n_drop = r->n_drop;
     const u64 clock0 = r->ins_clock0;
     const u32 use0 = c.policy == HB_POLICY_LFU ? 1u : 0u;
     u32 fresh = 0;
-    for (u32 j = blockIdx.x * blockDim.x + threadIdx.x; j < M; j += gridDim.x * blockDim.x) {
+    for (u32 j = block * blockDim.x + threadIdx.x; j < M; j += nblocks * blockDim.x) {
         const u32 s = (u32)uslot[miss_list[j]];
         if (j < n_drop) { // served to the caller but never resident after the call
             c.slot_state[s] = S_FREE;
@@ -1001,6 +1000,21 @@ __global__ void insert_new_kernel(CacheView c, const i32 *uslot, const u32 *miss
         c.slot_state[s] = S_CACHED;
     }
     add_occupied(&r->ht_occupied, fresh);
+}
+
+// One launch for both halves of the batched insert: the first `evict_blocks` blocks take the
+// victims out of the index, the others put the new lines in.  The two may interleave on the
+// open-addressing index: an insert only fills EMPTY or TOMB entries and an erase only turns its
+// own key into TOMB, so no probe chain ever gains an EMPTY entry in front of a live key; the
+// slots of the new lines were taken from the free stack before (alloc_kernel), the victims'
+// slots return to it for later calls.
+__global__ void __launch_bounds__(256)
+    evict_insert_kernel(CacheView c, const i32 *uslot, const u32 *miss_list, u32 evict_blocks) {
+    pdl_enter();
+    if (blockIdx.x < evict_blocks)
+        evict_apply(c, blockIdx.x, evict_blocks);
+    else
+        insert_new(c, uslot, miss_list, blockIdx.x - evict_blocks, gridDim.x - evict_blocks);
 }
 
 // =====================================================================================
@@ -1917,9 +1931,8 @@ void run_insert(hb_cache *c, size_t n, int clk_stage) {
         HB_LAUNCH(min_pick_kernel, sgrid, 256, 0, st, c->view);
         HB_LAUNCHED();
     }
-    HB_LAUNCH(evict_apply_kernel, lin_grid(n), 256, 0, st, c->view);
-    HB_LAUNCHED();
-    HB_LAUNCH(insert_new_kernel, lin_grid(n), 256, 0, st, c->view, c->uslot[0], c->miss_list[0]);
+    const u32 half = (u32)std::max(1, lin_grid(n) / 2);
+    HB_LAUNCH(evict_insert_kernel, 2 * half, 256, 0, st, c->view, c->uslot[0], c->miss_list[0], half);
     HB_LAUNCHED();
 }
 
