@@ -102,7 +102,7 @@ __device__ __forceinline__ u64 pack_status(u32 epoch, u32 flag, u32 value) {
 template <int KIND, bool FIRST, bool PIN, bool POUT>
 __global__ void __launch_bounds__(SORT_THREADS)
     sort_pass_kernel(const void *kin, const u32 *vin, u64 *kout, u32 *vout, size_t n, int shift,
-                     const u32 *__restrict__ totals, u64 *status, u32 *ticket, u32 epoch,
+                     const u32 *__restrict__ totals, u64 *status, u32 *counts, u32 *ticket, u32 epoch,
                      const u32 *mismatch) {
     pdl_enter();
     __shared__ u32 s_cnt[SORT_WARPS][RADIX];
@@ -139,6 +139,12 @@ __global__ void __launch_bounds__(SORT_THREADS)
     }
     rank_tile(shift, s_cnt, key, rank, valid);
     constexpr int DPT = RADIX / SORT_THREADS; // consecutive digits per thread
+    // With few tiles (a WDL batch: 52) every tile publishes its own digit counts once and sums the
+    // counts of ALL its predecessors with independent loads: one L2 round trip, where the chained
+    // look-back below pays one per 16 predecessors (the tiles of a small sort start together, so
+    // nobody finds a finished prefix to stop at).  tag = epoch folded to 19 bits, never 0.
+    const bool direct = gridDim.x <= (unsigned)kSortDirectTiles;
+    const u32 tag = (epoch % 0x7fffeu) + 1u;
     u32 cnt[DPT], tot[DPT];
     u32 tsum = 0;
 #pragma unroll
@@ -152,8 +158,11 @@ __global__ void __launch_bounds__(SORT_THREADS)
             run += t;
         }
         cnt[k] = run;
-        *reinterpret_cast<volatile u64 *>(&status[(size_t)tile * RADIX + b]) =
-            pack_status(epoch, tile == 0 ? 2u : 1u, run);
+        if (direct)
+            *reinterpret_cast<volatile u32 *>(&counts[(size_t)tile * RADIX + b]) = (tag << 13) | run;
+        else
+            *reinterpret_cast<volatile u64 *>(&status[(size_t)tile * RADIX + b]) =
+                pack_status(epoch, tile == 0 ? 2u : 1u, run);
         tot[k] = totals[b];
         tsum += tot[k];
     }
@@ -171,12 +180,26 @@ __global__ void __launch_bounds__(SORT_THREADS)
     u32 base = incl - tsum;
     for (unsigned w = 0; w < warp; w++)
         base += s_wsum[w];
-    // look back over the earlier tiles
+    // digit offsets of this tile = first position of the digit + its count in the earlier tiles
 #pragma unroll
     for (int k = 0; k < DPT; k++) {
         const int b = threadIdx.x * DPT + k;
         u32 excl = 0;
-        if (tile > 0) {
+        if (direct) {
+            u32 sv[kSortDirectTiles];
+#pragma unroll
+            for (int i = 0; i < kSortDirectTiles; i++)
+                sv[i] = i < (int)tile ? *reinterpret_cast<volatile u32 *>(&counts[(size_t)i * RADIX + b])
+                                      : (tag << 13);
+#pragma unroll
+            for (int i = 0; i < kSortDirectTiles; i++) {
+                if (i < (int)tile) {
+                    while ((sv[i] >> 13) != tag)
+                        sv[i] = *reinterpret_cast<volatile u32 *>(&counts[(size_t)i * RADIX + b]);
+                    excl += sv[i] & 0x1fffu;
+                }
+            }
+        } else if (tile > 0) {
             // kLook predecessors per round trip (independent loads); stop at the nearest one
             // that already holds a prefix
             constexpr int kLook = 16;
@@ -350,6 +373,8 @@ void KeyWorkspace::reserve(size_t n) {
     nblk_cap = (c + SORT_TILE - 1) / SORT_TILE;
     dev_alloc(sort_status, (size_t)RADIX * nblk_cap);
     HB_CUDA(cudaMemset(sort_status, 0, (size_t)RADIX * nblk_cap * sizeof(u64)));
+    dev_alloc(sort_counts, (size_t)RADIX * kSortDirectTiles);
+    HB_CUDA(cudaMemset(sort_counts, 0, (size_t)RADIX * kSortDirectTiles * sizeof(u32)));
     dev_alloc(uniq, c);
     dev_alloc(inverse, c);
     dev_alloc(seg_start, c + 1);
@@ -371,6 +396,7 @@ void KeyWorkspace::release() {
         dev_free(vals[i]);
     }
     dev_free(sort_status);
+    dev_free(sort_counts);
     dev_free(uniq);
     dev_free(inverse);
     dev_free(seg_start);
@@ -419,6 +445,8 @@ SortedKeys radix_sort_keys(KeyWorkspace &ws, const void *keys_in, int key_kind, 
         bool first = p == 0;
         bool f32 = first && key_kind == HB_KEYS_F32;
         u32 epoch = ws.next_sort_epoch();
+        if (nblk <= kSortDirectTiles && epoch % 0x7fffeu == 0) // the 19-bit tag starts over
+            HB_CUDA(cudaMemsetAsync(ws.sort_counts, 0, (size_t)RADIX * kSortDirectTiles * sizeof(u32), st));
         const u32 *tp = totals + (size_t)p * RADIX;
         u32 *ticket = ws.sort_tickets() + p;
         // keys below 2^32 travel packed with their index between the passes
@@ -426,7 +454,7 @@ SortedKeys radix_sort_keys(KeyWorkspace &ws, const void *keys_in, int key_kind, 
         const bool pin = packed && !first, pout = packed && p + 1 < passes;
 #define HB_SORT_PASS(KIND, F, PI, PO)                                                             \
     HB_LAUNCH((sort_pass_kernel<KIND, F, PI, PO>), nblk, SORT_THREADS, 0, st, \
-        kin, vin, ws.keys[out], ws.vals[out], n, shift, tp, ws.sort_status, ticket, epoch, mismatch)
+        kin, vin, ws.keys[out], ws.vals[out], n, shift, tp, ws.sort_status, ws.sort_counts, ticket, epoch, mismatch)
         if (f32 && pout)
             HB_SORT_PASS(HB_KEYS_F32, true, false, true);
         else if (f32)

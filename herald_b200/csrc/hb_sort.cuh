@@ -12,6 +12,7 @@
 
 namespace hb {
 
+constexpr int kSortDirectTiles = 56; // passes of at most this many tiles sum their predecessors' counts directly
 constexpr int kScanSlots = 12;  // independent grid-scan states per workspace
 constexpr int kScanBlock = 256; // threads per scan tile
 constexpr int kSortRadixBits = 9;
@@ -24,6 +25,7 @@ struct KeyWorkspace {
     u64 *keys[2] = {nullptr, nullptr}; // ping-pong sort buffers (keys)
     u32 *vals[2] = {nullptr, nullptr}; // ping-pong sort buffers (original index)
     u64 *sort_status = nullptr;        // [nblk][RADIX] look-back status words (epoch-tagged)
+    u32 *sort_counts = nullptr;        // [kSortDirectTiles][RADIX] per-tile digit counts (tag << 13 | count)
     size_t nblk_cap = 0;
     u32 sort_epoch = 0;                // one epoch per sort pass ever run on this workspace
     // results of unique_from_sorted
