@@ -211,31 +211,41 @@ __device__ __forceinline__ ScanResult grid_exclusive_scan(ScanState st, u32 valu
         } else {
             if (lane == 0)
                 atomicExch(&st.status[tile], (1ull << 32) | block_sum);
+            // kGroups x 32 predecessors are loaded before the first is examined: the tiles of a
+            // small problem start together, so nobody finds a finished prefix early and a
+            // round trip per 32 predecessors would be paid serially
+            constexpr int kGroups = 8;
             int look = (int)tile - 1;
-            while (true) {
-                int idx = look - (int)lane;
-                u64 s;
-                if (idx >= 0) {
-                    do {
-                        s = *((volatile u64 *)&st.status[idx]);
-                    } while ((s >> 32) == 0);
-                } else {
-                    s = 2ull << 32; // virtual tile before tile 0: prefix 0
-                }
-                unsigned is_prefix = __ballot_sync(FULL, (s >> 32) == 2);
-                u32 v = (u32)s;
-                if (is_prefix) {
-                    int first = __ffs(is_prefix) - 1; // nearest tile holding a full prefix
-                    if ((int)lane > first)
-                        v = 0;
+            bool found = false;
+            while (!found) {
+                u64 s[kGroups];
+#pragma unroll
+                for (int g = 0; g < kGroups; g++) {
+                    const int idx = look - g * 32 - (int)lane;
+                    s[g] = idx >= 0 ? *((volatile u64 *)&st.status[idx]) : (2ull << 32);
                 }
 #pragma unroll
-                for (int d = 16; d > 0; d >>= 1)
-                    v += __shfl_xor_sync(FULL, v, d);
-                prefix += v;
-                if (is_prefix)
-                    break;
-                look -= 32;
+                for (int g = 0; g < kGroups; g++) {
+                    if (found)
+                        continue;
+                    const int idx = look - g * 32 - (int)lane;
+                    if (idx >= 0)
+                        while ((s[g] >> 32) == 0)
+                            s[g] = *((volatile u64 *)&st.status[idx]);
+                    unsigned is_prefix = __ballot_sync(FULL, (s[g] >> 32) == 2);
+                    u32 v = (u32)s[g];
+                    if (is_prefix) {
+                        int first = __ffs(is_prefix) - 1; // nearest tile holding a full prefix
+                        if ((int)lane > first)
+                            v = 0;
+                    }
+#pragma unroll
+                    for (int d = 16; d > 0; d >>= 1)
+                        v += __shfl_xor_sync(FULL, v, d);
+                    prefix += v;
+                    found = is_prefix != 0;
+                }
+                look -= kGroups * 32;
             }
             if (lane == 0)
                 atomicExch(&st.status[tile], (2ull << 32) | (prefix + block_sum));

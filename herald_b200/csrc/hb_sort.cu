@@ -308,10 +308,26 @@ __global__ void __launch_bounds__(256)
     pdl_enter();
     const u32 U = *num_unique;
     bool bad = false;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
-         i += (size_t)gridDim.x * blockDim.x) {
-        const u32 r = inverse[i];
-        bad |= r >= U || uniq[r] != load_key<KIND>(kin, i);
+    // kSame elements per thread, each level of the dependent loads (inverse -> uniq) issued for
+    // all of them before the first use
+    constexpr int kSame = 4;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < n; i0 += stride * kSame) {
+        u32 r[kSame];
+        u64 k[kSame], q[kSame];
+#pragma unroll
+        for (int j = 0; j < kSame; j++) {
+            const size_t i = i0 + j * stride;
+            r[j] = i < n ? inverse[i] : 0;
+            k[j] = i < n ? load_key<KIND>(kin, i) : 0;
+        }
+#pragma unroll
+        for (int j = 0; j < kSame; j++)
+            q[j] = (i0 + j * stride < n && r[j] < U) ? uniq[r[j]] : ~0ull;
+#pragma unroll
+        for (int j = 0; j < kSame; j++)
+            if (i0 + j * stride < n)
+                bad |= r[j] >= U || q[j] != k[j];
     }
     if (__any_sync(FULL, bad) && lane_id() == 0)
         atomicAdd(mismatch, 1u);
