@@ -1,6 +1,6 @@
 set -x
 mkdir -p gpurun_out
-TAG=${TAG:-c3}
+TAG=${TAG:-chk}
 timeout 700 python -m pytest tests -m gpu -x -q 2>&1 | tail -15 > gpurun_out/${TAG}_pytest.log
 timeout 600 python bench.py --steps 50 --warmup 20 --no-cpu-baseline --no-e2e --seg-trace gpurun_out/${TAG}_segtrace.json > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err
 tail -3 gpurun_out/${TAG}_bench.err
