@@ -20,6 +20,9 @@
 // the Python wire format (:126-135, :166-168), is reproduced by hb_laia_next.
 #include <algorithm>
 #include <atomic>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <thread>
 #include <vector>
@@ -219,6 +222,8 @@ struct hb_laia {
     // scratch
     std::vector<u32> scores;             // [batch][W]
     std::vector<u32> assigned;           // [batch] worker of each sample
+    std::vector<u64> holders;            // [batch][T] bit z: the embedding is valid in worker z's snapshot
+                                         // (W <= 64; the reference's sample_emb_dep_, as a bit set)
 };
 
 namespace {
@@ -240,11 +245,18 @@ bool laia_advance(hb_laia *s) { // laia_scheduler.cc:126-135, 166
     }
 }
 
+double now_ms() {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
 void laia_plan_batch(hb_laia *s) {
+    static const bool timing = getenv("HERALD_LAIA_TIMING") != nullptr; // per-phase ms on stderr
+    const double t0 = timing ? now_ms() : 0;
     const size_t W = s->W, B = s->batch_size, T = s->num_table, S = s->num_sample;
     const size_t start = (s->batch_id * B) % S;
     auto pos_of = [&](size_t i) { return (start + i) % S; };
     // scoring: chunks of samples over the threads
+    const bool use_bits = W <= 64;
     const size_t chunks = std::min<size_t>(B, s->threads * 4);
     parallel_for(chunks, s->threads, [&](size_t c) {
         const size_t lo = B * c / chunks, hi = B * (c + 1) / chunks;
@@ -253,11 +265,19 @@ void laia_plan_batch(hb_laia *s) {
             u32 *sc = &s->scores[i * W];
             for (size_t z = 0; z < W; z++)
                 sc[z] = 0;
-            for (size_t j = 0; j < T; j++)
+            for (size_t j = 0; j < T; j++) {
+                u64 bits = 0;
                 for (size_t z = 0; z < W; z++)
-                    sc[z] += s->snaps[z].check(e[j]) ? 1u : 0u;
+                    if (s->snaps[z].check(e[j])) {
+                        sc[z]++;
+                        bits |= 1ull << (z & 63);
+                    }
+                if (use_bits)
+                    s->holders[i * T + j] = bits;
+            }
         }
     });
+    const double t1 = timing ? now_ms() : 0;
     // greedy assignment (serial: every choice depends on the workloads so far)
     std::vector<size_t> workload(W, 0);
     for (size_t i = 0; i < B; i++) {
@@ -275,6 +295,7 @@ void laia_plan_batch(hb_laia *s) {
         s->assigned[i] = (u32)best_w;
         workload[best_w]++;
     }
+    const double t2 = timing ? now_ms() : 0;
     // communication plan + snapshot update, one worker per thread
     parallel_for(W, s->threads, [&](size_t w) {
         std::vector<u64> &plan = s->plans[w];
@@ -284,9 +305,16 @@ void laia_plan_batch(hb_laia *s) {
             if (s->assigned[i] == w)
                 continue;
             const u64 *e = &s->embs[pos_of(i) * T];
-            for (size_t j = 0; j < T; j++)
-                if (snap.check(e[j]))
-                    plan.push_back(e[j]);
+            if (use_bits) { // what scoring saw (the snapshots have not changed since)
+                const u64 *h = &s->holders[i * T];
+                for (size_t j = 0; j < T; j++)
+                    if ((h[j] >> w) & 1ull)
+                        plan.push_back(e[j]);
+            } else {
+                for (size_t j = 0; j < T; j++)
+                    if (snap.check(e[j]))
+                        plan.push_back(e[j]);
+            }
         }
         std::sort(plan.begin(), plan.end());
         plan.erase(std::unique(plan.begin(), plan.end()), plan.end());
@@ -303,6 +331,9 @@ void laia_plan_batch(hb_laia *s) {
         for (u64 k : uniq)
             snap.get(k);
     });
+    if (timing)
+        fprintf(stderr, "laia batch %zu: score %.2f ms, assign %.2f ms, plan + snapshots %.2f ms\n", s->batch_id,
+                t1 - t0, t2 - t1, now_ms() - t2);
     s->batch_id++;
 }
 
@@ -337,6 +368,8 @@ int hb_laia_create(hb_laia **out, const uint64_t *sample_embs, size_t num_sample
     s->dist.assign(nrank * mini_batch_size, 0);
     s->scores.assign(s->batch_size * nrank, 0);
     s->assigned.assign(s->batch_size, 0);
+    if (nrank <= 64)
+        s->holders.assign(s->batch_size * num_table, 0);
     *out = s;
     HB_API_END();
 }

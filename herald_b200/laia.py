@@ -138,3 +138,79 @@ class MiniLRUCache(object):
                 _LIB.hb_minilru_destroy(self._h)
         except Exception:
             pass
+
+
+class LAIAScheduler(object):
+    """python/hetu/laia/laia_dataloader.py:28-169: the per-process front end of the planner that
+    `run_laia.py` builds (`LAIAScheduler(sparse_data, batch_size)`, then `start(config)`), keeps
+    `queue_size` batches planned ahead and hands out, for batch b, the sample indices of b and the
+    communication plan computed for b + 1 (the first plan is discarded, :108-114).  `config` needs
+    `nrank`, `rank`, `local_rank`, `cache_limit` (HetuConfig).  The `local_shared` / TopkScheduler
+    variant of the reference is not provided."""
+
+    def __init__(self, sparse_data, batch_size, drop_last=True, dataset="criteo", local_shared=False):
+        if local_shared:
+            raise NotImplementedError("the TopkScheduler (local_shared) variant is not provided")
+        self.sparse_data = np.array(sparse_data, np.float32).astype(np.intc)    # :30 (ids are float32-carried)
+        self.batch_size = batch_size
+        self.drop_last = drop_last
+        self.init = False
+        self.dataset = dataset
+        self.local_shared = False
+
+    def start(self, config, dataset_num=3, epoch_num=-1):
+        assert not self.init, "LAIA scheduler can only be initialized once"
+        self.local_rank = config.local_rank
+        self.samples_num = len(self.sparse_data) // config.nrank
+        self.queue_size = 5
+        self.batch_size = min(int(self.batch_size), self.samples_num // self.queue_size)
+        assert self.batch_size > 0, "Batch size %d invalid." % self.batch_size
+        self.batch_num = (int(np.ceil(self.samples_num / self.batch_size)) if not self.drop_last
+                          else self.samples_num // self.batch_size)
+        self.sched = LaiaScheduler()
+        epochs = epoch_num if epoch_num >= 0 else (1 << 62)          # -1: plan until closed
+        self.sched.start(self.sparse_data, self.sparse_data.shape[0], self.sparse_data.shape[1], epochs,
+                         self.batch_size, self.batch_num, int(config.nrank), int(config.rank),
+                         int(config.cache_limit), 16, 24)
+        self.channel_close = False
+        self.input_index, self.comm_plan, self.arr_map = [], [], {}
+        for i in range(self.queue_size):                             # :108-114
+            if i == 0:
+                self._channel_get()                                  # discard the first comm_plan
+            self.input_index.append(self._channel_get())
+            self.comm_plan.append(self._channel_get())
+            self.arr_map[i] = i
+        self.step = [0] * dataset_num
+        self.cur_min_step = 0
+        self.init = True
+
+    def _channel_get(self):
+        if self.channel_close:
+            raise RuntimeError("Channle have been closed, but still try to get value from it")
+        res = self.sched.pop()
+        assert isinstance(res, list)
+        if len(res) == 1 and res[0] == 0:                            # :137-139 (a plan of exactly [0] too)
+            self.channel_close = True
+            return []
+        return res
+
+    def get_input_index(self, batch_id):
+        return self.input_index[self.arr_map[batch_id]]
+
+    def get_comm_plan(self, batch_id):
+        return self.comm_plan[self.arr_map[batch_id]]
+
+    def step_forward(self, dataset_id):                              # :150-169
+        self.step[dataset_id] += 1
+        new_min_step = min(self.step)
+        while self.cur_min_step < new_min_step:
+            if self.channel_close or (self.sched.length() < 2
+                                      and new_min_step - self.cur_min_step < self.queue_size):
+                break
+            min_batch_id = self.cur_min_step % self.batch_num
+            arr_index = self.arr_map.pop(min_batch_id)
+            self.input_index[arr_index] = self._channel_get()
+            self.comm_plan[arr_index] = self._channel_get()
+            new_batch_id = (min_batch_id + self.queue_size) % self.batch_num
+            self.arr_map[new_batch_id] = arr_index
+            self.cur_min_step += 1

@@ -165,3 +165,29 @@ def test_mini_lru_random_against_port():
         else:
             assert a.check(k) == b.check(k)
     assert list(a.get_keys()) == b.get_keys()
+
+
+def test_laia_front_end_pairs_indices_with_the_next_plan():
+    """laia_dataloader.py:108-114, 150-169: batch b = (sample indices of b, plan computed for b + 1);
+    five batches planned ahead; stepping every dataset forward refills the oldest slot."""
+    from herald_b200.laia import LAIAScheduler
+
+    class Config(object):
+        nrank, rank, local_rank, cache_limit = 2, 1, 1, 30
+
+    rng = np.random.default_rng(11)
+    data = ((rng.zipf(1.3, (160, 4)) - 1) % 50 + 1).astype(np.float32)  # ids >= 1: a plan never reads as [0]
+    front = LAIAScheduler(data, batch_size=8)
+    front.start(Config, dataset_num=1, epoch_num=1)
+    assert front.batch_num == 10 and front.queue_size == 5
+    planner = laia_port.LaiaPlanner(data.astype(np.int64), 8, 2, 30, 1, 10)
+    seq = []
+    while True:
+        r = planner.next_all()
+        if r is None:
+            break
+        seq.append((r[0][1], r[1][1]))                                # rank 1: (plan, dist)
+    for b in range(8):
+        assert front.get_input_index(b % front.batch_num) == seq[b][1], b
+        assert front.get_comm_plan(b % front.batch_num) == seq[b + 1][0], b
+        front.step_forward(0)
