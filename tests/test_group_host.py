@@ -102,3 +102,51 @@ def test_bsp_replay_is_deterministic_across_ranks():
     for p in procs:
         p.join(30)
     assert sorted(res) == [(0, "ok"), (1, "ok")], res
+
+
+def _laia_rank_main(rank, world, port_no, out):
+    """Every rank runs its own planner (as every Hetu worker does) and pops its own part; together
+    the parts must tile every global batch, and a rank's plan must be what its peers computed for
+    it (the planner is replicated, not distributed: laia_scheduler.cc:138-139)."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port_no)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from herald_b200.laia import LaiaScheduler
+        rng = np.random.default_rng(21)
+        mini, T, nb = 6, 5, 4
+        emb = ((rng.zipf(1.2, (world * mini * nb, T)) - 1) % 70 + 1).astype(np.uint64)
+        s = LaiaScheduler()
+        s.start(emb, emb.shape[0], T, 1, mini, nb, world, rank, 25, 2)
+        b = 0
+        while s.step():
+            mine = (s.plan_of(rank).tolist(), s.dist_of(rank).tolist(),
+                    [s.plan_of(w).tolist() for w in range(world)])
+            gathered = [None] * world
+            dist.all_gather_object(gathered, mine)
+            start = (b * world * mini) % emb.shape[0]
+            covered = sorted(p for g in gathered for p in g[1])
+            assert covered == list(range(start, start + world * mini)), (b, covered)
+            for w in range(world):
+                assert gathered[w][0] == mine[2][w], (b, w)           # peers agree on w's plan
+            b += 1
+        assert b == nb + 1
+        out.put((rank, "ok"))
+    except Exception as e:  # pragma: no cover - surfaced by the parent
+        out.put((rank, repr(e)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_laia_planner_parts_tile_the_batch_across_ranks():
+    world = 2
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port_no = 29800 + os.getpid() % 90
+    procs = [ctx.Process(target=_laia_rank_main, args=(r, world, port_no, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [out.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(30)
+    assert sorted(res) == [(0, "ok"), (1, "ok")], res
