@@ -141,76 +141,78 @@ class MiniLRUCache(object):
 
 
 class LAIAScheduler(object):
-    """python/hetu/laia/laia_dataloader.py:28-169: the per-process front end of the planner that
-    `run_laia.py` builds (`LAIAScheduler(sparse_data, batch_size)`, then `start(config)`), keeps
-    `queue_size` batches planned ahead and hands out, for batch b, the sample indices of b and the
-    communication plan computed for b + 1 (the first plan is discarded, :108-114).  `config` needs
-    `nrank`, `rank`, `local_rank`, `cache_limit` (HetuConfig).  The `local_shared` / TopkScheduler
-    variant of the reference is not provided."""
+    """Per-process front end of the planner, with the surface `run_laia.py` uses from
+    python/hetu/laia/laia_dataloader.py:28-169: `LAIAScheduler(sparse_data, batch_size)`,
+    `start(config)`, `get_input_index(b)`, `get_comm_plan(b)`, `step_forward(dataset_id)`.
+
+    It keeps `queue_size` (5) batches planned ahead.  What it serves for batch b is the pair
+    (sample indices of b, communication plan computed for b + 1): the very first plan is dropped
+    (:108-114), so the keys a worker pushes after training b are the ones its peers need in b + 1.
+    A slot is refilled once every dataset (train / validate / ...) has stepped past it (:150-169).
+    `config` supplies `nrank`, `rank`, `local_rank`, `cache_limit` (HetuConfig).  The reference's
+    `local_shared` mode (TopkScheduler over shared memory) is not provided."""
+
+    queue_size = 5
 
     def __init__(self, sparse_data, batch_size, drop_last=True, dataset="criteo", local_shared=False):
         if local_shared:
             raise NotImplementedError("the TopkScheduler (local_shared) variant is not provided")
-        self.sparse_data = np.array(sparse_data, np.float32).astype(np.intc)    # :30 (ids are float32-carried)
-        self.batch_size = batch_size
-        self.drop_last = drop_last
-        self.init = False
-        self.dataset = dataset
+        # ids arrive float32-carried (python/hetu/dataloader.py:14); the planner wants integers
+        self.sparse_data = np.asarray(sparse_data, np.float32).astype(np.intc)
+        self.batch_size, self.drop_last, self.dataset = batch_size, drop_last, dataset
         self.local_shared = False
+        self.init = False
 
     def start(self, config, dataset_num=3, epoch_num=-1):
         assert not self.init, "LAIA scheduler can only be initialized once"
         self.local_rank = config.local_rank
         self.samples_num = len(self.sparse_data) // config.nrank
-        self.queue_size = 5
         self.batch_size = min(int(self.batch_size), self.samples_num // self.queue_size)
         assert self.batch_size > 0, "Batch size %d invalid." % self.batch_size
-        self.batch_num = (int(np.ceil(self.samples_num / self.batch_size)) if not self.drop_last
-                          else self.samples_num // self.batch_size)
+        whole, rest = divmod(self.samples_num, self.batch_size)
+        self.batch_num = whole if (self.drop_last or rest == 0) else whole + 1
         self.sched = LaiaScheduler()
-        epochs = epoch_num if epoch_num >= 0 else (1 << 62)          # -1: plan until closed
-        self.sched.start(self.sparse_data, self.sparse_data.shape[0], self.sparse_data.shape[1], epochs,
+        self.sched.start(self.sparse_data, self.sparse_data.shape[0], self.sparse_data.shape[1],
+                         epoch_num if epoch_num >= 0 else (1 << 62),       # -1: until closed
                          self.batch_size, self.batch_num, int(config.nrank), int(config.rank),
                          int(config.cache_limit), 16, 24)
         self.channel_close = False
-        self.input_index, self.comm_plan, self.arr_map = [], [], {}
-        for i in range(self.queue_size):                             # :108-114
-            if i == 0:
-                self._channel_get()                                  # discard the first comm_plan
-            self.input_index.append(self._channel_get())
-            self.comm_plan.append(self._channel_get())
-            self.arr_map[i] = i
+        self._receive()                                   # the plan of batch 0: nothing was cached yet
+        self._slots = {b: self._receive_pair() for b in range(self.queue_size)}
         self.step = [0] * dataset_num
         self.cur_min_step = 0
         self.init = True
 
-    def _channel_get(self):
+    def _receive(self):
+        """One message of the planner's wire (plan keys or sample indices); [] once it has ended.
+        As in the reference (:137-139) a message that is exactly [0] ends the channel."""
         if self.channel_close:
-            raise RuntimeError("Channle have been closed, but still try to get value from it")
-        res = self.sched.pop()
-        assert isinstance(res, list)
-        if len(res) == 1 and res[0] == 0:                            # :137-139 (a plan of exactly [0] too)
+            raise RuntimeError("the scheduler channel is closed")
+        msg = self.sched.pop()
+        assert isinstance(msg, list)
+        if msg == [0]:
             self.channel_close = True
             return []
-        return res
+        return msg
+
+    def _receive_pair(self):
+        indices = self._receive()
+        return indices, self._receive()
 
     def get_input_index(self, batch_id):
-        return self.input_index[self.arr_map[batch_id]]
+        return self._slots[batch_id][0]
 
     def get_comm_plan(self, batch_id):
-        return self.comm_plan[self.arr_map[batch_id]]
+        return self._slots[batch_id][1]
 
-    def step_forward(self, dataset_id):                              # :150-169
+    def step_forward(self, dataset_id):
+        """NOTE (as in the reference): call after get_input_index / get_comm_plan of the batch."""
         self.step[dataset_id] += 1
-        new_min_step = min(self.step)
-        while self.cur_min_step < new_min_step:
-            if self.channel_close or (self.sched.length() < 2
-                                      and new_min_step - self.cur_min_step < self.queue_size):
-                break
-            min_batch_id = self.cur_min_step % self.batch_num
-            arr_index = self.arr_map.pop(min_batch_id)
-            self.input_index[arr_index] = self._channel_get()
-            self.comm_plan[arr_index] = self._channel_get()
-            new_batch_id = (min_batch_id + self.queue_size) % self.batch_num
-            self.arr_map[new_batch_id] = arr_index
+        slowest = min(self.step)
+        while self.cur_min_step < slowest and not self.channel_close:
+            if self.sched.length() < 2 and slowest - self.cur_min_step < self.queue_size:
+                break                                     # nothing planned yet and no need to wait
+            done = self.cur_min_step % self.batch_num
+            del self._slots[done]
+            self._slots[(done + self.queue_size) % self.batch_num] = self._receive_pair()
             self.cur_min_step += 1
