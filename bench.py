@@ -325,7 +325,17 @@ def herald_main(args, rank, world, local_rank):
             dist.broadcast_object_list(obj, src=0)
             return obj[0]
 
-        ps.group_init(rank, world, local_rank, exchange)
+        # NCCL prints "NCCL version ..." on file descriptor 1 while the communicator comes up:
+        # keep stdout for the one JSON line
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            ps.group_init(rank, world, local_rank, exchange)
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
 
     dev = hb.gpu(local_rank)
     B, D, V = args.batch, args.dim, args.vocab
