@@ -334,6 +334,10 @@ def herald_main(args, rank, world, local_rank):
             ps.group_init(rank, world, local_rank, exchange)
         finally:
             sys.stdout.flush()
+            try:
+                ctypes.CDLL(None).fflush(None)      # anything still in C stdio buffers goes to stderr too
+            except Exception:
+                pass
             os.dup2(saved_fd, 1)
             os.close(saved_fd)
 
