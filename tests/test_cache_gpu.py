@@ -385,3 +385,31 @@ def test_perf_sampling(oracle_impl):
         assert all(p["num_all"] == 40 and p["time"] > 0 for p in perf)
     finally:
         h.close()
+
+
+@pytest.mark.parametrize("policy,bound", [("lru", 10), ("lfu", 2)])
+def test_laia_plan_as_push_keys(oracle_impl, policy, bound):
+    """run_laia's loop for one worker of three: the planner (herald_b200.laia, host C++) chooses
+    the samples and the push plan, the GPU cache executes lookup + update_with_push_keys; rows,
+    versions and counters against the oracle driven with the same calls."""
+    from herald_b200.laia import LaiaScheduler
+    rng = np.random.default_rng(17)
+    W, mini, T, nb, V, D, cap = 3, 24, 6, 6, 300, 8, 40
+    emb = ((rng.zipf(1.15, (W * mini * nb, T)) - 1) % V).astype(np.uint64)
+    s = LaiaScheduler()
+    s.start(emb, emb.shape[0], T, 1, mini, nb, W, 0, cap, 2)
+    h = GpuHarness(oracle_impl, policy, cap, bound, _rows(rng, V, D))
+    try:
+        assert s.step()
+        dist = s.dist_of(0)
+        for b in range(nb):
+            keys = emb[dist.astype(np.int64)].reshape(-1)
+            h.lookup(keys, "batch %d" % b)
+            assert s.step()                                           # plan for batch b + 1
+            grads = rng.normal(0, 1e-3, (keys.size, D)).astype(np.float32)
+            h.update(keys, grads, s.plan_of(0), "batch %d" % b)
+            dist = s.dist_of(0)
+        h.check_state("final")
+        h.check_lines("final")
+    finally:
+        h.close()

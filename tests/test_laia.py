@@ -191,3 +191,41 @@ def test_laia_front_end_pairs_indices_with_the_next_plan():
         assert front.get_input_index(b % front.batch_num) == seq[b][1], b
         assert front.get_comm_plan(b % front.batch_num) == seq[b + 1][0], b
         front.step_forward(0)
+
+
+def test_plans_drive_the_cache_update_of_every_worker():
+    """run_laia's loop on the CPU oracle (one server, one cache per worker): worker w looks up the
+    samples the planner gave it, trains, and updates with the plan of the NEXT batch as `push_keys`
+    (laia_dataloader.py:108-114 -> cstable.py:64-80 -> cache.cc:248-334).  Checks the contract
+    between planner and cache: a plan is ascending unique keys the cache accepts, and the lines it
+    names are exactly the ones pushed (plus dataless lines, which are pushed regardless)."""
+    from oracle import port
+    rng = np.random.default_rng(4)
+    W, mini, T, nb, V, D, cap = 3, 16, 6, 5, 400, 8, 60
+    emb = ((rng.zipf(1.15, (W * mini * nb, T)) - 1) % V).astype(np.uint64)
+    scheds = []
+    for w in range(W):
+        s = LaiaScheduler()
+        s.start(emb, emb.shape[0], T, 1, mini, nb, W, w, cap, 2)
+        scheds.append(s)
+    srv = port.Server(V, D, rng.normal(0, 0.01, (V, D)).astype(np.float32))
+    caches = [port.Cache(srv, "lru", cap, 10) for _ in range(W)]
+    assert all(s.step() for s in scheds)
+    dist = [s.dist_of(w) for w, s in enumerate(scheds)]
+    for b in range(nb):
+        keys = [emb[dist[w].astype(np.int64)].reshape(-1) for w in range(W)]
+        for w in range(W):
+            caches[w].embedding_lookup(keys[w])
+        more = [s.step() for s in scheds]                             # plans for batch b + 1
+        assert all(more)
+        for w in range(W):
+            plan = scheds[w].plan_of(w)
+            assert np.all(np.diff(plan.astype(np.int64)) > 0)         # ascending, unique
+            grads = rng.normal(0, 1e-3, (keys[w].size, D)).astype(np.float32)
+            perf = caches[w].embedding_update(keys[w], grads, plan)
+            touched = np.unique(keys[w])
+            expect = np.intersect1d(touched, plan).size
+            # pushed = planned lines that this batch touched (+ dataless lines of update misses)
+            assert perf["num_transfered"] - perf["num_evict"] >= expect - perf["num_miss"]
+            assert perf["num_transfered"] - perf["num_evict"] <= expect + perf["num_miss"]
+        dist = [s.dist_of(w) for w, s in enumerate(scheds)]
