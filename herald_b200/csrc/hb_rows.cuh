@@ -135,14 +135,15 @@ __global__ void __launch_bounds__(kRowBlock)
 // One persistent kernel does the whole reduce:
 //   * hot phase — a Zipf batch has ids that occur thousands of times and the add ORDER is fixed
 //     by the parity contract, so such a segment cannot be split by rows; it is split by COLUMNS.
-//     A work item is (hot row, 32-float column chunk) — 16-float chunks for the very hot rows.  The CTA streams the chunk of every
-//     occurrence through a kHotStages-deep cp.async ring in shared memory (all 8 warps issue,
-//     128 occurrences x 128 B per stage) while warp 0 adds them in order, one column per lane:
-//     the critical path is the dependent FADD chain itself, not memory latency.  Items are taken
-//     from a ticket, longest rows first; the CTA that finishes the last chunk of a row applies
-//     the row's scalars (f.end).
-//   * cold phase — every warp takes tickets of 32 consecutive uniques and walks them ROWS at a
-//     time: the metadata of all 32 is loaded lane-parallel, then the row / gradient / owner-row
+//     A work item is (hot row, 32-float column chunk) — 16-float chunks for the very hot rows.
+//     The CTA streams the chunk of every occurrence through a cp.async ring in shared memory
+//     (hot_stages() deep; all 8 warps issue, 128 occurrences x 128 B per stage; the occurrence
+//     indices travel through a second ring, copied ahead in the same groups) while warp 0 adds
+//     them in order, one column per lane.  Items are taken from a ticket, longest rows first;
+//     the CTA that finishes the last chunk of a row applies the row's scalars (f.end).
+//   * cold phase — every warp takes tickets of ticket_rows() (16) uniques, strided over the key
+//     range, and walks them ROWS at a time: the metadata of the ticket is loaded lane-parallel
+//     (F::peek + the segment bounds first, then F::begin), then the row / gradient / owner-row
 //     loads of ROWS segments are in flight together (128-bit per lane) before the first add.
 constexpr int kHotTileRows = 128; // occurrences per pipeline stage
 // 3 x 128 x 128 B = 48 KB (+ 6 KB of indices) of dynamic shared memory per CTA, x 2 CTAs/SM.  Measured
