@@ -41,10 +41,8 @@ class MiniLru {
         mask_ = hs - 1;
         table_.assign(hs, kEmpty);
         const size_t nodes = capacity + 2; // one transient node beyond the capacity
-        key_.resize(nodes);
-        prev_.resize(nodes);
-        next_.resize(nodes);
-        valid_.resize(nodes);
+        tagged_ = nodes < 0x00ffffffu;     // (0xff tag | 0xffffff node) would read as kEmpty
+        node_.resize(nodes);
         free_.reserve(nodes);
         for (size_t i = nodes; i-- > 0;)
             free_.push_back((u32)i);
@@ -52,8 +50,23 @@ class MiniLru {
     }
 
     bool check(u64 key) const { // mini_lru_cache.h:55-63
-        const u32 n = find(key);
-        return n != kNil && valid_[n];
+        return check(key, hash(key));
+    }
+    // the same with the key's hash supplied (scoring probes W snapshots with one key)
+    bool check(u64 key, size_t hashed) const {
+        const u32 n = find(key, hashed);
+        return n != kNil && node_[n].valid;
+    }
+    static size_t hash_of(u64 key) {
+        return hash(key);
+    }
+    void prefetch_entry_h(size_t hashed) const {
+        __builtin_prefetch(&table_[hashed & mask_]);
+    }
+    void prefetch_node_h(size_t hashed) const {
+        const u32 e = table_[hashed & mask_];
+        if (e != kEmpty && (!tagged_ || (e & 0xff000000u) == tag_of(hashed)))
+            __builtin_prefetch(&node_[node_of(e)]);
     }
 
     // -1 hit, -2 stale hit, 0 miss, 1 miss that evicted a valid line (mini_lru_cache.h:69-105)
@@ -61,26 +74,26 @@ class MiniLru {
         const u32 n = find(key);
         if (n == kNil)
             return insert(key);
-        const int res = valid_[n] ? -1 : -2;
+        const int res = node_[n].valid ? -1 : -2;
         unlink(n);
         push_front(n);
-        valid_[n] = 1;
+        node_[n].valid = 1;
         return res;
     }
 
     int insert(u64 key) { // key must be absent
         const u32 n = free_.back();
         free_.pop_back();
-        key_[n] = key;
-        valid_[n] = 1;
+        node_[n].key = key;
+        node_[n].valid = 1;
         push_front(n);
         index_insert(key, n);
         size_++;
         if (size_ > cap_) {
             const u32 v = tail_;
-            const int res = valid_[v] ? 1 : 0;
+            const int res = node_[v].valid ? 1 : 0;
             unlink(v);
-            index_erase(key_[v]);
+            index_erase(node_[v].key);
             free_.push_back(v);
             size_--;
             return res;
@@ -91,7 +104,7 @@ class MiniLru {
     void outdate(u64 key) { // mini_lru_cache.h:118-125
         const u32 n = find(key);
         if (n != kNil)
-            valid_[n] = 0;
+            node_[n].valid = 0;
     }
 
     void evict(u64 key) { // mini_lru_cache.h:107-116
@@ -104,84 +117,209 @@ class MiniLru {
         size_--;
     }
 
-
     void valid_keys(std::vector<u64> &out) const { // get_keys(): valid keys, ascending
         out.clear();
-        for (u32 n = head_; n != kNil; n = next_[n])
-            if (valid_[n])
-                out.push_back(key_[n]);
+        for (u32 n = head_; n != kNil; n = node_[n].next)
+            if (node_[n].valid)
+                out.push_back(node_[n].key);
         std::sort(out.begin(), out.end());
+    }
+
+    // A snapshot of a 3.4 M-line cache does not fit any CPU cache and every operation is a chain
+    // of dependent misses (index entry -> node -> list neighbours).  The planner knows the keys it
+    // is about to touch, so it runs these three a few keys ahead of the operation itself:
+    void prefetch_entry(u64 key) const { // the index entry of the key's home position
+        __builtin_prefetch(&table_[hash(key) & mask_]);
+    }
+    void prefetch_node(u64 key) const { // needs the index entry: the node it points to
+        prefetch_node_h(hash(key));
+    }
+    void prefetch_links(u64 key) const { // needs the node: its neighbours in the recency list
+        const size_t hashed = hash(key);
+        const u32 e = table_[hashed & mask_];
+        if (e == kEmpty || (tagged_ && (e & 0xff000000u) != tag_of(hashed)))
+            return;
+        const u32 n = node_of(e);
+        const u32 p = node_[n].prev, x = node_[n].next;
+        if (p != kNil)
+            __builtin_prefetch(&node_[p]);
+        if (x != kNil)
+            __builtin_prefetch(&node_[x]);
     }
 
   private:
     static constexpr u32 kNil = 0xffffffffu, kEmpty = 0xffffffffu;
+    struct Node { // one cache line touch per node
+        u64 key;
+        u32 prev, next;
+        u32 valid;
+        u32 pad;
+    };
     static size_t hash(u64 k) {
         k ^= k >> 33;
         k *= 0xff51afd7ed558ccdull;
         k ^= k >> 33;
         return (size_t)k;
     }
+    // An index entry is (tag << 24 | node): 8 bits of the key's hash next to the node number, so a
+    // probe that lands on another key's entry is rejected without touching that key's node (a
+    // cache miss in a 3.4 M-line snapshot).  Needs node numbers below 2^24 - 1; larger snapshots
+    // use untagged entries (tag_shift_ = 32: tag and node mask degenerate).
+    u32 tag_of(size_t hashed) const {
+        return tagged_ ? (u32)((hashed >> 40) & 0xffu) << 24 : 0u;
+    }
+    u32 node_of(u32 entry) const {
+        return tagged_ ? (entry & 0x00ffffffu) : entry;
+    }
     u32 find(u64 key) const {
-        for (size_t h = hash(key) & mask_;; h = (h + 1) & mask_) {
-            const u32 n = table_[h];
-            if (n == kEmpty)
+        return find(key, hash(key));
+    }
+    u32 find(u64 key, size_t hashed) const {
+        const u32 tag = tag_of(hashed);
+        for (size_t h = hashed & mask_;; h = (h + 1) & mask_) {
+            const u32 e = table_[h];
+            if (e == kEmpty)
                 return kNil;
-            if (key_[n] == key)
+            if (tagged_ && (e & 0xff000000u) != tag)
+                continue;
+            const u32 n = node_of(e);
+            if (node_[n].key == key)
                 return n;
         }
     }
     void index_insert(u64 key, u32 n) {
-        size_t h = hash(key) & mask_;
+        const size_t hashed = hash(key);
+        size_t h = hashed & mask_;
         while (table_[h] != kEmpty)
             h = (h + 1) & mask_;
-        table_[h] = n;
+        table_[h] = tag_of(hashed) | n;
     }
     void index_erase(u64 key) { // linear probing with backward shift: no tombstones
         size_t h = hash(key) & mask_;
-        while (key_[table_[h]] != key)
+        while (node_[node_of(table_[h])].key != key)
             h = (h + 1) & mask_;
         size_t hole = h;
         for (size_t j = (h + 1) & mask_;; j = (j + 1) & mask_) {
-            const u32 n = table_[j];
-            if (n == kEmpty)
+            const u32 e = table_[j];
+            if (e == kEmpty)
                 break;
-            const size_t home = hash(key_[n]) & mask_;
-            // n may move into the hole if its home is not in the (cyclic) interval (hole, j]
+            const size_t home = hash(node_[node_of(e)].key) & mask_;
+            // e may move into the hole if its home is not in the (cyclic) interval (hole, j]
             const bool between = hole <= j ? (home > hole && home <= j) : (home > hole || home <= j);
             if (!between) {
-                table_[hole] = n;
+                table_[hole] = e;
                 hole = j;
             }
         }
         table_[hole] = kEmpty;
     }
     void unlink(u32 n) {
-        const u32 p = prev_[n], x = next_[n];
+        const u32 p = node_[n].prev, x = node_[n].next;
         if (p != kNil)
-            next_[p] = x;
+            node_[p].next = x;
         else
             head_ = x;
         if (x != kNil)
-            prev_[x] = p;
+            node_[x].prev = p;
         else
             tail_ = p;
     }
     void push_front(u32 n) {
-        prev_[n] = kNil;
-        next_[n] = head_;
+        node_[n].prev = kNil;
+        node_[n].next = head_;
         if (head_ != kNil)
-            prev_[head_] = n;
+            node_[head_].prev = n;
         head_ = n;
         if (tail_ == kNil)
             tail_ = n;
     }
 
     size_t cap_, mask_ = 0, size_ = 0;
-    std::vector<u32> table_, prev_, next_, free_;
-    std::vector<u64> key_;
-    std::vector<u8> valid_;
+    bool tagged_ = false;
+    std::vector<u32> table_, free_;
+    std::vector<Node> node_;
     u32 head_, tail_;
 };
+
+// v := ascending unique values of v.  LSD radix sort, 11-bit digits over the significant bits
+// (embedding ids: 3 passes for a 33.7 M-row table), then one scan — the plan lists hold every
+// occurrence of every shared row (~0.5 M entries, mostly repeats of hot rows) and a comparison sort
+// of them was 40 % of the planner.
+void radix_sort_unique(std::vector<u64> &v, std::vector<u64> &tmp) {
+    const size_t n = v.size();
+    if (n < 2)
+        return;
+    if (n < 2048) {
+        std::sort(v.begin(), v.end());
+        v.erase(std::unique(v.begin(), v.end()), v.end());
+        return;
+    }
+    u64 all = 0;
+    for (u64 x : v)
+        all |= x;
+    int bits = 0;
+    while (bits < 64 && (all >> bits) != 0)
+        bits++;
+    constexpr int RB = 11;
+    constexpr size_t R = (size_t)1 << RB;
+    tmp.resize(n);
+    u64 *src = v.data(), *dst = tmp.data();
+    size_t count[R];
+    for (int shift = 0; shift < bits; shift += RB) {
+        std::memset(count, 0, sizeof(count));
+        for (size_t i = 0; i < n; i++)
+            count[(src[i] >> shift) & (R - 1)]++;
+        size_t run = 0;
+        for (size_t d = 0; d < R; d++) {
+            const size_t c = count[d];
+            count[d] = run;
+            run += c;
+        }
+        for (size_t i = 0; i < n; i++)
+            dst[count[(src[i] >> shift) & (R - 1)]++] = src[i];
+        std::swap(src, dst);
+    }
+    if (src != v.data())
+        std::memcpy(v.data(), src, n * sizeof(u64));
+    v.erase(std::unique(v.begin(), v.end()), v.end());
+}
+
+// out := the ids whose bit is set, ascending; the bitmap is all zero again afterwards
+void drain_bitmap(std::vector<u64> &bm, std::vector<u64> &out) {
+    out.clear();
+    for (size_t wi = 0; wi < bm.size(); wi++) {
+        u64 w = bm[wi];
+        if (!w)
+            continue;
+        bm[wi] = 0;
+        while (w) {
+            out.push_back(((u64)wi << 6) | (u64)__builtin_ctzll(w));
+            w &= w - 1;
+        }
+    }
+}
+
+// f(i) for i in [0, n) with the three prefetch stages of `lru` running 24 / 16 / 8 keys ahead
+template <class F>
+void for_keys_prefetched(const MiniLru &lru, const std::vector<u64> &keys, F f) {
+    constexpr size_t kA = 24, kB = 16, kC = 8;
+    const size_t n = keys.size();
+    for (size_t i = 0; i < std::min(n, kA); i++)
+        lru.prefetch_entry(keys[i]);
+    for (size_t i = 0; i < std::min(n, kB); i++)
+        lru.prefetch_node(keys[i]);
+    for (size_t i = 0; i < std::min(n, kC); i++)
+        lru.prefetch_links(keys[i]);
+    for (size_t i = 0; i < n; i++) {
+        if (i + kA < n)
+            lru.prefetch_entry(keys[i + kA]);
+        if (i + kB < n)
+            lru.prefetch_node(keys[i + kB]);
+        if (i + kC < n)
+            lru.prefetch_links(keys[i + kC]);
+        f(keys[i]);
+    }
+}
 
 // run f(t) for t in [0, n) on up to `threads` std::threads (the calling thread takes part)
 template <class F>
@@ -210,6 +348,8 @@ void parallel_for(size_t n, size_t threads, F f) {
 
 using namespace hb;
 
+constexpr u64 kBitmapIds = 1ull << 31; // 256 MB of bits per worker at most; larger ids take the radix sort
+
 struct hb_laia {
     std::vector<u64> embs; // [num_sample][num_table]
     size_t num_sample = 0, num_table = 0, mini = 0, W = 0, rank = 0, batch_size = 0;
@@ -224,6 +364,9 @@ struct hb_laia {
     std::vector<u32> assigned;           // [batch] worker of each sample
     std::vector<u64> holders;            // [batch][T] bit z: the embedding is valid in worker z's snapshot
                                          // (W <= 64; the reference's sample_emb_dep_, as a bit set)
+    u64 max_key = 0;                     // largest embedding id of the sample set
+    std::vector<std::vector<u64>> seen;  // per worker: one bit per id (ids below kBitmapIds), all zero
+                                         // between uses — ascending unique keys without a sort
 };
 
 namespace {
@@ -260,20 +403,66 @@ void laia_plan_batch(hb_laia *s) {
     const size_t chunks = std::min<size_t>(B, s->threads * 4);
     parallel_for(chunks, s->threads, [&](size_t c) {
         const size_t lo = B * c / chunks, hi = B * (c + 1) / chunks;
+        // the index entries of sample i + 2 and the nodes of sample i + 1 are prefetched while
+        // sample i is scored: W x T dependent-miss chains per sample otherwise
+        constexpr size_t kMemo = 4096;
+        struct Memo {
+            u64 key, bits;
+        };
+        std::vector<Memo> memo;
+        if (use_bits)
+            memo.assign(kMemo, Memo{~0ull, 0});
+        auto prefetch = [&](size_t i, bool nodes) {
+            const u64 *e = &s->embs[pos_of(i) * T];
+            for (size_t j = 0; j < T; j++) {
+                const size_t hk = MiniLru::hash_of(e[j]);
+                if (use_bits && memo[hk & (kMemo - 1)].key == e[j])
+                    continue; // a repeat: answered from the memo
+                for (size_t z = 0; z < W; z++) {
+                    if (nodes)
+                        s->snaps[z].prefetch_node_h(hk);
+                    else
+                        s->snaps[z].prefetch_entry_h(hk);
+                }
+            }
+        };
+        // (Zipf ids repeat: the small direct-mapped memo id -> holder bits declared above answers the
+        // repeats of this chunk without probing W snapshots again; they do not change during scoring)
+        if (lo < hi)
+            prefetch(lo, false);
+        if (lo + 1 < hi)
+            prefetch(lo + 1, false);
+        if (lo < hi)
+            prefetch(lo, true);
         for (size_t i = lo; i < hi; i++) {
+            if (i + 2 < hi)
+                prefetch(i + 2, false);
+            if (i + 1 < hi)
+                prefetch(i + 1, true);
             const u64 *e = &s->embs[pos_of(i) * T];
             u32 *sc = &s->scores[i * W];
             for (size_t z = 0; z < W; z++)
                 sc[z] = 0;
             for (size_t j = 0; j < T; j++) {
-                u64 bits = 0;
-                for (size_t z = 0; z < W; z++)
-                    if (s->snaps[z].check(e[j])) {
-                        sc[z]++;
-                        bits |= 1ull << (z & 63);
+                const size_t hk = MiniLru::hash_of(e[j]);
+                if (use_bits) {
+                    Memo &m = memo[hk & (kMemo - 1)];
+                    if (m.key != e[j]) {
+                        u64 bits = 0;
+                        for (size_t z = 0; z < W; z++)
+                            if (s->snaps[z].check(e[j], hk))
+                                bits |= 1ull << z;
+                        m.key = e[j];
+                        m.bits = bits;
                     }
-                if (use_bits)
-                    s->holders[i * T + j] = bits;
+                    s->holders[i * T + j] = m.bits;
+                    for (u64 b = m.bits; b; b &= b - 1)
+                        sc[__builtin_ctzll(b)]++;
+                } else {
+                    for (size_t z = 0; z < W; z++)
+                        if (s->snaps[z].check(e[j], hk))
+                            sc[z]++;
+                }
             }
         }
     });
@@ -297,10 +486,21 @@ void laia_plan_batch(hb_laia *s) {
     }
     const double t2 = timing ? now_ms() : 0;
     // communication plan + snapshot update, one worker per thread
+    double sub[5] = {0, 0, 0, 0, 0}; // worker 0's share of the phase (timing only)
     parallel_for(W, s->threads, [&](size_t w) {
+        const bool tw = timing && w == 0;
+        double c0 = tw ? now_ms() : 0;
         std::vector<u64> &plan = s->plans[w];
         plan.clear();
         MiniLru &snap = s->snaps[w];
+        std::vector<u64> &bm = s->seen[w];
+        const bool bitmap = !bm.empty();
+        auto add = [&](u64 k) {
+            if (bitmap)
+                bm[k >> 6] |= 1ull << (k & 63);
+            else
+                plan.push_back(k);
+        };
         for (size_t i = 0; i < B; i++) {
             if (s->assigned[i] == w)
                 continue;
@@ -309,31 +509,45 @@ void laia_plan_batch(hb_laia *s) {
                 const u64 *h = &s->holders[i * T];
                 for (size_t j = 0; j < T; j++)
                     if ((h[j] >> w) & 1ull)
-                        plan.push_back(e[j]);
+                        add(e[j]);
             } else {
                 for (size_t j = 0; j < T; j++)
                     if (snap.check(e[j]))
-                        plan.push_back(e[j]);
+                        add(e[j]);
             }
         }
-        std::sort(plan.begin(), plan.end());
-        plan.erase(std::unique(plan.begin(), plan.end()), plan.end());
-        for (u64 k : plan)
-            snap.outdate(k);
+        if (tw) { sub[0] = now_ms() - c0; c0 = now_ms(); }
+        std::vector<u64> scratch;
+        if (bitmap)
+            drain_bitmap(bm, plan);
+        else
+            radix_sort_unique(plan, scratch);
+        if (tw) { sub[1] = now_ms() - c0; c0 = now_ms(); }
+        for_keys_prefetched(snap, plan, [&](u64 k) { snap.outdate(k); });
+        if (tw) { sub[2] = now_ms() - c0; c0 = now_ms(); }
         std::vector<u64> uniq;
         uniq.reserve(s->mini * T);
         for (size_t j = 0; j < s->mini; j++) {
             const u64 *e = &s->embs[s->dist[w * s->mini + j] * T];
-            uniq.insert(uniq.end(), e, e + T);
+            if (bitmap)
+                for (size_t t = 0; t < T; t++)
+                    bm[e[t] >> 6] |= 1ull << (e[t] & 63);
+            else
+                uniq.insert(uniq.end(), e, e + T);
         }
-        std::sort(uniq.begin(), uniq.end());
-        uniq.erase(std::unique(uniq.begin(), uniq.end()), uniq.end());
-        for (u64 k : uniq)
-            snap.get(k);
+        if (bitmap)
+            drain_bitmap(bm, uniq);
+        else
+            radix_sort_unique(uniq, scratch);
+        if (tw) { sub[3] = now_ms() - c0; c0 = now_ms(); }
+        for_keys_prefetched(snap, uniq, [&](u64 k) { snap.get(k); });
+        if (tw) sub[4] = now_ms() - c0;
     });
     if (timing)
-        fprintf(stderr, "laia batch %zu: score %.2f ms, assign %.2f ms, plan + snapshots %.2f ms\n", s->batch_id,
-                t1 - t0, t2 - t1, now_ms() - t2);
+        fprintf(stderr,
+                "laia batch %zu: score %.2f ms, assign %.2f ms, plan + snapshots %.2f ms (worker 0: collect %.2f, "
+                "sort %.2f, outdate %.2f, own keys %.2f, touch %.2f)\n",
+                s->batch_id, t1 - t0, t2 - t1, now_ms() - t2, sub[0], sub[1], sub[2], sub[3], sub[4]);
     s->batch_id++;
 }
 
@@ -370,6 +584,12 @@ int hb_laia_create(hb_laia **out, const uint64_t *sample_embs, size_t num_sample
     s->assigned.assign(s->batch_size, 0);
     if (nrank <= 64)
         s->holders.assign(s->batch_size * num_table, 0);
+    for (u64 k : s->embs)
+        s->max_key = std::max(s->max_key, k);
+    s->seen.resize(nrank);
+    if (s->max_key < kBitmapIds)
+        for (auto &bm : s->seen)
+            bm.assign((size_t)(s->max_key >> 6) + 1, 0);
     *out = s;
     HB_API_END();
 }
