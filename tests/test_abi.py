@@ -88,3 +88,43 @@ def test_missing_library_is_an_import_error(tmp_path, monkeypatch):
     mod = importlib.util.module_from_spec(spec)
     with pytest.raises(ImportError):
         spec.loader.exec_module(mod)
+
+
+def test_every_kernel_waits_for_its_predecessor():
+    """Programmatic dependent launch discipline: every kernel of the library is
+    launched through HB_LAUNCH (programmatic stream serialization) and must start with
+    pdl_enter() — griddepcontrol.wait before any memory access.  A kernel without it would run
+    ahead of the kernel it depends on."""
+    csrc = os.path.join(ROOT, "herald_b200", "csrc")
+    kernels = 0
+    for name in sorted(os.listdir(csrc)):
+        if not name.endswith((".cu", ".cuh")):
+            continue
+        text = open(os.path.join(csrc, name)).read()
+        code = re.sub(r"//[^\n]*", "", text)
+        assert "<<<" not in code, "%s launches a kernel without HB_LAUNCH" % name
+        for m in re.finditer(r"__global__", code):
+            # the kernel's parameter list, then its body
+            i = m.end()
+            while True:
+                j = code.index("(", i)
+                ident = re.search(r"([A-Za-z_]\w*)\s*$", code[i:j])
+                depth, k = 0, j
+                while True:
+                    depth += code[k] == "("
+                    depth -= code[k] == ")"
+                    k += 1
+                    if depth == 0:
+                        break
+                if ident and ident.group(1) == "__launch_bounds__":
+                    i = k
+                    continue
+                break
+            rest = code[k:].lstrip()
+            if not rest.startswith("{"):
+                continue                                   # a declaration
+            body = rest[1:].lstrip()
+            assert body.startswith("pdl_enter();"), "%s: kernel %s does not start with pdl_enter()" % (
+                name, ident.group(1) if ident else "?")
+            kernels += 1
+    assert kernels >= 40
