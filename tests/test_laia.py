@@ -229,3 +229,21 @@ def test_plans_drive_the_cache_update_of_every_worker():
             assert perf["num_transfered"] - perf["num_evict"] >= expect - perf["num_miss"]
             assert perf["num_transfered"] - perf["num_evict"] <= expect + perf["num_miss"]
         dist = [s.dist_of(w) for w, s in enumerate(scheds)]
+
+
+@pytest.mark.parametrize("W,offset,n_keys,mini", [(3, 1 << 33, 5000, 900), (65, 0, 90, 40),
+                                                   (66, 1 << 40, 3000, 40)])
+def test_planner_paths_without_bitmap_or_holder_bits(W, offset, n_keys, mini):
+    """Ids above 2^31 take the radix sort instead of the id bitmap, more than 64 workers probe the
+    snapshots again instead of reading holder bits: same plans as the port."""
+    rng = np.random.default_rng(W)
+    T, nb, cap = 5, 3, 2500 if mini > 100 else 700        # the 900-sample case builds plans of > 2048 entries
+    emb = (((rng.zipf(1.2, (W * mini * nb, T)) - 1) % n_keys) + offset).astype(np.uint64)
+    p = dict(W=W, mini=mini, T=T, nb=nb, cap=cap, ep=1, emb=emb)
+    got, scheds = run_ours(p, threads=4)
+    planner = laia_port.LaiaPlanner(emb, mini, W, cap, 1, nb)
+    for b, (plans, dist) in enumerate(got):
+        eplans, edist = planner.next_all()
+        assert plans == eplans and dist == edist, "batch %d" % b
+    assert planner.next_all() is None
+    assert scheds[0].snapshot_keys(W - 1).tolist() == planner.snaps[W - 1].get_keys()
