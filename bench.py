@@ -294,7 +294,9 @@ def seg_trace(path, run_step):
     a = np.frombuffer(buf, dtype=np.uint64).astype(np.int64)
     grid, nitems = int(a[0]), int(a[1])
     cta = a[2:2 + 4 * 2048].reshape(2048, 4)[:grid]
-    items = a[2 + 4 * 2048:].reshape(1024, 3)[:min(nitems, 1024)]
+    items = a[2 + 4 * 2048:].reshape(1024, 3)[:min(nitems, 1024)].copy()
+    waited = (items[:, 2] >> 32) * 16          # adder cycles spent waiting for the ring
+    items[:, 2] &= 0xffffffff
     t0 = int(cta[:, 0].min())
     out = {"grid": grid, "hot_items": nitems,
            "kernel_span_us": (int(cta[:, 2].max()) - t0) / 1e3,
@@ -304,6 +306,7 @@ def seg_trace(path, run_step):
            "cta_items": np.percentile(cta[:, 3], [0, 50, 100]).tolist(),
            "items": [[(int(x[0]) - t0) / 1e3, (int(x[1]) - t0) / 1e3, int(x[2])] for x in items[:64]],
            "item_ns_per_occurrence": [float((x[1] - x[0]) / max(1, x[2])) for x in items[:64]],
+           "item_wait_cycles_per_occurrence": [float(w / max(1, x[2])) for w, x in zip(waited[:64], items[:64])],
            "last_item_end_us": (int(items[:, 1].max()) - t0) / 1e3 if len(items) else 0.0}
     with open(path, "w") as f:
         json.dump(out, f)

@@ -1026,15 +1026,15 @@ struct AccumulatePush {
     struct Acc {
         typename V::T d, g, t; // cache row, pending gradient, owner row (read ahead for the push)
     };
-    struct Ctx { // everything end() needs is read by begin(): end() only stores
-        u64 trow;
-        i64 version, tver;
+    // what the data phase needs of a line (16 bytes, travels in the work item)
+    enum : u8 { X_GRAD = 1, X_DATALESS = 2, X_PUSHED = 4, X_LOCAL = 8 };
+    struct Ctx {
         i32 s;
-        i32 upd0, upd;
+        u32 trow; // row inside the owner's shard (a shard holds < 2^32 rows)
         u32 mpos; // multi-GPU: slot in the owner's mailbox (batch section)
-        u8 flags, owner;
-        bool dataless, pushed, local;
-        u8 pad[3];
+        u8 bits;  // X_GRAD: the line holds a pending gradient to continue from
+        u8 owner;
+        u8 pad[2];
     };
     CacheView c;
     const u64 *uniq;
@@ -1074,30 +1074,24 @@ struct AccumulatePush {
     __device__ MailboxSection outbox(int owner) const {
         return mailbox_section(c.pv.out[owner], 0, c.pv.cap, c.width);
     }
-    // the two loads every row starts with, issued by the cold phase together with the segment
-    // bounds (one dependent-load level less per ticket)
-    struct Pre {
-        i32 s;
-        u64 key;
-    };
-    __device__ Pre peek(size_t u) const {
-        return Pre{uslot[u], uniq[u]};
-    }
-    __device__ bool begin(size_t u, u32 cnt, Ctx &x) const {
-        return begin(peek(u), u, cnt, x);
-    }
-    __device__ bool begin(const Pre &pre, size_t u, u32 cnt, Ctx &x) const {
-        x.s = pre.s;
-        const u64 key = pre.key;
+    // One thread per unique key (plan kernel): the push decision and every per-line / per-row
+    // scalar of the call — update count, version, owner version, mailbox header — are settled
+    // here; the data kernel only moves rows.
+    __device__ bool open(size_t u, u32 cnt, Ctx &x) const {
+        x.s = uslot[u];
+        const u64 key = uniq[u];
         x.owner = 0;
         x.mpos = 0;
+        x.bits = 0;
+        x.pad[0] = x.pad[1] = 0;
+        u64 trow = 0;
+        bool local = false;
         if (c.pv.world > 1) { // every line goes through the owner's mailbox, the local ones too:
                               // the owner applies all sources in rank order
             if (key >= c.table_len)
                 return false;
-            x.owner = (u8)owner_of(c.pv, key, x.trow);
+            x.owner = (u8)owner_of(c.pv, key, trow);
             x.mpos = (u32)u - c.pv.lo[x.owner];
-            x.local = false;
             if (x.mpos >= c.pv.cap) {
                 atomicMax(&c.regs->error, (u32)E_MAILBOX);
                 return false;
@@ -1109,29 +1103,55 @@ struct AccumulatePush {
         } else {
             if (x.s < 0)
                 return false;
-            x.trow = key - c.row_begin;
-            x.local = x.trow < c.nrows_local;
+            trow = key - c.row_begin;
+            local = trow < c.nrows_local;
         }
-        // owner version read ahead of the push decision (same load level as the line's scalars)
-        const i64 tv = x.local ? c.tver[x.trow] : 0;
-        x.upd0 = c.slot_updates[x.s];
-        x.flags = c.slot_flags[x.s];
-        x.version = c.slot_version[x.s];
-        x.upd = x.upd0 + (i32)cnt;
-        x.dataless = x.flags & F_DATALESS;
+        x.trow = (u32)trow;
+        const i32 upd0 = c.slot_updates[x.s];
+        const u8 flags = c.slot_flags[x.s];
+        const i64 version = c.slot_version[x.s];
+        const i32 upd = upd0 + (i32)cnt;
+        const bool dataless = flags & F_DATALESS;
+        bool pushed;
         if (push_keys)
-            x.pushed = !x.dataless && in_plan(key); // cache.cc:296
+            pushed = !dataless && in_plan(key); // cache.cc:296
         else
-            x.pushed = (i64)x.upd > push_bound || x.dataless; // cache.cc:157
-        x.tver = tv;
+            pushed = (i64)upd > push_bound || dataless; // cache.cc:157
+        x.bits = (upd0 != 0 ? X_GRAD : 0) | (dataless ? X_DATALESS : 0) | (pushed ? X_PUSHED : 0) |
+                 (local ? X_LOCAL : 0);
+        if (!(flags & F_GRAD))
+            c.slot_flags[x.s] = flags | F_GRAD;
+        if (c.pv.world > 1) {
+            const MailboxSection m = outbox(x.owner);
+            m.key[x.mpos] = trow;
+            m.upd[x.mpos] = pushed ? upd : 0; // 0 = slot not pushed this call
+        }
+        if (pushed) {
+            if (local)
+                c.tver[trow] += upd; // PSFhandle_embedding.cc:24
+            atomicAdd(block_counter(), 1u);
+        }
+        if (defer_cleanup) {
+            c.slot_updates[x.s] = upd;
+        } else if (push_keys) { // cache.cc:308-314: every touched line, every call
+            c.slot_version[x.s] = version + upd;
+            c.slot_updates[x.s] = pushed ? 0 : upd;
+        } else if (pushed && !dataless) { // cache.cc:171-177
+            c.slot_version[x.s] = version + upd;
+            c.slot_updates[x.s] = 0;
+        } else {
+            c.slot_updates[x.s] = upd;
+        }
         return true;
     }
     __device__ Acc load(const Ctx &x, size_t k) const {
         Acc a;
         const size_t o = (size_t)x.s * c.width + k * VEC;
-        a.d = x.dataless ? V::zero() : V::ld_rmw(c.data + o);
-        a.g = x.upd0 != 0 ? V::ld_rmw(c.grad + o) : V::zero();
-        a.t = (x.pushed && x.local) ? V::ld_rmw(c.trows + x.trow * c.width + k * VEC) : V::zero();
+        a.d = (x.bits & X_DATALESS) ? V::zero() : V::ld_rmw(c.data + o);
+        a.g = (x.bits & X_GRAD) ? V::ld_rmw(c.grad + o) : V::zero();
+        a.t = (x.bits & (X_PUSHED | X_LOCAL)) == (X_PUSHED | X_LOCAL)
+                  ? V::ld_rmw(c.trows + (size_t)x.trow * c.width + k * VEC)
+                  : V::zero();
         return a;
     }
     __device__ Acc step(const Acc &a, const typename V::T &g) const {
@@ -1143,41 +1163,15 @@ struct AccumulatePush {
     }
     __device__ void store(const Ctx &x, size_t k, const Acc &a) const {
         const size_t o = (size_t)x.s * c.width + k * VEC;
-        if (!x.dataless)
+        const bool dataless = x.bits & X_DATALESS, pushed = x.bits & X_PUSHED;
+        if (!dataless)
             V::st(c.data + o, a.d);
-        if (x.pushed && x.local) // PSFhandle_embedding.cc:25-26: row += pushed grad
-            V::st(c.trows + x.trow * c.width + k * VEC, V::add(a.t, a.g));
-        else if (x.pushed && c.pv.world > 1) // deposit the pushed gradient at the owner (NVLink store)
+        if (pushed && (x.bits & X_LOCAL)) // PSFhandle_embedding.cc:25-26: row += pushed grad
+            V::st(c.trows + (size_t)x.trow * c.width + k * VEC, V::add(a.t, a.g));
+        else if (pushed && c.pv.world > 1) // deposit the pushed gradient at the owner (NVLink store)
             V::st(outbox(x.owner).grad + (size_t)x.mpos * c.width + k * VEC, a.g);
-        if (!x.pushed || (defer_cleanup && !x.dataless))
+        if (!pushed || (defer_cleanup && !dataless))
             V::st(c.grad + o, a.g);
-    }
-    __device__ void end(const Ctx &x) const { // one thread per row
-        if (!(x.flags & F_GRAD))
-            c.slot_flags[x.s] = x.flags | F_GRAD;
-        if (c.pv.world > 1) {
-            const MailboxSection m = outbox(x.owner);
-            m.key[x.mpos] = x.trow;
-            m.upd[x.mpos] = x.pushed ? x.upd : 0; // 0 = slot not pushed this call
-        }
-        if (x.pushed) {
-            if (x.local)
-                c.tver[x.trow] = x.tver + x.upd; // PSFhandle_embedding.cc:24
-            atomicAdd(block_counter(), 1u);
-        }
-        if (defer_cleanup) {
-            c.slot_updates[x.s] = x.upd;
-            return;
-        }
-        if (push_keys) { // cache.cc:308-314: every touched line, every call
-            c.slot_version[x.s] = x.version + x.upd;
-            c.slot_updates[x.s] = x.pushed ? 0 : x.upd;
-        } else if (x.pushed && !x.dataless) { // cache.cc:171-177
-            c.slot_version[x.s] = x.version + x.upd;
-            c.slot_updates[x.s] = 0;
-        } else {
-            c.slot_updates[x.s] = x.upd;
-        }
     }
 };
 
@@ -2090,6 +2084,7 @@ int hb_table_create(int node_id, size_t length, size_t width, int device, hb_tab
     size_t per = length / world, rem = length % world;
     t->row_begin = (size_t)rank * per + std::min<size_t>(rank, rem);
     t->nrows = per + ((size_t)rank < rem ? 1 : 0);
+    HB_CHECK(t->nrows < (1ull << 32), "a shard holds fewer than 2^32 rows");
     dmalloc_shared(t->rows, t->nrows * width);
     dmalloc_shared(t->ver, t->nrows);
     HB_CUDA(cudaMemset(t->rows, 0, std::max<size_t>(t->nrows * width, 1) * sizeof(float)));

@@ -69,8 +69,7 @@ struct AddIntoRows {
     using Ctx = size_t; // destination row
     __device__ void kernel_begin() const {}
     __device__ void kernel_end() const {}
-    __device__ void end(const Ctx &) const {}
-    __device__ bool begin(size_t u, u32, Ctx &row) const {
+    __device__ bool open(size_t u, u32, Ctx &row) const {
         row = (size_t)uniq[u];
         return true;
     }
@@ -102,8 +101,7 @@ struct AddIntoTwoRows {
     using Ctx = size_t;
     __device__ void kernel_begin() const {}
     __device__ void kernel_end() const {}
-    __device__ void end(const Ctx &) const {}
-    __device__ bool begin(size_t u, u32, Ctx &row) const {
+    __device__ bool open(size_t u, u32, Ctx &row) const {
         row = (size_t)uniq[u];
         return true;
     }
@@ -185,8 +183,7 @@ struct AdamSegments {
     using Ctx = size_t;
     __device__ void kernel_begin() const {}
     __device__ void kernel_end() const {}
-    __device__ void end(const Ctx &) const {}
-    __device__ bool begin(size_t u, u32, Ctx &row) const {
+    __device__ bool open(size_t u, u32, Ctx &row) const {
         row = (size_t)uniq[u];
         return true;
     }

@@ -121,50 +121,61 @@ __global__ void __launch_bounds__(kRowBlock)
 }
 
 // ---- segment reduce by unique key, applied to a destination row -----------------------
-// For unique u:  F::Ctx ctx; if (!f.begin(u, cnt, ctx)) skip;
-//   per column chunk c:  acc = f.load(ctx, c);
+// Functor contract (instantiated for the cold path's vector width VEC and, as F1, for VEC = 1):
+//   bool open(u, cnt, Ctx &)   ONCE per unique key, by one thread of the plan kernel: reads (and
+//                              may write) the row's scalars and leaves in Ctx (<= 16 B, trivially
+//                              copyable) everything the data phase needs
+//   per column chunk c:  acc = load(ctx, c);
 //                        for each occurrence p in ascending original index:
-//                            acc = f.step(acc, vals[perm[p], c]);
-//                        f.store(ctx, c, acc);
-//   f.end(ctx)   (ONE thread per row: writes the per-row scalars from values begin() read)
-// begin() and end() contain no warp-collective operation: the cold phase calls them with a
-// different row in every lane.
+//                            acc = step(acc, vals[perm[p], c]);
+//                        store(ctx, c, acc);
+//   kernel_begin() / kernel_end()   block-level hooks of the plan kernel (counters)
 // The adds happen in occurrence order, so the result is deterministic and bit-identical to a
 // serial CPU loop over the batch (Line::accumulate order, src/hetu_cache/include/embedding.h:78-91).
 //
-// One persistent kernel does the whole reduce:
-//   * hot phase — a Zipf batch has ids that occur thousands of times and the add ORDER is fixed
-//     by the parity contract, so such a segment cannot be split by rows; it is split by COLUMNS.
-//     A work item is (hot row, 32-float column chunk) — 16-float chunks for the very hot rows.
-//     The CTA streams the chunk of every occurrence through a cp.async ring in shared memory
-//     (hot_stages() deep; all 8 warps issue, 128 occurrences x 128 B per stage; the occurrence
-//     indices travel through a second ring, copied ahead in the same groups) while warp 0 adds
-//     them in order, one column per lane.  Items are taken from a ticket, longest rows first;
-//     the CTA that finishes the last chunk of a row applies the row's scalars (f.end).
-//   * cold phase — every warp takes tickets of ticket_rows() (16) uniques, strided over the key
-//     range, and walks them ROWS at a time: the metadata of the ticket is loaded lane-parallel
-//     (F::peek + the segment bounds first, then F::begin), then the row / gradient / owner-row
-//     loads of ROWS segments are in flight together (128-bit per lane) before the first add.
-constexpr int kHotTileRows = 128; // occurrences per pipeline stage
-// 3 x 128 x 128 B = 48 KB (+ 6 KB of indices) of dynamic shared memory per CTA, x 2 CTAs/SM.  Measured
-// on B200 (profiles/r01_segtrace_*.json): the per-occurrence rate of a hot chain does not depend on
-// the ring depth (3 .. 10 stages give 6.8 ns), but every 16 KB stage is taken from the SM's L1, and the
-// cold phase needs L1 lines for its 12 x 512 B loads in flight per warp: 6 stages -> 111 us, 3 -> 89 us.
-constexpr int kHotStagesDefault = 3;
+// Two kernels:
+//   seg_plan_kernel  one thread per unique: open() + one 32-byte work item {first sorted position,
+//       occurrences, first occurrence's source row, class, Ctx}, written in TICKET order (ticket t
+//       holds the uniques t, t + T, t + 2T, ...: ids that are hot tend to be neighbours in key
+//       order, a strided ticket spreads them), and the work lists of the long segments.  The data
+//       kernel reads its metadata with ONE coalesced load per ticket instead of three dependent
+//       levels of scattered ones.
+//   segment_reduce_kernel  persistent, warp-specialised:
+//     * hot group (warps 0 .. kHotWarps-1 of every CTA) — a Zipf batch has ids that occur thousands
+//       of times and the add ORDER is fixed by the parity contract, so such a segment cannot be split
+//       by rows; it is split by COLUMNS.  A work item is (hot row, 32-float column chunk) — 16-float
+//       chunks for the very hot rows.  The producer warps stream the chunk of every occurrence into
+//       a shared-memory ring with cp.async (the occurrence indices prefetched in registers one
+//       turn ahead) and signal each stage's `full` mbarrier when their copies have landed
+//       (cp.async.mbarrier.arrive); warp 0 only adds: it waits on `full`, runs the dependent FADD
+//       chain out of shared memory (loads one batch ahead of the adds, the next stage's barrier
+//       tested three batches ahead) and releases the stage through its `empty` mbarrier.  No
+//       CTA-wide barrier anywhere in the chain.
+//     * every other warp, and the hot group once the hot items are gone: first the MEDIUM rows
+//       (more than `med` occurrences: one warp per row, eight gradient rows in flight), then the
+//       cold tickets, kColdRows rows at a time with the row / gradient / owner-row loads of all of
+//       them in flight together (128-bit per lane); the next ticket's number and work items are
+//       fetched while the current one is processed.
+constexpr int kHotWarps = 3;                   // 1 adder + 2 producers
+constexpr int kHotProducers = kHotWarps - 1;
+constexpr int kHotStageFloats = 2048;          // 8 KB per ring stage: 128 occurrences x 16 columns
+constexpr int kHotStageBytes = kHotStageFloats * 4; // or 64 occurrences x 32 columns
+constexpr int kHotStagesDefault = 6;
 constexpr int kHotStagesMax = 12;
-constexpr int kHotStageBytes = kHotTileRows * 32 * 4;
-// dynamic shared memory of segment_reduce_kernel: the data ring + the index ring (2 x the ring
-// depth of the 16-column variant = 4 x stages tiles of kHotTileRows u32)
+// dynamic shared memory of segment_reduce_kernel: the ring, then full[S] / empty[S] mbarriers
 constexpr size_t hot_smem_bytes(int stages) {
-    return (size_t)stages * kHotStageBytes + (size_t)4 * stages * kHotTileRows * 4;
+    return (size_t)stages * kHotStageBytes + (size_t)2 * stages * 8 + 16;
 }
 constexpr u32 kVeryHot = 1024; // rows above this go first (longest-processing-time-first)
+constexpr u32 kMediumDefault = 4;
 
-// ring depth of the hot phase ($HERALD_HOT_STAGES, 3 .. 12): the bytes a CTA keeps in flight are
-// (stages - 1) x 16 KB, which is what hides HBM latency under the dependent add chain
+// ring depth of the hot phase ($HERALD_HOT_STAGES, 2 .. 12): the bytes the producers keep in
+// flight are what hides HBM latency under the dependent add chain
 int hot_stages();
 // uniques per cold-phase ticket ($HERALD_TICKET_ROWS, 4 .. 32)
 u32 ticket_rows();
+// segments longer than this (and not hot) are taken one warp per row ($HERALD_MED_THRESHOLD)
+u32 medium_threshold();
 
 // optional per-CTA timeline of the last segment_reduce launch (diagnostics, HBSegTraceEnable):
 // [0] = grid, [1] = hot items; then 4 words per CTA {start, hot phase end, end, items taken};
@@ -195,37 +206,36 @@ __device__ __forceinline__ T shfl_pod(const T &v, int src) {
     return out.t;
 }
 
-// optional two-step row opening: F::peek(u) (loads that depend on nothing but u) + F::begin(pre, u,
-// cnt, ctx); functors without peek keep the one-step begin(u, cnt, ctx)
-template <class F>
-__device__ __forceinline__ auto seg_peek(const F &f, size_t u, int) -> decltype(f.peek(u)) {
-    return f.peek(u);
-}
-template <class F>
-__device__ __forceinline__ int seg_peek(const F &, size_t, long) {
-    return 0;
-}
-template <class F, class P>
-__device__ __forceinline__ auto seg_begin(const F &f, const P &pre, size_t u, u32 cnt,
-                                          typename F::Ctx &x, int) -> decltype(f.begin(pre, u, cnt, x)) {
-    return f.begin(pre, u, cnt, x);
-}
-template <class F, class P>
-__device__ __forceinline__ bool seg_begin(const F &f, const P &, size_t u, u32 cnt, typename F::Ctx &x,
-                                          long) {
-    return f.begin(u, cnt, x);
-}
+// classes of a work item
+enum : u32 { SEG_SKIP = 0, SEG_COLD = 1, SEG_LISTED = 2 };
+
+// One unique key's work item, 32 bytes (two 128-bit loads per lane).
+struct __align__(16) SegItemHead {
+    u32 s0;  // first sorted position
+    u32 cnt; // occurrences
+    u32 p0;  // perm[s0]: source row of the first occurrence
+    u32 cls;
+};
+template <class Ctx>
+struct __align__(16) SegItem {
+    SegItemHead h;
+    Ctx ctx;
+    static_assert(sizeof(Ctx) <= 16, "segment contexts travel in 16 bytes");
+};
+constexpr size_t kSegItemBytes = 32;
 
 struct HotLists {
-    u32 *very_hot; // [cap] unique indices with count > kVeryHot
-    u32 *hot;      // [cap] unique indices with hot_threshold < count <= kVeryHot
-    u32 *done_a;   // [cap] finished chunks per very-hot row (zeroed by build_hot_lists_kernel)
-    u32 *done_b;   // [cap] same for the hot list
-    u32 *ctrl;     // [0] = #very_hot, [1] = #hot, [2] = hot ticket, [3] = cold ticket (zeroed with
-                   // the scan arena)
+    u32 *very_hot; // [cap] item indices of the rows with count > kVeryHot
+    u32 *hot;      // [cap] ... hot_threshold < count <= kVeryHot
+    u32 *medium;   // [cap] ... med_threshold < count <= hot_threshold
+    u32 *ctrl;     // [0] = #very_hot, [1] = #hot, [2] = hot ticket, [3] = cold ticket, [4] = #medium,
+                   // [5] = medium ticket (zeroed with the scan arena)
+    void *items;   // [cap + 32] work items in ticket order
     u64 *trace;    // diagnostics timeline or null
     int stages;    // ring depth of the hot phase
-    u32 ticket_rows; // uniques per cold ticket (<= 32; $HERALD_TICKET_ROWS)
+    u32 ticket_rows; // uniques per cold ticket (<= 32)
+    u32 med_threshold;
+    u32 mode;        // diagnostics ($HERALD_SEG_MODE): bit 0 = cold work waits for every hot group
 };
 
 __device__ __forceinline__ u32 rows_warp_append(u32 *counter, bool pred) {
@@ -240,31 +250,55 @@ __device__ __forceinline__ u32 rows_warp_append(u32 *counter, bool pred) {
     return base + __popc(m & lanemask_lt());
 }
 
-static __global__ void __launch_bounds__(256)
-    build_hot_lists_kernel(const u32 *__restrict__ seg_start, const u32 *__restrict__ num_unique,
-                           u32 hot_threshold, HotLists hl) {
+template <class F>
+__global__ void __launch_bounds__(256)
+    seg_plan_kernel(const u32 *__restrict__ seg_start, const u32 *__restrict__ perm,
+                    const u32 *__restrict__ num_unique, u32 hot_threshold, HotLists hl, F f) {
     pdl_enter();
+    using Item = SegItem<typename F::Ctx>;
+    static_assert(sizeof(Item) == kSegItemBytes, "work items are 32 bytes");
+    Item *items = reinterpret_cast<Item *>(hl.items);
     const u32 U = *num_unique;
+    const u32 TK = hl.ticket_rows;
+    const u32 T = (U + TK - 1) / TK;
+    const u32 total = T * TK;
+    const u32 med = min(hl.med_threshold, hot_threshold);
+    f.kernel_begin();
     const u32 stride = gridDim.x * blockDim.x;
-    const u32 rounds = (U + stride - 1) / stride;
-    for (u32 it = 0; it < rounds; it++) {
-        const u32 u = it * stride + blockIdx.x * blockDim.x + threadIdx.x;
-        u32 cnt = 0;
-        if (u < U)
-            cnt = seg_start[u + 1] - seg_start[u];
-        const bool a = cnt > kVeryHot && cnt > hot_threshold;
-        const bool b = !a && cnt > hot_threshold;
-        u32 pa = rows_warp_append(&hl.ctrl[0], a);
-        if (a) {
-            hl.very_hot[pa] = u;
-            hl.done_a[pa] = 0;
+    const u32 rounds = (total + stride - 1) / stride;
+    for (u32 it = 0; it < rounds; it++) { // block-uniform trip count: the appends are warp-collective
+        const u32 i = it * stride + blockIdx.x * blockDim.x + threadIdx.x;
+        const u32 t = i / TK, l = i - t * TK;
+        const u32 u = t + l * T;
+        Item item;
+        item.h.s0 = item.h.cnt = item.h.p0 = 0;
+        item.h.cls = SEG_SKIP;
+        item.ctx = typename F::Ctx();
+        if (i < total && u < U) {
+            item.h.s0 = seg_start[u];
+            item.h.cnt = seg_start[u + 1] - item.h.s0;
+            if (item.h.cnt > 0 && f.open((size_t)u, item.h.cnt, item.ctx)) {
+                item.h.p0 = perm[item.h.s0];
+                item.h.cls = item.h.cnt > med ? SEG_LISTED : SEG_COLD;
+            }
         }
-        u32 pb = rows_warp_append(&hl.ctrl[1], b);
-        if (b) {
-            hl.hot[pb] = u;
-            hl.done_b[pb] = 0;
-        }
+        if (i < total)
+            items[i] = item;
+        const bool listed = item.h.cls == SEG_LISTED;
+        const bool a = listed && item.h.cnt > hot_threshold && item.h.cnt > kVeryHot;
+        const bool b = listed && !a && item.h.cnt > hot_threshold;
+        const bool m = listed && !a && !b;
+        const u32 pa = rows_warp_append(&hl.ctrl[0], a);
+        if (a)
+            hl.very_hot[pa] = i;
+        const u32 pb = rows_warp_append(&hl.ctrl[1], b);
+        if (b)
+            hl.hot[pb] = i;
+        const u32 pm = rows_warp_append(&hl.ctrl[4], m);
+        if (m)
+            hl.medium[pm] = i;
     }
+    f.kernel_end();
 }
 
 __device__ __forceinline__ void cp_async_f32(float *smem_dst, const float *gsrc) {
@@ -275,152 +309,196 @@ __device__ __forceinline__ void cp_async_16(float *smem_dst, const float *gsrc) 
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
 }
-__device__ __forceinline__ void cp_async_commit() {
-    asm volatile("cp.async.commit_group;" ::: "memory");
+
+// ---- mbarrier (shared::cta) -------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void *p) {
+    return (unsigned)__cvta_generic_to_shared(p);
 }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+__device__ __forceinline__ void mbar_init(u64 *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(u64 *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// the executing thread's arrival happens when all its earlier cp.async copies have landed; the
+// barrier's expected count already includes it (.noinc)
+__device__ __forceinline__ void mbar_arrive_on_copies(u64 *bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_test(u64 *bar, unsigned parity) { // non-blocking
+    unsigned ok;
+    asm volatile("{\n\t.reg .pred p;\n\t"
+                 "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                 "selp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok)
+                 : "r"(smem_u32(bar)), "r"(parity)
+                 : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(u64 *bar, unsigned parity) {
+    asm volatile("{\n\t.reg .pred p;\n\t"
+                 "HB_WAIT_%=:\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+                 "@p bra HB_DONE_%=;\n\t"
+                 "bra HB_WAIT_%=;\n\t"
+                 "HB_DONE_%=:\n\t}" ::"r"(smem_u32(bar)),
+                 "r"(parity)
+                 : "memory");
+}
+// named barrier of the hot group (barrier 0 is __syncthreads)
+__device__ __forceinline__ void hot_group_sync() {
+    asm volatile("bar.sync 1, %0;" ::"n"(kHotWarps * 32) : "memory");
 }
 
-// One hot work item: columns [q*W, q*W + W) of one hot row, all its occurrences in order.
-// The CTA streams the W-float chunk of every occurrence through an S-deep cp.async ring
-// ([S][kHotTileRows][W] floats); warp 0 adds them, one column per lane (lanes >= W idle).
-// WIDE (rows 16 B aligned, D % 4 == 0): a thread copies 16 B, W/4 threads cover one occurrence
-// (LDGSTS costs ~8 cycles per warp instruction whatever its width, so 16 B copies are what keeps
-// the ring ahead of the adder); otherwise 4 B per thread and W == 32, one occurrence per warp
-// instruction.
-template <int W, bool WIDE, class F1>
-__device__ __forceinline__ void hot_chunk(const F1 &f1, const typename F1::Ctx &ctx, float *s_ring,
-                                          u32 *s_perm, u32 S, const u32 *__restrict__ perm,
-                                          const float *__restrict__ vals, size_t D, u32 s0, u32 s1,
-                                          u32 q) {
+// ring stage / phase parity of the CTA's kt-th hot tile
+struct HotRing {
+    float *ring;
+    u64 *full, *empty;
+    u32 S;
+    u32 stage, phase; // of the next tile
+    __device__ __forceinline__ void advance() {
+        if (++stage == S) {
+            stage = 0;
+            phase ^= 1u;
+        }
+    }
+    __device__ __forceinline__ void advance(u32 n) { // n < 2 * S steps at a time are enough here
+        for (u32 i = 0; i < n; i++)
+            advance();
+    }
+};
+
+// Producer warp `p` of kHotProducers: tiles p, p + P, ... of one hot item (columns [q*W, q*W + W)
+// of every occurrence).  WIDE (rows 16 B aligned, D % 4 == 0): a thread copies 16 B, W/4 threads
+// cover one occurrence (LDGSTS costs ~8 cycles per warp instruction whatever its width);
+// otherwise 4 B per thread and W == 32, one occurrence per warp instruction.
+template <int W, bool WIDE>
+__device__ __forceinline__ void hot_produce(HotRing hr, u32 p, const u32 *__restrict__ seg_perm,
+                                            const float *__restrict__ vals, size_t D, u32 cnt, u32 q) {
     static_assert(WIDE || W == 32, "the 4-byte copy path moves one 32-column chunk per warp");
-    constexpr int RPW = kHotTileRows / kRowWarps;              // rows of a stage per warp (4 B path)
-    constexpr int TPR = W / 4;                                 // threads per occurrence (16 B path)
-    constexpr int RPI = kRowBlock / TPR;                       // occurrences per CTA-wide copy round
-    constexpr int CPT = WIDE ? kHotTileRows / RPI : RPW;       // copies per thread per stage
-    const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
-    const u32 cnt = s1 - s0;
+    constexpr int TILE = kHotStageFloats / W;  // occurrences per stage
+    constexpr int TPR = WIDE ? W / 4 : 32;     // threads per occurrence
+    constexpr int OPI = 32 / TPR;              // occurrences per warp instruction
+    constexpr int NI = TILE / OPI;             // copy instructions per tile
+    constexpr int NR = TILE / 32;              // index registers per lane and tile
+    const unsigned lane = lane_id();
+    const u32 sub = lane / TPR;
+    const u32 off = WIDE ? (lane % TPR) * 4 : lane; // float offset inside the chunk
+    const bool col_ok = (size_t)q * W + off < D;
+    const float *src = vals + (size_t)q * W + off;
+    const u32 ntiles = (cnt + TILE - 1) / TILE;
+    hr.advance(p);
+    // The occurrence indices of this warp's next tile are loaded one turn ahead into a second
+    // register set; the two sets swap roles by unrolling the turn loop twice (a register move
+    // from the set being loaded would wait for the load: one memory latency per tile).
+    auto load_idx = [&](u32 (&idx)[NR], u32 k) {
+#pragma unroll
+        for (int j = 0; j < NR; j++) {
+            const u32 o = k * TILE + j * 32 + lane;
+            idx[j] = (k < ntiles && o < cnt) ? seg_perm[o] : 0;
+        }
+    };
+    auto fill = [&](const u32 (&idx)[NR], u32 k) {
+        mbar_wait(&hr.empty[hr.stage], hr.phase ^ 1u);
+        float *stage = hr.ring + (size_t)hr.stage * kHotStageFloats;
+        const u32 base = k * TILE;
+#pragma unroll
+        for (int i = 0; i < NI; i++) {
+            const u32 o = i * OPI + sub;
+            const u32 pi = __shfl_sync(FULL, idx[(i * OPI) / 32], ((i * OPI) % 32) + sub);
+            if (base + o < cnt && col_ok) {
+                if (WIDE)
+                    cp_async_16(stage + o * W + off, src + (size_t)pi * D);
+                else
+                    cp_async_f32(stage + o * W + off, src + (size_t)pi * D);
+            }
+        }
+        mbar_arrive_on_copies(&hr.full[hr.stage]);
+        hr.advance(kHotProducers);
+    };
+    u32 ia[NR], ib[NR];
+    u32 k = p;
+    load_idx(ia, k);
+    while (k < ntiles) {
+        load_idx(ib, k + kHotProducers);
+        fill(ia, k);
+        k += kHotProducers;
+        if (k >= ntiles)
+            break;
+        load_idx(ia, k + kHotProducers);
+        fill(ib, k);
+        k += kHotProducers;
+    }
+}
+
+// The adder warp: one column per lane, every occurrence in order.  Lanes >= W mirror lanes < W
+// (same shared-memory words, results dropped): the chain runs without a divergent region.
+// A full stage is consumed by fully unrolled code with a rolling window: value j + kAhead is
+// loaded right before value j is added, so the loads stay kAhead occurrences in front of the
+// dependent FADD chain and no register is copied.
+template <int W, class F1>
+__device__ __forceinline__ void hot_add(HotRing hr, const F1 &f1, const typename F1::Ctx &ctx, size_t D,
+                                        u32 cnt, u32 q, u64 &waited) {
+    constexpr int TILE = kHotStageFloats / W;
+    constexpr int kAhead = 16;
+    static_assert(TILE >= 4 * kAhead, "the next stage is tested three windows before the end");
+    const unsigned lane = lane_id();
+    const unsigned rl = lane & (W - 1);
     const size_t col = (size_t)q * W + lane;
     const bool active = lane < (unsigned)W && col < D;
-    decltype(f1.load(ctx, 0)) acc;
-    if (warp == 0 && active)
-        acc = f1.load(ctx, col);
-    const u32 ntiles = (cnt + kHotTileRows - 1) / kHotTileRows;
-    const u32 my_row = WIDE ? (threadIdx.x / TPR) : warp * RPW;       // first row it copies
-    const u32 my_off = WIDE ? (threadIdx.x % TPR) * 4 : lane;         // float offset in the chunk
-    const bool cp_active = (size_t)q * W + my_off < D;
-    const float *my_src = vals + (size_t)q * W + my_off;
-    // The occurrence indices (perm) travel through their own shared-memory ring of 2S tiles,
-    // copied S - 1 tiles ahead of the data copies that read them and committed in the same
-    // cp.async groups: a data copy never waits for an index load from global memory (with the
-    // indices prefetched one tile ahead in registers, every tile paid one L2/HBM latency:
-    // 10 ns per occurrence instead of the ~2.5 ns of the dependent FADD chain).
-    const u32 PS = 2 * S;
-    const u32 *seg_perm = perm + s0;
-    auto copy_perm = [&](u32 tile, u32 slot) {
-        const u32 i = tile * kHotTileRows + threadIdx.x;
-        if (threadIdx.x < kHotTileRows && i < cnt)
-            cp_async_f32(reinterpret_cast<float *>(s_perm + slot * kHotTileRows + threadIdx.x),
-                         reinterpret_cast<const float *>(seg_perm + i));
-    };
-    u32 issue_slot = 0; // (next tile to issue) % S, kept without a division
-    u32 pslot_r = 0;    // (next tile to issue) % 2S
-    u32 next_tile = 0;
-    auto issue = [&]() {
-        float *stage = s_ring + (size_t)issue_slot * kHotTileRows * W;
-        const u32 *pt = s_perm + pslot_r * kHotTileRows;
-        issue_slot = issue_slot + 1 == S ? 0 : issue_slot + 1;
-        pslot_r = pslot_r + 1 == PS ? 0 : pslot_r + 1;
-        const u32 base = next_tile * kHotTileRows;
-        next_tile++;
-#pragma unroll
-        for (int j = 0; j < CPT; j++) {
-            const u32 row = my_row + (WIDE ? RPI * j : j);
-            if (base + row < cnt && cp_active) {
-                const u32 pi = pt[row];
-                if (WIDE)
-                    cp_async_16(stage + row * W + my_off, my_src + (size_t)pi * D);
-                else
-                    cp_async_f32(stage + row * W + my_off, my_src + (size_t)pi * D);
-            }
-        }
-    };
-    // prologue: indices of tiles 0 .. 2S-3, then the data of tiles 0 .. S-2
-    for (u32 t = 0; t + 2 < PS && t < ntiles; t++)
-        copy_perm(t, t);
-    cp_async_commit();
-    cp_async_wait<0>();
-    __syncthreads();
-#pragma unroll 1
-    for (u32 k = 0; k < S - 1; k++) {
-        issue();
-        cp_async_commit();
+    const size_t lcol = (size_t)q * W + rl;
+    decltype(f1.load(ctx, 0)) acc = f1.load(ctx, lcol < D ? lcol : (size_t)q * W);
+    const u32 ntiles = (cnt + TILE - 1) / TILE;
+    {
+        const long long c0 = clock64();
+        mbar_wait(&hr.full[hr.stage], hr.phase);
+        waited += (u64)(clock64() - c0);
     }
-    u32 pslot_w = PS - 2; // slot of index tile k + 2S - 2
-    u32 read_slot = 0;
     for (u32 k = 0; k < ntiles; k++) {
-        // groups are committed one per tile, in order: at most S - 2 newer than tile k may still
-        // be pending (wait_group takes an immediate, so the depth is switched; waiting for more
-        // than necessary on a deeper ring is still correct)
-        if (S >= 24)
-            cp_async_wait<22>();
-        else if (S >= 20)
-            cp_async_wait<18>();
-        else if (S >= 16)
-            cp_async_wait<14>();
-        else if (S >= 12)
-            cp_async_wait<10>();
-        else if (S >= 10)
-            cp_async_wait<8>();
-        else if (S >= 8)
-            cp_async_wait<6>();
-        else if (S >= 6)
-            cp_async_wait<4>();
-        else if (S == 5)
-            cp_async_wait<3>();
-        else if (S == 4)
-            cp_async_wait<2>();
-        else
-            cp_async_wait<1>();
-        __syncthreads(); // ... everyone's has; and stage k-1 has been consumed
-        issue();         // tile k + S - 1 into the slot tile k - 1 occupied
-        copy_perm(k + PS - 2, pslot_w); // its slot held tile k - 2, last read S + 1 iterations ago
-        pslot_w = pslot_w + 1 == PS ? 0 : pslot_w + 1;
-        cp_async_commit();
-        if (warp == 0 && active) {
-            const float *stage = s_ring + (size_t)read_slot * kHotTileRows * W + lane;
-            const u32 rows = min((u32)kHotTileRows, cnt - k * kHotTileRows);
-            if (rows == kHotTileRows) {
-                // full tile: completely unrolled, so the shared-memory loads run ahead of the
-                // dependent adds as far as the register file allows
-                float g[kHotTileRows];
+        const float *st = hr.ring + (size_t)hr.stage * kHotStageFloats + rl;
+        u64 *const my_empty = &hr.empty[hr.stage];
+        const u32 rows = min((u32)TILE, cnt - k * TILE);
+        hr.advance();
+        const bool more = k + 1 < ntiles;
+        bool next_ready = false;
+        if (rows == TILE) {
+            float v[TILE];
 #pragma unroll
-                for (int j = 0; j < kHotTileRows; j++)
-                    g[j] = stage[j * W];
+            for (int j = 0; j < kAhead; j++)
+                v[j] = st[j * W];
 #pragma unroll
-                for (int j = 0; j < kHotTileRows; j++)
-                    acc = f1.step(acc, g[j]);
-            } else {
-                u32 r = 0;
-                for (; r + 16 <= rows; r += 16) {
-                    float g[16];
-#pragma unroll
-                    for (int j = 0; j < 16; j++)
-                        g[j] = stage[(r + j) * W];
-#pragma unroll
-                    for (int j = 0; j < 16; j++)
-                        acc = f1.step(acc, g[j]);
-                }
-                for (; r < rows; r++)
-                    acc = f1.step(acc, stage[r * W]);
+            for (int j = 0; j < TILE; j++) {
+                if (j + kAhead < TILE)
+                    v[j + kAhead] = st[(j + kAhead) * W];
+                if (j == TILE - 3 * kAhead && more) // its result is back before the last add
+                    next_ready = mbar_test(&hr.full[hr.stage], hr.phase);
+                acc = f1.step(acc, v[j]);
             }
+        } else {
+            u32 r = 0;
+            for (; r + kAhead <= rows; r += kAhead) {
+                float g[kAhead];
+#pragma unroll
+                for (int j = 0; j < kAhead; j++)
+                    g[j] = st[(r + j) * W];
+#pragma unroll
+                for (int j = 0; j < kAhead; j++)
+                    acc = f1.step(acc, g[j]);
+            }
+            for (; r < rows; r++)
+                acc = f1.step(acc, st[r * W]);
         }
-        read_slot = read_slot + 1 == S ? 0 : read_slot + 1;
+        // every value of the stage has been consumed (the adds above depend on the loads)
+        __syncwarp();
+        if (lane == 0)
+            mbar_arrive(my_empty);
+        if (more && !next_ready) {
+            const long long c0 = clock64();
+            mbar_wait(&hr.full[hr.stage], hr.phase);
+            waited += (u64)(clock64() - c0);
+        }
     }
-    cp_async_wait<0>();
-    if (warp == 0 && active)
+    if (active)
         f1.store(ctx, col, acc);
 }
 
@@ -428,14 +506,18 @@ __device__ __forceinline__ void hot_chunk(const F1 &f1, const typename F1::Ctx &
 // VEC = 1 (the hot path addresses single columns).
 template <int VEC, int ROWS, class FV, class F1>
 __global__ void __launch_bounds__(kRowBlock, 2)
-    segment_reduce_kernel(const u32 *__restrict__ seg_start, const u32 *__restrict__ perm,
-                          const u32 *__restrict__ num_unique, const float *__restrict__ vals,
-                          size_t D, u32 hot_threshold, HotLists hl, FV fv, F1 f1) {
+    segment_reduce_kernel(const u32 *__restrict__ perm, const u32 *__restrict__ num_unique,
+                          const float *__restrict__ vals, size_t D, u32 hot_threshold, HotLists hl,
+                          FV fv, F1 f1) {
     pdl_enter();
-    extern __shared__ __align__(16) float s_ring[]; // [stages][kHotTileRows][32], then the index ring
+    extern __shared__ __align__(16) float s_ring[]; // [stages][kHotStageFloats], then the mbarriers
     __shared__ u32 s_item;
+    using Item = SegItem<typename FV::Ctx>;
+    static_assert(sizeof(typename FV::Ctx) == sizeof(typename F1::Ctx), "one context type");
+    const Item *__restrict__ items = reinterpret_cast<const Item *>(hl.items);
     const u32 S = (u32)hl.stages;
-    u32 *const s_perm = reinterpret_cast<u32 *>(s_ring + (size_t)S * kHotTileRows * 32); // [4S][kHotTileRows]
+    u64 *const s_full = reinterpret_cast<u64 *>(s_ring + (size_t)S * kHotStageFloats);
+    u64 *const s_empty = s_full + S;
     u64 *const trace = hl.trace;
     u32 items_taken = 0;
     if (trace && threadIdx.x == 0 && blockIdx.x < kTraceCtas) {
@@ -447,14 +529,19 @@ __global__ void __launch_bounds__(kRowBlock, 2)
     constexpr bool WIDE = VEC == 4; // rows are 16 B aligned and D % 4 == 0
     const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
     const u32 U = *num_unique;
-    fv.kernel_begin();
+    const bool hot_on = hot_threshold != 0xffffffffu;
 
-    // Every CTA runs the hot items first, then the cold tickets.  (Measured alternative: letting one
-    // CTA of every SM start with the cold tickets makes the chains 2.5x slower — a hot chain's copies
-    // queue behind the cold neighbour's loads for the whole run instead of the second half — and
-    // the kernel went from 89 us to 200 us.)
-    // ------------------------------- hot phase -------------------------------------------
-    if (hot_threshold != 0xffffffffu) {
+    // ------------------------------- hot group --------------------------------------------
+    if (hot_on) {
+        if (threadIdx.x == 0) {
+            for (u32 i = 0; i < S; i++) {
+                mbar_init(&s_full[i], 32); // the 32 lanes of the producer warp that fills the stage
+                mbar_init(&s_empty[i], 1); // the adder's lane 0
+            }
+        }
+        __syncthreads();
+    }
+    if (hot_on && warp < (unsigned)kHotWarps) {
         // very hot rows are cut into 16-column chunks when the rows allow 16 B copies: half the
         // bytes per occurrence in the ring = twice the occurrences in flight on the longest chains
         const u32 QB = (u32)((D + 31) / 32);
@@ -462,11 +549,12 @@ __global__ void __launch_bounds__(kRowBlock, 2)
         const u32 nA = hl.ctrl[0], nB = hl.ctrl[1];
         const u32 itemsA = nA * QA;
         const u32 total = itemsA + nB * QB;
+        HotRing hr{s_ring, s_full, s_empty, S, 0u, 0u};
         while (true) {
-            __syncthreads(); // the ring and s_item of the previous item are no longer in use
+            hot_group_sync(); // s_item of the previous item has been read by everyone
             if (threadIdx.x == 0)
                 s_item = atomicAdd(&hl.ctrl[2], 1u);
-            __syncthreads();
+            hot_group_sync();
             const u32 t = s_item;
             if (t >= total)
                 break;
@@ -474,147 +562,212 @@ __global__ void __launch_bounds__(kRowBlock, 2)
             if (trace && threadIdx.x == 0 && t < kTraceItems)
                 trace[2 + 4 * (size_t)kTraceCtas + 3 * t] = global_timer_ns();
             const bool very = t < itemsA;
-            const u32 h = very ? t / QA : nA + (t - itemsA) / QB;
+            const u32 h = very ? t / QA : (t - itemsA) / QB;
             const u32 q = very ? t % QA : (t - itemsA) % QB;
-            const u32 u = very ? hl.very_hot[h] : hl.hot[h - nA];
-            u32 *done = very ? &hl.done_a[h] : &hl.done_b[h - nA];
-            const u32 nchunks = very ? QA : QB;
-            const u32 s0 = seg_start[u], s1 = seg_start[u + 1];
-            const u32 cnt = s1 - s0;
-            typename F1::Ctx ctx;
-            const bool ok = f1.begin(u, cnt, ctx);
-            if (ok) {
+            const Item it = items[very ? hl.very_hot[h] : hl.hot[h]];
+            const u32 cnt = it.h.cnt;
+            const u32 W = (very && WIDE) ? 16u : 32u;
+            const u32 ntiles = (cnt + kHotStageFloats / W - 1) / (kHotStageFloats / W);
+            u64 waited = 0;
+            if (warp == 0) {
+                typename F1::Ctx ctx;
+                memcpy(&ctx, &it.ctx, sizeof(ctx));
+                if (very && WIDE)
+                    hot_add<16>(hr, f1, ctx, D, cnt, q, waited);
+                else
+                    hot_add<32>(hr, f1, ctx, D, cnt, q, waited);
+            } else {
+                const u32 *sp = perm + it.h.s0;
                 if constexpr (WIDE) {
                     if (very)
-                        hot_chunk<16, true>(f1, ctx, s_ring, s_perm, S * 2, perm, vals, D, s0, s1, q);
+                        hot_produce<16, true>(hr, warp - 1, sp, vals, D, cnt, q);
                     else
-                        hot_chunk<32, true>(f1, ctx, s_ring, s_perm, S, perm, vals, D, s0, s1, q);
+                        hot_produce<32, true>(hr, warp - 1, sp, vals, D, cnt, q);
                 } else {
-                    hot_chunk<32, false>(f1, ctx, s_ring, s_perm, S, perm, vals, D, s0, s1, q);
+                    hot_produce<32, false>(hr, warp - 1, sp, vals, D, cnt, q);
                 }
             }
-            // the CTA that completes the row's last chunk applies the per-row scalars
-            if (warp == 0) {
-                u32 prev = 0;
-                __syncwarp();
-                if (lane == 0) {
-                    __threadfence();
-                    prev = atomicAdd(done, 1u);
-                }
-                prev = __shfl_sync(FULL, prev, 0);
-                if (prev == nchunks - 1 && ok && lane == 0) {
-                    __threadfence();
-                    f1.end(ctx);
-                }
-            }
+            // every warp of the group moves its view of the ring past this item's tiles
+            for (u32 i = 0; i < ntiles % (2 * S); i++)
+                hr.advance();
             if (trace && threadIdx.x == 0 && t < kTraceItems) {
                 trace[2 + 4 * (size_t)kTraceCtas + 3 * t + 1] = global_timer_ns();
-                trace[2 + 4 * (size_t)kTraceCtas + 3 * t + 2] = cnt;
+                trace[2 + 4 * (size_t)kTraceCtas + 3 * t + 2] = (u64)cnt | ((waited >> 4) << 32);
             }
+        }
+        if ((hl.mode & 1u) && threadIdx.x == 0) {
+            __threadfence();
+            atomicAdd(&hl.ctrl[6], 1u);
         }
         if (trace && threadIdx.x == 0 && blockIdx.x == 0)
             trace[1] = total;
-    }
-    if (trace && threadIdx.x == 0 && blockIdx.x < kTraceCtas) {
-        trace[2 + 4 * blockIdx.x + 1] = global_timer_ns();
-        trace[2 + 4 * blockIdx.x + 3] = items_taken;
+        if (trace && threadIdx.x == 0 && blockIdx.x < kTraceCtas) {
+            trace[2 + 4 * blockIdx.x + 1] = global_timer_ns();
+            trace[2 + 4 * blockIdx.x + 3] = items_taken;
+        }
     }
 
-    // ------------------------------- cold phase ------------------------------------------
-    // Ticket t covers the uniques t, t + T, t + 2T, ... (T tickets): ids that are hot tend to be
-    // neighbours in key order, a strided ticket spreads their longer segments over many warps.
+    if (hot_on && (hl.mode & 1u)) { // diagnostics: the hot chains run on an otherwise idle chip
+        while (*reinterpret_cast<volatile u32 *>(&hl.ctrl[6]) < gridDim.x)
+            __nanosleep((hl.mode & 2u) ? 20000 : 200);
+    }
     const size_t nvec = D / VEC;
-    const u32 TK = hl.ticket_rows;
-    const u32 T = (U + TK - 1) / TK;
-    while (true) {
-        u32 t = 0;
-        if (lane == 0)
-            t = atomicAdd(&hl.ctrl[3], 1u);
-        t = __shfl_sync(FULL, t, 0);
-        if (t >= T)
-            break;
-        // lane-parallel metadata of the 32 uniques of this ticket
-        const u32 my_u = t + lane * T;
-        const bool mine = lane < TK && my_u < U;
-        const auto my_pre = seg_peek(fv, mine ? my_u : 0u, 0);
-        const u32 my_s0 = mine ? seg_start[my_u] : 0;
-        const u32 my_cnt = mine ? seg_start[my_u + 1] - my_s0 : 0;
-        const bool my_cold = my_cnt > 0 && my_cnt <= hot_threshold;
-        const u32 my_p0 = my_cold ? perm[my_s0] : 0;
-        const int nrows = __popc(__ballot_sync(FULL, mine)); // valid lanes are 0 .. nrows-1
-        // every lane opens its own row: the dependent scalar loads of 32 rows overlap
-        typename FV::Ctx my_ctx;
-        const bool my_ok = my_cold && seg_begin(fv, my_pre, my_u, my_cnt, my_ctx, 0);
-#pragma unroll 1
-        for (int g0 = 0; g0 < nrows; g0 += ROWS) {
-            typename FV::Ctx ctx[ROWS];
-            u32 s0[ROWS], cnt[ROWS], p0[ROWS];
-            bool ok[ROWS];
-#pragma unroll
-            for (int r = 0; r < ROWS; r++) {
-                const int from = (g0 + r) & 31;
-                s0[r] = __shfl_sync(FULL, my_s0, from);
-                cnt[r] = __shfl_sync(FULL, my_cnt, from);
-                p0[r] = __shfl_sync(FULL, my_p0, from);
-                ok[r] = g0 + r < nrows && __shfl_sync(FULL, my_ok, from);
-                ctx[r] = shfl_pod(my_ctx, from);
-            }
-            // warp-uniform column loop (lanes beyond the row width idle): the shuffles below
-            // need every lane
+    // ------------------------------- medium rows ------------------------------------------
+    // one warp per row, eight gradient rows in flight; taken before the cold tickets so that the
+    // longest serial pieces of the kernel start first
+    {
+        const u32 nM = hl.ctrl[4];
+        while (nM) {
+            u32 t = 0;
+            if (lane == 0)
+                t = atomicAdd(&hl.ctrl[5], 1u);
+            t = __shfl_sync(FULL, t, 0);
+            if (t >= nM)
+                break;
+            const Item it = items[hl.medium[t]];
+            const u32 s0 = it.h.s0, cnt = it.h.cnt;
             for (size_t c0 = 0; c0 < nvec; c0 += 32) {
                 const size_t c = c0 + lane;
                 const bool cv = c < nvec;
-                decltype(fv.load(ctx[0], 0)) acc[ROWS];
-                typename V::T g[ROWS];
+                decltype(fv.load(it.ctx, 0)) acc;
+                if (cv)
+                    acc = fv.load(it.ctx, c);
+                for (u32 b = 0; b < cnt; b += 32) {
+                    const u32 nb = min(32u, cnt - b);
+                    const u32 pl = lane < nb ? perm[s0 + b + lane] : 0;
+                    for (u32 j = 0; j < nb; j += 8) {
+                        typename V::T gg[8];
 #pragma unroll
-                for (int r = 0; r < ROWS; r++)
-                    if (ok[r] && cv) {
-                        acc[r] = fv.load(ctx[r], c);
-                        g[r] = V::ld_nc(vals + (size_t)p0[r] * D + c * VEC);
-                    }
-#pragma unroll
-                for (int r = 0; r < ROWS; r++)
-                    if (ok[r] && cv)
-                        acc[r] = fv.step(acc[r], g[r]);
-                // further occurrences (few rows have any): 32 at a time, their source rows
-                // fetched lane-parallel, four gradient rows in flight
-#pragma unroll
-                for (int r = 0; r < ROWS; r++) {
-                    if (!ok[r] || cnt[r] < 2)
-                        continue;
-                    for (u32 b = 1; b < cnt[r]; b += 32) {
-                        const u32 nb = min(32u, cnt[r] - b);
-                        const u32 pl = lane < nb ? perm[s0[r] + b + lane] : 0;
-                        for (u32 j = 0; j < nb; j += 4) {
-                            typename V::T gg[4];
-#pragma unroll
-                            for (int k = 0; k < 4; k++) {
-                                const u32 pi = __shfl_sync(FULL, pl, (j + k) & 31);
-                                if (j + k < nb && cv)
-                                    gg[k] = V::ld_nc(vals + (size_t)pi * D + c * VEC);
-                            }
-#pragma unroll
-                            for (int k = 0; k < 4; k++)
-                                if (j + k < nb && cv)
-                                    acc[r] = fv.step(acc[r], gg[k]);
+                        for (int k = 0; k < 8; k++) {
+                            const u32 pi = __shfl_sync(FULL, pl, (j + k) & 31);
+                            if (j + k < nb && cv)
+                                gg[k] = V::ld_nc(vals + (size_t)pi * D + c * VEC);
                         }
+#pragma unroll
+                        for (int k = 0; k < 8; k++)
+                            if (j + k < nb && cv)
+                                acc = fv.step(acc, gg[k]);
                     }
                 }
-#pragma unroll
-                for (int r = 0; r < ROWS; r++)
-                    if (ok[r] && cv)
-                        fv.store(ctx[r], c, acc[r]);
+                if (cv)
+                    fv.store(it.ctx, c, acc);
             }
         }
-        if (my_ok)
-            fv.end(my_ctx);
+    }
+
+    // ------------------------------- cold tickets ------------------------------------------
+    // Ticket t = work items [t*TK, t*TK + TK), one per lane.  The ticket after the next is drawn
+    // and the next ticket's items are loaded while the current ticket is processed.
+    {
+        const u32 TK = hl.ticket_rows;
+        const u32 T = (U + TK - 1) / TK;
+        constexpr int XPR = 32 / ROWS; // further occurrences per row whose indices one load covers
+        auto draw = [&]() {
+            u32 t = 0;
+            if (lane == 0)
+                t = atomicAdd(&hl.ctrl[3], 1u);
+            return t; // lane 0's value counts; broadcast where it is used
+        };
+        auto fetch = [&](u32 t) {
+            Item it;
+            it.h.s0 = it.h.cnt = it.h.p0 = 0;
+            it.h.cls = SEG_SKIP;
+            if (t < T && lane < TK)
+                it = items[(size_t)t * TK + lane];
+            return it;
+        };
+        u32 t_cur = __shfl_sync(FULL, draw(), 0);
+        Item it_cur = fetch(t_cur);
+        u32 t_next_raw = draw();
+        while (t_cur < T) {
+            const u32 t_next = __shfl_sync(FULL, t_next_raw, 0);
+            const Item it_next = fetch(t_next);
+            t_next_raw = draw();
+            const Item my = it_cur;
+            const bool my_cold = my.h.cls == SEG_COLD;
+            const unsigned cold_mask = __ballot_sync(FULL, my_cold);
+#pragma unroll 1
+            for (u32 g0 = 0; g0 < TK; g0 += ROWS) {
+                if (((cold_mask >> g0) & ((1u << ROWS) - 1u)) == 0)
+                    continue;
+                typename FV::Ctx ctx[ROWS];
+                u32 cnt[ROWS], p0[ROWS];
+                bool ok[ROWS];
+                u32 max_cnt = 0;
+#pragma unroll
+                for (int r = 0; r < ROWS; r++) {
+                    const int from = (g0 + r) & 31;
+                    ok[r] = (cold_mask >> from) & 1u;
+                    const u32 rc = __shfl_sync(FULL, my.h.cnt, from);
+                    cnt[r] = ok[r] ? rc : 0;
+                    p0[r] = __shfl_sync(FULL, my.h.p0, from);
+                    ctx[r] = shfl_pod(my.ctx, from);
+                    max_cnt = max(max_cnt, cnt[r]);
+                }
+                // source rows of the further occurrences (few rows have any): lane r*XPR + j holds
+                // the one of occurrence 1 + j of row r; issued together with the row loads
+                const int xr = (int)(lane / XPR), xj = (int)(lane % XPR);
+                const int xfrom = (g0 + xr) & 31;
+                const u32 xs0 = __shfl_sync(FULL, my.h.s0, xfrom);
+                const u32 xc = __shfl_sync(FULL, my.h.cnt, xfrom);
+                const u32 xcnt = ((cold_mask >> xfrom) & 1u) ? xc : 0;
+                u32 xi = 0;
+                if (max_cnt > 1 && 1u + xj < xcnt)
+                    xi = perm[xs0 + 1 + xj];
+                // warp-uniform column loop (lanes beyond the row width idle): the shuffles below
+                // need every lane
+                for (size_t c0 = 0; c0 < nvec; c0 += 32) {
+                    const size_t c = c0 + lane;
+                    const bool cv = c < nvec;
+                    decltype(fv.load(ctx[0], 0)) acc[ROWS];
+                    typename V::T g[ROWS];
+#pragma unroll
+                    for (int r = 0; r < ROWS; r++)
+                        if (ok[r] && cv) {
+                            acc[r] = fv.load(ctx[r], c);
+                            g[r] = V::ld_nc(vals + (size_t)p0[r] * D + c * VEC);
+                        }
+#pragma unroll
+                    for (int r = 0; r < ROWS; r++)
+                        if (ok[r] && cv)
+                            acc[r] = fv.step(acc[r], g[r]);
+                    // further occurrences: one of every row per round, all rows' loads in flight
+                    for (u32 jb = 1; jb < max_cnt; jb += XPR) {
+                        u32 xcur = xi;
+                        if (jb > 1) // (only with a medium threshold above XPR)
+                            xcur = jb + xj < xcnt ? perm[xs0 + jb + xj] : 0;
+                        const u32 jend = min(max_cnt, jb + (u32)XPR);
+                        for (u32 j = jb; j < jend; j++) {
+#pragma unroll
+                            for (int r = 0; r < ROWS; r++) {
+                                const u32 pi = __shfl_sync(FULL, xcur, r * XPR + (int)(j - jb));
+                                if (j < cnt[r] && cv)
+                                    g[r] = V::ld_nc(vals + (size_t)pi * D + c * VEC);
+                            }
+#pragma unroll
+                            for (int r = 0; r < ROWS; r++)
+                                if (j < cnt[r] && cv)
+                                    acc[r] = fv.step(acc[r], g[r]);
+                        }
+                    }
+#pragma unroll
+                    for (int r = 0; r < ROWS; r++)
+                        if (ok[r] && cv)
+                            fv.store(ctx[r], c, acc[r]);
+                }
+            }
+            t_cur = t_next;
+            it_cur = it_next;
+        }
     }
     if (trace && blockIdx.x < kTraceCtas) {
         __syncthreads();
-        if (threadIdx.x == 0)
+        if (threadIdx.x == 0) {
             trace[2 + 4 * blockIdx.x + 2] = global_timer_ns();
+            if (!hot_on)
+                trace[2 + 4 * blockIdx.x + 1] = trace[2 + 4 * blockIdx.x];
+        }
     }
-    fv.kernel_end();
 }
 
 // ---- one warp per listed row: f.begin(r); f.apply(r, c) per column chunk; f.end(r) -------------

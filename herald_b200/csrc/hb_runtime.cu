@@ -34,7 +34,7 @@ int hot_stages() {
     static const int stages = [] {
         const char *e = getenv("HERALD_HOT_STAGES");
         int v = e ? atoi(e) : kHotStagesDefault;
-        return std::min(std::max(v, 3), kHotStagesMax);
+        return std::min(std::max(v, 2), kHotStagesMax);
     }();
     return stages;
 }
@@ -42,8 +42,17 @@ int hot_stages() {
 u32 ticket_rows() {
     static const u32 rows = [] {
         const char *e = getenv("HERALD_TICKET_ROWS");
-        int v = e ? atoi(e) : 16; // measured: 16 rows per ticket balance the tail best (0.114 vs 0.119 ms)
+        int v = e ? atoi(e) : 8; // the next ticket's work items are prefetched, so tickets can be small
         return (u32)std::min(std::max(v, 4), 32);
+    }();
+    return rows;
+}
+
+u32 medium_threshold() {
+    static const u32 rows = [] {
+        const char *e = getenv("HERALD_MED_THRESHOLD");
+        int v = e ? atoi(e) : (int)kMediumDefault;
+        return (u32)std::max(v, 1);
     }();
     return rows;
 }

@@ -15,8 +15,6 @@ constexpr u32 kDefaultHotThreshold = 64;
 // ordinary-sized batches through the hot path
 u32 default_hot_threshold();
 
-// f1 / f4: the same functor instantiated for VEC = 1 and VEC = 4; v4 selects the 128-bit cold
-// path.  `n` = number of values (upper bound of any segment length).
 template <class K>
 int persistent_grid(K kernel, size_t smem) {
     int per_sm = 0;
@@ -35,34 +33,45 @@ inline int seg_rows() {
     return rows;
 }
 
+inline u32 seg_mode() {
+    static const u32 mode = [] {
+        const char *e = getenv("HERALD_SEG_MODE");
+        return e ? (u32)atoi(e) : 0u;
+    }();
+    return mode;
+}
+
 template <int VEC, int ROWS, class FV, class F1>
 void launch_segment_reduce(KeyWorkspace &ws, const u32 *perm, const float *vals, size_t D, size_t n,
                            bool hot, u32 thr, const HotLists &hl, cudaStream_t st, FV fv, F1 f1) {
     auto k = segment_reduce_kernel<VEC, ROWS, FV, F1>;
     const size_t smem = hot_smem_bytes(hot_stages());
     static const int full = persistent_grid(k, smem);
-    const size_t chunks = (n + ticket_rows() - 1) / ticket_rows(); // upper bound of the cold tickets
-    int grid = (int)std::max<size_t>(1, std::min<size_t>(full, (chunks + kRowWarps - 1) / kRowWarps));
-    HB_LAUNCH(k, hot ? full : grid, kRowBlock, smem, st, ws.seg_start, perm, ws.num_unique, vals, D, thr, hl,
-                                                  fv, f1);
+    // one warp per cold ticket (upper bound) or medium row
+    const size_t units = (n + ticket_rows() - 1) / ticket_rows() + n / (medium_threshold() + 1);
+    int grid = (int)std::max<size_t>(1, std::min<size_t>(full, (units + kRowWarps - 1) / kRowWarps));
+    HB_LAUNCH(k, hot ? full : grid, kRowBlock, smem, st, perm, ws.num_unique, vals, D, thr, hl, fv, f1);
     HB_LAUNCHED();
 }
 
+// f1 / f4: the same functor instantiated for VEC = 1 and VEC = 4; v4 selects the 128-bit cold
+// path.  `n` = number of values (upper bound of any segment length).
 template <class F1, class F4>
 void run_segment_reduce(KeyWorkspace &ws, const u32 *perm, const float *vals, size_t D, size_t n,
                         bool v4, u32 hot_threshold, cudaStream_t st, F1 f1, F4 f4) {
     if (n == 0)
         return;
     const bool hot = n > hot_threshold;
-    HotLists hl{ws.hot_a, ws.hot_b, ws.hot_done_a, ws.hot_done_b, ws.hot_ctrl(), seg_trace_buffer(),
-                hot_stages(), ticket_rows()};
-    if (hot) {
-        int g = (int)std::min<size_t>((n + 255) / 256, (size_t)sm_count() * 4);
-        HB_LAUNCH(build_hot_lists_kernel, std::max(g, 1), 256, 0, st, ws.seg_start, ws.num_unique,
-                                                             hot_threshold, hl);
+    const u32 thr = hot ? hot_threshold : 0xffffffffu;
+    HotLists hl{ws.hot_a, ws.hot_b, ws.medium, ws.hot_ctrl(), ws.seg_items, seg_trace_buffer(),
+                hot_stages(), ticket_rows(), medium_threshold(), seg_mode()};
+    {   // open every unique row and lay the work items out in ticket order
+        const size_t total = n + ticket_rows();
+        int g = (int)std::min<size_t>((total + 255) / 256, (size_t)sm_count() * 8);
+        HB_LAUNCH(seg_plan_kernel<F4>, std::max(g, 1), 256, 0, st, ws.seg_start, perm, ws.num_unique, thr,
+                                                        hl, f4);
         HB_LAUNCHED();
     }
-    const u32 thr = hot ? hot_threshold : 0xffffffffu;
     const bool r4 = seg_rows() == 4;
     if (v4 && r4)
         launch_segment_reduce<4, 4>(ws, perm, vals, D, n, hot, thr, hl, st, f4, f1);

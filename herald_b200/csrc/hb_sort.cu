@@ -401,8 +401,12 @@ void KeyWorkspace::reserve(size_t n) {
     sorted_valid = false;
     dev_alloc(hot_a, c);
     dev_alloc(hot_b, c);
-    dev_alloc(hot_done_a, c);
-    dev_alloc(hot_done_b, c);
+    dev_alloc(medium, c);
+    {
+        char *p = nullptr;
+        dev_alloc(p, (c + 32) * 32); // kSegItemBytes per work item
+        seg_items = p;
+    }
     cap = c;
 }
 
@@ -420,8 +424,12 @@ void KeyWorkspace::release() {
     dev_free(scan_arena);
     dev_free(hot_a);
     dev_free(hot_b);
-    dev_free(hot_done_a);
-    dev_free(hot_done_b);
+    dev_free(medium);
+    {
+        char *p = reinterpret_cast<char *>(seg_items);
+        dev_free(p);
+        seg_items = nullptr;
+    }
     cap = 0;
 }
 

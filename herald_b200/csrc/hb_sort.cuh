@@ -33,11 +33,11 @@ struct KeyWorkspace {
     u32 *inverse = nullptr;   // [cap]   rank of keys[i] in uniq
     u32 *seg_start = nullptr; // [cap+1] first sorted position of each unique key
     u32 *num_unique = nullptr; // device scalar
-    // hot-segment work lists (see hb_rows.cuh); the control words live behind the scan arena so
-    // that reset_scans() zeroes them with the same memset
-    u32 *hot_a = nullptr, *hot_b = nullptr; // [cap]
-    u32 *hot_done_a = nullptr, *hot_done_b = nullptr; // [cap] finished chunks per hot row
-    // scan arena: kScanSlots x (ticket + status[ntile_cap]), then 2 control words (hot lists),
+    // segment-reduce work lists and work items (see hb_rows.cuh); the control words live behind the
+    // scan arena so that reset_scans() zeroes them with the same memset
+    u32 *hot_a = nullptr, *hot_b = nullptr, *medium = nullptr; // [cap] item indices
+    void *seg_items = nullptr; // [cap + 32] x 32 B, ticket order
+    // scan arena: kScanSlots x (ticket + status[ntile_cap]), then 4 control words (work lists),
     // then the sort's digit totals [kMaxSortPasses][RADIX] and its per-pass tile tickets
     u64 *scan_arena = nullptr;
     size_t ntile_cap = 0;
@@ -49,14 +49,14 @@ struct KeyWorkspace {
         return ntile_cap + 1;
     }
     size_t arena_words() const {
-        return (size_t)kScanSlots * scan_slot_words() + 2 + (kMaxSortPasses * kSortRadix) / 2 +
+        return (size_t)kScanSlots * scan_slot_words() + 4 + (kMaxSortPasses * kSortRadix) / 2 +
                kMaxSortPasses / 2 + 1;
     }
-    u32 *hot_ctrl() const { // 4 x u32
+    u32 *hot_ctrl() const { // 8 x u32
         return reinterpret_cast<u32 *>(scan_arena + (size_t)kScanSlots * scan_slot_words());
     }
     u32 *sort_totals() const {
-        return hot_ctrl() + 4;
+        return hot_ctrl() + 8;
     }
     u32 *sort_tickets() const {
         return sort_totals() + kMaxSortPasses * kSortRadix;

@@ -47,6 +47,9 @@ def module():
         _lib.oracle_read_rows.argtypes = [ctypes.c_int, ctypes.c_void_p]
         _lib.oracle_read_versions.argtypes = [ctypes.c_int, ctypes.c_void_p]
         _lib.oracle_clear_table.argtypes = [ctypes.c_int]
+        _lib.oracle_read_rows_at.argtypes = [ctypes.c_int, ctypes.c_void_p, sz, ctypes.c_void_p,
+                                             ctypes.c_void_p]
+        _lib.oracle_add_rows_at.argtypes = [ctypes.c_int, ctypes.c_void_p, sz, ctypes.c_void_p]
     return _mod
 
 
@@ -79,6 +82,27 @@ class Server:
         out = np.empty(self.length, np.int64)
         _lib.oracle_read_versions(self.id, out.ctypes.data)
         return out
+
+    # ---- selected rows only: tables too large to copy whole (bench-scale parity) ------------
+    def rows_at(self, keys):
+        """(rows, versions) of ascending `keys` as a never-synced worker would be sent them."""
+        keys = np.ascontiguousarray(keys, np.uint64).reshape(-1)
+        assert keys.size < 2 or bool(np.all(keys[1:] > keys[:-1])), "ascending unique keys"
+        rows = np.empty((keys.size, self.width), np.float32)
+        ver = np.empty(keys.size, np.int64)
+        if keys.size:
+            _lib.oracle_read_rows_at(self.id, keys.ctypes.data, keys.size, rows.ctypes.data,
+                                     ver.ctypes.data)
+        return rows, ver
+
+    def load_rows_at(self, keys, rows):
+        """rows[keys] += given rows (SparsePush): on a zero-initialised table this loads them."""
+        keys = np.ascontiguousarray(keys, np.uint64).reshape(-1)
+        assert keys.size < 2 or bool(np.all(keys[1:] > keys[:-1])), "ascending unique keys"
+        rows = np.ascontiguousarray(rows, np.float32)
+        assert rows.shape == (keys.size, self.width)
+        if keys.size:
+            _lib.oracle_add_rows_at(self.id, keys.ctypes.data, keys.size, rows.ctypes.data)
 
     def close(self):
         if self.id is not None:

@@ -213,6 +213,56 @@ void oracle_read_versions(int id, int64_t *out) {
     }
 }
 
+// Rows / versions of SELECTED keys (ascending, global row ids) through the sync protocol with
+// "never synced" clients: what a fresh worker would be sent.  Nothing on the server changes.
+void oracle_read_rows_at(int id, const uint64_t *keys, size_t n, float *out_rows,
+                         int64_t *out_ver) {
+    const ps::TableMeta &meta = ps::g_meta.at(id);
+    ::SArray<uint64_t> k(n);
+    for (size_t i = 0; i < n; i++)
+        k[i] = keys[i];
+    ps::for_each_range(meta, k, [&](size_t s, size_t start, size_t end, size_t base) {
+        if (start == end)
+            return;
+        ::SArray<ps::version_t> ver(end - start);
+        for (size_t i = 0; i < end - start; i++)
+            ver[i] = -1;
+        ps::PSFData<ps::kSyncEmbedding>::Request req((ps::Key)id, ps::rebased(k, start, end, base),
+                                                     ver, 0);
+        ps::PSFData<ps::kSyncEmbedding>::Response resp;
+        ps::server(s).serve(req, resp);
+        auto &idx = std::get<0>(resp);
+        auto &rv = std::get<1>(resp);
+        auto &rows = std::get<2>(resp);
+        for (size_t j = 0; j < idx.size(); j++) {
+            const size_t pos = start + idx[j];
+            if (out_ver)
+                out_ver[pos] = rv[j];
+            if (out_rows)
+                std::copy(rows.begin() + j * meta.width, rows.begin() + (j + 1) * meta.width,
+                          out_rows + pos * meta.width);
+        }
+    });
+}
+
+// rows[keys[i], :] += vals[i, :] (SparsePush).  On a zero-initialised table this LOADS exact rows
+// at the given keys without materialising the whole table on the Python side.
+void oracle_add_rows_at(int id, const uint64_t *keys, size_t n, const float *vals) {
+    const ps::TableMeta &meta = ps::g_meta.at(id);
+    ::SArray<uint64_t> k(n);
+    for (size_t i = 0; i < n; i++)
+        k[i] = keys[i];
+    ps::for_each_range(meta, k, [&](size_t s, size_t start, size_t end, size_t base) {
+        if (start == end)
+            return;
+        ::SArray<float> v((end - start) * meta.width);
+        std::copy(vals + start * meta.width, vals + end * meta.width, v.begin());
+        ps::PSFData<ps::SparsePush>::Request req((ps::Key)id, ps::rebased(k, start, end, base), v);
+        ps::PSFData<ps::SparsePush>::Response resp;
+        ps::server(s).serve(req, resp);
+    });
+}
+
 void oracle_clear_table(int id) {
     auto it = ps::g_meta.find(id);
     if (it == ps::g_meta.end())

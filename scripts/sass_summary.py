@@ -29,7 +29,8 @@ for line in sass.splitlines():
     for key, pat in (("LDG.128", r"\bLDG\.E[\w.]*\.128"), ("STG.128", r"\bSTG\.E[\w.]*\.128"),
                      ("LDGSTS", r"\bLDGSTS"), ("ACQBULK", r"\bACQBULK"), ("PREEXIT", r"\bPREEXIT"),
                      ("LDL", r"\bLDL\b"), ("STL", r"\bSTL\b"), ("ATOMG/RED", r"\b(ATOMG|RED)\."),
-                     ("VOTE", r"\bVOTE\."), ("BAR", r"\bBAR\.")):
+                     ("VOTE", r"\bVOTE\."), ("BAR", r"\bBAR\."), ("SYNCS", r"\bSYNCS\."),
+                     ("UBLKCP", r"\bUBLKCP"), ("ARRIVES", r"\bARRIVES\.")):
         if re.search(pat, line):
             counts[cur][key] += 1
 def demangle(n):
@@ -37,7 +38,8 @@ def demangle(n):
         return subprocess.run(["c++filt", n], capture_output=True, text=True).stdout.strip()
     except Exception:
         return n
-cols = ["LDG.128", "STG.128", "LDGSTS", "ACQBULK", "PREEXIT", "LDL", "STL", "ATOMG/RED", "VOTE", "BAR"]
+cols = ["LDG.128", "STG.128", "LDGSTS", "ACQBULK", "PREEXIT", "LDL", "STL", "ATOMG/RED", "VOTE", "BAR", "SYNCS",
+        "UBLKCP", "ARRIVES"]
 print("%-78s %4s %5s %6s %5s | %s" % ("kernel", "regs", "stack", "smem", "local", " ".join("%9s" % c for c in cols)))
 for fn in sorted(counts, key=demangle):
     name = re.sub(r"\(anonymous namespace\)::|hb::", "", demangle(fn))
