@@ -139,6 +139,7 @@ __device__ __forceinline__ u64 make_prio(u32 use, u64 stamp) {
 __global__ void op_begin_kernel(CacheRegs *r, u64 *clk, int flush) {
     pdl_enter();
     r->clock0 = r->clock;
+    r->error = 0; // the previous call's failure has been reported in its own record
     clk[0] = r->clock;
     clk[1] = clk[2] = clk[3] = r->clock;
     r->U = r->M = r->alloc_base = 0;
@@ -1686,10 +1687,17 @@ u64 *clk_of(hb_cache *c) {
     return reinterpret_cast<u64 *>(reinterpret_cast<char *>(c->dev_record) + 64);
 }
 
+void sync_all(hb_cache *c) {
+    HB_CUDA(cudaStreamSynchronize(c->side));
+    HB_CUDA(cudaStreamSynchronize(c->h2d));
+    HB_CUDA(cudaStreamSynchronize(c->stream));
+    HB_CUDA(cudaStreamSynchronize(c->d2h));
+}
+
 void ensure_batch(hb_cache *c, size_t n) {
     if (n <= c->batch_cap)
         return;
-    HB_CUDA(cudaStreamSynchronize(c->stream));
+    sync_all(c);
     size_t cap = std::max<size_t>(n, 4096);
     for (int b = 0; b < 2; b++) {
         c->ws[b].reserve(cap);
@@ -1706,7 +1714,7 @@ void ensure_batch(hb_cache *c, size_t n) {
 void ensure_keys_stage(hb_cache *c, size_t n) {
     if (n * 8 <= c->keys_stage_cap)
         return;
-    HB_CUDA(cudaStreamSynchronize(c->stream));
+    sync_all(c);
     size_t cap = std::max<size_t>(n, 4096) * 8;
     for (int b = 0; b < 2; b++) {
         if (c->keys_stage[b])
@@ -1717,20 +1725,21 @@ void ensure_keys_stage(hb_cache *c, size_t n) {
     c->keys_stage_cap = cap;
 }
 
-// keys as given by the caller -> device pointer (staged when they live in host memory)
+// keys as given by the caller -> device pointer (staged when they live in host memory).  Only the
+// sort reads the raw keys, so the copy goes to the side stream, in front of it.
 const void *stage_keys(hb_cache *c, const void *keys, int kind, size_t n, int which) {
     if (n == 0 || is_device_ptr(keys))
         return keys;
     size_t bytes = n * (kind == HB_KEYS_F32 ? 4 : 8);
     HB_CHECK(bytes <= c->keys_stage_cap, "key staging buffer not reserved");
-    HB_CUDA(cudaMemcpyAsync(c->keys_stage[which], keys, bytes, cudaMemcpyHostToDevice, c->stream));
+    HB_CUDA(cudaMemcpyAsync(c->keys_stage[which], keys, bytes, cudaMemcpyHostToDevice, c->side));
     return c->keys_stage[which];
 }
 
 float *rows_stage(hb_cache *c, size_t n, int which) {
     size_t need = n * c->width;
     if (need > c->rows_stage_cap[which]) {
-        HB_CUDA(cudaStreamSynchronize(c->stream));
+        sync_all(c);
         dfree(c->rows_stage[which]);
         dmalloc(c->rows_stage[which], need);
         c->rows_stage_cap[which] = need;
@@ -1785,17 +1794,49 @@ void mark(hb_cache *c, int k) {
     c->phase_mask[idx] |= 1u << k;
 }
 
-void begin_call(hb_cache *c, bool flush = false, int batches = 1) {
+// Side stream: sort + unique of one key batch into workspace `wsi`.  `check`: the batch may be the
+// one the workspace already holds sorted (Hetu's BSP loop updates the batch it looked up one call
+// earlier, ParameterServerCommunicate.py:48-52) — then an exact device-side comparison runs first
+// and the sort kernels return at once when it finds no difference.
+void presort(hb_cache *c, const void *dev_keys, int kind, size_t n, int wsi, bool check) {
+    KeyWorkspace &ws = c->ws[wsi];
+    cudaStream_t sd = c->side;
+    c->cur_ticks += n;
+    ws.reset_side(sd);
+    const u32 *same = check ? check_same_keys(ws, dev_keys, kind, n, sd) : nullptr;
+    // the kernels below rewrite the workspace: its main-stream readers enqueued so far must be done
+    // (the comparison above only reads it, and what it reads was written on this stream)
+    HB_CUDA(cudaStreamWaitEvent(sd, c->ev_ws_free[wsi], 0));
+    SortedKeys sk{nullptr, nullptr};
+    if (n)
+        sk = radix_sort_keys(ws, dev_keys, kind, n, c->key_bits, sd, same);
+    c->sorted[wsi] = sk;
+    unique_from_sorted(ws, sk, n, sd, same);
+    ws.sorted_valid = n > 0;
+    ws.sorted_n = n;
+    HB_CUDA(cudaEventRecord(c->ev_sorted[wsi], sd));
+}
+
+// Call boundary on the main stream.  Everything that is not a kernel (memsets, event records and
+// waits) is gathered here: between two kernels it would cost their launch overlap (PDL).
+// ws_a / ws_b: workspaces the call's kernels read (their presort must have finished); -1 = none.
+void begin_call(hb_cache *c, bool flush, int ws_a, int ws_b = -1) {
     int idx = (int)(c->calls % hb_cache::kRing);
     c->phase_mask[idx] = 0;
-    // the scan arenas of the workspaces this call uses are zeroed here, next to the other
-    // non-kernel stream operations of a call boundary: a memset between two kernels would cost
-    // their launch overlap
-    for (int b = 0; b < batches; b++)
-        c->ws[b].reset_scans(c->stream);
+    c->dl_of_call[idx] = 0;
+    for (int w : {ws_a, ws_b})
+        if (w >= 0) {
+            c->ws[w].reset_main(c->stream);
+            HB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_sorted[w], 0));
+        }
     HB_CUDA(cudaEventRecord(c->ev_begin[idx], c->stream));
     HB_LAUNCH(op_begin_kernel, 1, 1, 0, c->stream, c->view.regs, clk_of(c), flush ? 1 : 0);
     HB_LAUNCHED();
+}
+
+// the main-stream readers of workspace `wsi` enqueued so far end here
+void release_ws(hb_cache *c, int wsi) {
+    HB_CUDA(cudaEventRecord(c->ev_ws_free[wsi], c->stream));
 }
 
 void end_call(hb_cache *c, int last_stage, u32 kind, size_t n, bool inserted) {
@@ -1812,20 +1853,11 @@ void end_call(hb_cache *c, int last_stage, u32 kind, size_t n, bool inserted) {
     c->incoming_ring[c->calls % hb_cache::kRing] = 0;
 }
 
-// sort + unique + resolve (+ alloc) of one key batch
-void resolve_batch(hb_cache *c, const void *dev_keys, int kind, size_t n, int batch, bool dataless,
-                   int clk_stage, bool marks = true) {
-    KeyWorkspace &ws = c->ws[batch];
+// resolve (+ alloc) of the batch workspace `wsi` holds; `batch` = which counter set of the call
+void resolve_batch(hb_cache *c, size_t n, int batch, int wsi, bool dataless, int clk_stage,
+                   bool marks = true) {
+    KeyWorkspace &ws = c->ws[wsi];
     cudaStream_t st = c->stream;
-    c->cur_ticks += n;
-    SortedKeys sk{nullptr, nullptr};
-    const u32 *same = check_same_keys(ws, dev_keys, kind, n, st);
-    if (n)
-        sk = radix_sort_keys(ws, dev_keys, kind, n, c->key_bits, st, same);
-    c->sorted[batch] = sk;
-    unique_from_sorted(ws, sk, n, st, same);
-    ws.sorted_valid = n > 0;
-    ws.sorted_n = n;
     if (marks)
         mark(c, 0);
     u32 ntiles = (u32)std::max(1, ceil_div(n, kScanBlock * kResolveItems));
@@ -1848,23 +1880,23 @@ bool vec4(const hb_cache *c, const void *user_rows) {
     return c->width % 4 == 0 && reinterpret_cast<uintptr_t>(user_rows) % 16 == 0;
 }
 
-void run_sync(hb_cache *c, size_t n) {
+void run_sync(hb_cache *c, size_t n, int wsi) {
     if (!n)
         return;
     int grid = row_grid((n + 31) / 32);
     if (c->width % 4 == 0)
-        HB_LAUNCH((sync_kernel<4, 4>), grid, kRowBlock, 0, c->stream, c->view, c->ws[0].uniq, c->uslot[0],
+        HB_LAUNCH((sync_kernel<4, 4>), grid, kRowBlock, 0, c->stream, c->view, c->ws[wsi].uniq, c->uslot[0],
                                                              c->pull_bound);
     else
-        HB_LAUNCH((sync_kernel<1, 4>), grid, kRowBlock, 0, c->stream, c->view, c->ws[0].uniq, c->uslot[0],
+        HB_LAUNCH((sync_kernel<1, 4>), grid, kRowBlock, 0, c->stream, c->view, c->ws[wsi].uniq, c->uslot[0],
                                                              c->pull_bound);
     HB_LAUNCHED();
 }
 
-void run_gather(hb_cache *c, size_t n, float *dev_dest) {
+void run_gather(hb_cache *c, size_t n, int wsi, float *dev_dest) {
     if (!n)
         return;
-    IndexFromSlots idx{c->uslot[0], c->ws[0].inverse};
+    IndexFromSlots idx{c->uslot[0], c->ws[wsi].inverse};
     int grid = row_grid((n + 3) / 4);
     if (vec4(c, dev_dest))
         HB_LAUNCH((gather_rows_kernel<4, 4, IndexFromSlots>), grid, kRowBlock, 0, c->stream, c->view.data, dev_dest, n, c->width, idx);
@@ -1955,16 +1987,16 @@ void exchange_pushes(hb_cache *c) {
 }
 
 // accumulate + push of batch `batch`, then flush of pending victims, then drop dataless lines
-void run_accumulate(hb_cache *c, size_t n, int batch, const float *dev_grads, const u64 *dev_push_keys,
-                    size_t n_push, bool use_plan, bool defer_cleanup = false) {
+void run_accumulate(hb_cache *c, size_t n, int batch, int wsi, const float *dev_grads,
+                    const u64 *dev_push_keys, size_t n_push, bool use_plan, bool defer_cleanup = false) {
     cudaStream_t st = c->stream;
-    KeyWorkspace &ws = c->ws[batch];
+    KeyWorkspace &ws = c->ws[wsi];
     if (c->view.pv.world > 1) {
         HB_LAUNCH(owner_bounds_kernel, 1, 32, 0, st, c->view, ws.uniq, ws.num_unique);
         HB_LAUNCHED();
     }
     if (n) {
-        const u32 *p = c->sorted[batch].perm;
+        const u32 *p = c->sorted[wsi].perm;
         const u64 *plan = use_plan ? dev_push_keys : nullptr;
         u32 plan_n = (u32)n_push;
         if (use_plan && !dev_push_keys) { // empty plan: nothing is pushed
@@ -2037,24 +2069,37 @@ const u64 *stage_push_keys(hb_cache *c, const void *push_keys, int kind, size_t 
     return reinterpret_cast<const u64 *>(dev);
 }
 
+// gradients as given by the caller -> device pointer.  Host gradients travel on the upload stream
+// (behind the previous consumer of the staging buffer); the main stream waits for them at the call
+// boundary (begin_call follows).
+const float *stage_grads(hb_cache *c, const float *grads, size_t n) {
+    if (!n || is_device_ptr(grads))
+        return grads;
+    float *stage = rows_stage(c, n, 2);
+    HB_CUDA(cudaStreamWaitEvent(c->h2d, c->ev_grads_free, 0));
+    HB_CUDA(cudaMemcpyAsync(stage, grads, n * c->width * sizeof(float), cudaMemcpyHostToDevice, c->h2d));
+    HB_CUDA(cudaEventRecord(c->ev_up, c->h2d));
+    HB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_up, 0));
+    return stage;
+}
+
 void do_update(hb_cache *c, const void *keys, int kind, size_t n, const float *grads,
                const void *push_keys, int push_kind, size_t n_push, bool use_plan) {
     Guard g(c->device);
     ensure_batch(c, n);
     ensure_keys_stage(c, n);
-    cudaStream_t st = c->stream;
+    const int w = c->cur; // the workspace of the most recent lookup: usually this very batch
     const void *dkeys = stage_keys(c, keys, kind, n, 0);
-    const float *dgrads = grads;
-    if (n && !is_device_ptr(grads)) {
-        float *stage = rows_stage(c, n, 1);
-        HB_CUDA(cudaMemcpyAsync(stage, grads, n * c->width * sizeof(float), cudaMemcpyHostToDevice, st));
-        dgrads = stage;
-    }
+    presort(c, dkeys, kind, n, w, /*check=*/true);
+    const float *dgrads = stage_grads(c, grads, n);
     const u64 *dpush = use_plan ? stage_push_keys(c, push_keys, push_kind, n_push) : nullptr;
-    begin_call(c, /*flush=*/true);
-    resolve_batch(c, dkeys, kind, n, 0, /*dataless=*/true, 0);
-    run_accumulate(c, n, 0, dgrads, dpush, n_push, use_plan);
+    begin_call(c, /*flush=*/true, w);
+    resolve_batch(c, n, 0, w, /*dataless=*/true, 0);
+    run_accumulate(c, n, 0, w, dgrads, dpush, n_push, use_plan);
     end_call(c, 1, 1, n, false);
+    release_ws(c, w);
+    if (dgrads != grads)
+        HB_CUDA(cudaEventRecord(c->ev_grads_free, c->stream));
 }
 
 } // namespace
@@ -2219,6 +2264,13 @@ int hb_cache_create(int policy, size_t limit, size_t length, size_t width, int n
     c->key_bits = bits_for(std::max<size_t>(length, t->length));
     c->hot_threshold = default_hot_threshold();
     HB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    HB_CUDA(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
+    HB_CUDA(cudaStreamCreateWithFlags(&c->h2d, cudaStreamNonBlocking));
+    HB_CUDA(cudaStreamCreateWithFlags(&c->d2h, cudaStreamNonBlocking));
+    for (cudaEvent_t *e : {&c->ev_ws_free[0], &c->ev_ws_free[1], &c->ev_sorted[0], &c->ev_sorted[1],
+                           &c->ev_up, &c->ev_grads_free, &c->ev_gathered[0], &c->ev_gathered[1],
+                           &c->ev_dl[0], &c->ev_dl[1]})
+        HB_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
     // row store: limit resident lines + slack for the running call's fresh lines and for dirty
     // victims waiting for the next push
     c->slack = std::max<size_t>(1 << 16, std::min<size_t>(limit, 1 << 22));
@@ -2329,7 +2381,7 @@ int hb_cache_destroy(hb_cache *c) {
     HB_API_BEGIN();
     if (c) {
         Guard g(c->device);
-        HB_CUDA(cudaStreamSynchronize(c->stream));
+        sync_all(c);
         CacheView &v = c->view;
         dfree(v.slot_key);
         dfree(v.slot_version);
@@ -2363,8 +2415,9 @@ int hb_cache_destroy(hb_cache *c) {
             dfree(c->miss_list[b]);
             if (c->keys_stage[b])
                 cudaFree(c->keys_stage[b]);
-            dfree(c->rows_stage[b]);
         }
+        for (int b = 0; b < 3; b++)
+            dfree(c->rows_stage[b]);
         if (c->push_keys_stage)
             cudaFree(c->push_keys_stage);
         cudaFree(c->dev_record);
@@ -2375,7 +2428,14 @@ int hb_cache_destroy(hb_cache *c) {
             cudaEventDestroy(e);
         for (auto &e : c->ev_phase)
             cudaEventDestroy(e);
+        for (cudaEvent_t e : {c->ev_ws_free[0], c->ev_ws_free[1], c->ev_sorted[0], c->ev_sorted[1],
+                              c->ev_up, c->ev_grads_free, c->ev_gathered[0], c->ev_gathered[1],
+                              c->ev_dl[0], c->ev_dl[1]})
+            cudaEventDestroy(e);
         cudaStreamDestroy(c->stream);
+        cudaStreamDestroy(c->side);
+        cudaStreamDestroy(c->h2d);
+        cudaStreamDestroy(c->d2h);
         delete c;
     }
     HB_API_END();
@@ -2418,7 +2478,7 @@ int hb_cache_reserve(hb_cache *c, size_t max_keys) {
     Guard g(c->device);
     ensure_batch(c, max_keys);
     if (c->view.pv.world > 1 && max_keys > c->mailbox_cap) {
-        HB_CUDA(cudaStreamSynchronize(c->stream));
+        sync_all(c);
         setup_mailbox(c, max_keys); // collective
     }
     HB_API_END();
@@ -2430,6 +2490,32 @@ int hb_cache_stream(hb_cache *c, void **stream) {
     HB_API_END();
 }
 
+// dest of a lookup: the caller's device buffer, or one of two device staging buffers from which
+// the download stream copies to the caller's host buffer.  *k = staging buffer (-1: none); the main
+// stream is made to wait until the previous download out of that buffer has finished.
+static float *stage_dest(hb_cache *c, float *dest, size_t n, int *k) {
+    *k = -1;
+    if (!n || is_device_ptr(dest))
+        return dest;
+    *k = c->dl_next;
+    c->dl_next ^= 1;
+    float *d = rows_stage(c, n, *k);
+    HB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_dl[*k], 0));
+    return d;
+}
+
+// after the gather: hand the staged rows to the download stream
+static void download_dest(hb_cache *c, float *dest, const float *ddest, size_t n, int k) {
+    if (k < 0)
+        return;
+    HB_CUDA(cudaEventRecord(c->ev_gathered[k], c->stream));
+    HB_CUDA(cudaStreamWaitEvent(c->d2h, c->ev_gathered[k], 0));
+    HB_CUDA(cudaMemcpyAsync(dest, ddest, n * c->width * sizeof(float), cudaMemcpyDeviceToHost, c->d2h));
+    HB_CUDA(cudaEventRecord(c->ev_dl[k], c->d2h));
+    c->dl_of_call[c->calls % hb_cache::kRing] = k + 1;
+    c->dl_seq[k] = c->calls + 1;
+}
+
 int hb_cache_lookup(hb_cache *c, const void *keys, int key_kind, size_t n, float *dest) {
     HB_API_BEGIN();
     Guard g(c->device);
@@ -2437,21 +2523,25 @@ int hb_cache_lookup(hb_cache *c, const void *keys, int key_kind, size_t n, float
     ensure_batch(c, n);
     ensure_keys_stage(c, n);
     maybe_rebuild_index(c, n);
+    // a lookup sorts into the workspace the previous lookup did NOT use: that one usually still
+    // serves the update of its batch (same keys, no second sort)
+    const int w = c->cur ^ 1;
     const void *dkeys = stage_keys(c, keys, key_kind, n, 0);
-    bool host_dest = n && !is_device_ptr(dest);
-    float *ddest = host_dest ? rows_stage(c, n, 0) : dest;
-    begin_call(c);
-    resolve_batch(c, dkeys, key_kind, n, 0, /*dataless=*/false, 0);
-    run_sync(c, n);
+    presort(c, dkeys, key_kind, n, w, /*check=*/false);
+    c->cur = w;
+    int k;
+    float *ddest = stage_dest(c, dest, n, &k);
+    begin_call(c, false, w);
+    resolve_batch(c, n, 0, w, /*dataless=*/false, 0);
+    run_sync(c, n, w);
     mark(c, 2);
-    run_gather(c, n, ddest);
+    run_gather(c, n, w, ddest);
     mark(c, 3);
+    release_ws(c, w); // the insert phase works on slots, not on the workspace
+    download_dest(c, dest, ddest, n, k);
     run_insert(c, n, 1);
     c->pending_upper += n;
     end_call(c, 2, 0, n, true);
-    if (host_dest)
-        HB_CUDA(cudaMemcpyAsync(dest, ddest, n * c->width * sizeof(float), cudaMemcpyDeviceToHost,
-                                c->stream));
     HB_API_END();
 }
 
@@ -2480,25 +2570,28 @@ int hb_cache_push_pull(hb_cache *c, const void *pull_keys, int pull_kind, size_t
     ensure_keys_stage(c, std::max(n_pull, n_push));
     maybe_rebuild_index(c, n_pull);
     cudaStream_t st = c->stream;
-    const void *dpull = stage_keys(c, pull_keys, pull_kind, n_pull, 0);
+    // the push batch is usually the previous call's pull batch (ASP prefetch,
+    // ParameterServerCommunicate.py:36-38): it is checked against that workspace; the pull batch
+    // goes to the other one
+    const int wpush = c->cur, wpull = c->cur ^ 1;
     const void *dpush = stage_keys(c, push_keys, push_kind, n_push, 1);
-    bool host_dest = n_pull && !is_device_ptr(dest);
-    float *ddest = host_dest ? rows_stage(c, n_pull, 0) : dest;
-    const float *dgrads = grads;
-    if (n_push && !is_device_ptr(grads)) {
-        float *stage = rows_stage(c, n_push, 1);
-        HB_CUDA(cudaMemcpyAsync(stage, grads, n_push * c->width * sizeof(float),
-                                cudaMemcpyHostToDevice, st));
-        dgrads = stage;
-    }
-    begin_call(c, /*flush=*/true, /*batches=*/2);
+    presort(c, dpush, push_kind, n_push, wpush, /*check=*/true);
+    const void *dpull = stage_keys(c, pull_keys, pull_kind, n_pull, 0);
+    presort(c, dpull, pull_kind, n_pull, wpull, /*check=*/false);
+    c->cur = wpull;
+    int k;
+    float *ddest = stage_dest(c, dest, n_pull, &k);
+    const float *dgrads = stage_grads(c, grads, n_push);
+    begin_call(c, /*flush=*/true, wpull, wpush);
     // cache.cc:360-391: pull-side lookup, then push-side lookup + accumulate
-    resolve_batch(c, dpull, pull_kind, n_pull, 0, /*dataless=*/false, 0, false);
-    resolve_batch(c, dpush, push_kind, n_push, 1, /*dataless=*/true, 1, false);
+    resolve_batch(c, n_pull, 0, wpull, /*dataless=*/false, 0, false);
+    resolve_batch(c, n_push, 1, wpush, /*dataless=*/true, 1, false);
     // server order (PSFhandle_embedding.cc:66-79): push first, then sync
-    run_accumulate(c, n_push, 1, dgrads, nullptr, 0, false, /*defer_cleanup=*/true);
-    run_sync(c, n_pull);
-    run_gather(c, n_pull, ddest);
+    run_accumulate(c, n_push, 1, wpush, dgrads, nullptr, 0, false, /*defer_cleanup=*/true);
+    run_sync(c, n_pull, wpull);
+    run_gather(c, n_pull, wpull, ddest);
+    release_ws(c, wpull);
+    download_dest(c, dest, ddest, n_pull, k);
     run_insert(c, n_pull, 2);
     if (n_push) {
         HB_LAUNCH(cleanup_pushed_kernel, lin_grid(n_push), 256, 0, st, c->view, c->uslot[1], c->push_bound);
@@ -2506,9 +2599,8 @@ int hb_cache_push_pull(hb_cache *c, const void *pull_keys, int pull_kind, size_t
     }
     c->pending_upper += n_pull;
     end_call(c, 3, 2, n_pull, true);
-    if (host_dest)
-        HB_CUDA(cudaMemcpyAsync(dest, ddest, n_pull * c->width * sizeof(float),
-                                cudaMemcpyDeviceToHost, st));
+    if (dgrads != grads)
+        HB_CUDA(cudaEventRecord(c->ev_grads_free, c->stream));
     HB_API_END();
 }
 
@@ -2644,10 +2736,31 @@ static void fill_perf(hb_cache *c, uint64_t call, hb_perf *perf) {
     }
 }
 
+// Report the device-side failures of the calls [c->err_checked, upto] that have not been reported
+// yet.  Every call's record carries its own error word (op_begin clears the device's), so a failed
+// call is reported once and the cache stays usable.
+static void check_errors(hb_cache *c, uint64_t upto) {
+    static const char *names[] = {"", "row store slack exhausted (too many transient/pending lines)",
+                                  "cache index full", "key outside the table",
+                                  "pending-eviction list overflow",
+                                  "owner mailbox too small (hb_cache_reserve / HERALD_MAILBOX_ROWS)",
+                                  "a peer did not reach the exchange barrier"};
+    uint64_t first = c->err_checked;
+    if (upto + 1 > first + hb_cache::kRing)
+        first = upto + 1 - hb_cache::kRing;
+    u32 err = 0;
+    for (uint64_t call = first; call <= upto; call++)
+        err = std::max(err, c->ring[call % hb_cache::kRing].error);
+    c->err_checked = upto + 1;
+    if (err)
+        throw Error(std::string("device-side cache failure: ") + names[std::min<u32>(err, 6)]);
+}
+
 int hb_cache_wait(hb_cache *c, hb_perf *perf) {
     HB_API_BEGIN();
     Guard g(c->device);
     HB_CUDA(cudaStreamSynchronize(c->stream));
+    HB_CUDA(cudaStreamSynchronize(c->d2h));
     if (c->calls) {
         int idx = (int)((c->calls - 1) % hb_cache::kRing);
         const PerfRecord &r = c->ring[idx];
@@ -2655,16 +2768,53 @@ int hb_cache_wait(hb_cache *c, hb_perf *perf) {
         c->pending_upper = std::max<size_t>(c->pending_upper, r.pending);
         if (perf)
             fill_perf(c, c->calls - 1, perf);
-        if (r.error) {
-            static const char *names[] = {"", "row store slack exhausted (too many transient/pending lines)",
-                                          "cache index full", "key outside the table",
-                                          "pending-eviction list overflow",
-                                          "owner mailbox too small (hb_cache_reserve / HERALD_MAILBOX_ROWS)",
-                                          "a peer did not reach the exchange barrier"};
-            throw Error(std::string("device-side cache failure: ") + names[std::min<u32>(r.error, 6)]);
-        }
+        check_errors(c, c->calls - 1);
     } else if (perf) {
         std::memset(perf, 0, sizeof(*perf));
+    }
+    HB_API_END();
+}
+
+int hb_cache_last_call(hb_cache *c, uint64_t *seq) {
+    HB_API_BEGIN();
+    HB_CHECK(c->calls > 0, "no call has been enqueued");
+    *seq = c->calls - 1;
+    HB_API_END();
+}
+
+int hb_cache_wait_call(hb_cache *c, uint64_t seq, hb_perf *perf) {
+    HB_API_BEGIN();
+    Guard g(c->device);
+    HB_CHECK(seq < c->calls, "no such call");
+    HB_CHECK(seq + hb_cache::kRing > c->calls, "call too old: its record has been overwritten");
+    const int idx = (int)(seq % hb_cache::kRing);
+    HB_CUDA(cudaEventSynchronize(c->ev_end[idx]));
+    if (const int k1 = c->dl_of_call[idx]) {
+        // the download stream is in order: an event recorded for a later call covers this one
+        HB_CUDA(cudaEventSynchronize(c->ev_dl[k1 - 1]));
+    }
+    if (seq + 1 == c->calls) {
+        const PerfRecord &r = c->ring[idx];
+        c->occ_upper = r.ht_occupied;
+        c->pending_upper = std::max<size_t>(c->pending_upper, r.pending);
+    }
+    if (perf)
+        fill_perf(c, seq, perf);
+    check_errors(c, seq);
+    HB_API_END();
+}
+
+int hb_cache_perf_range(hb_cache *c, uint64_t first, int count, hb_perf *out, int *kinds) {
+    HB_API_BEGIN();
+    Guard g(c->device);
+    HB_CHECK(count >= 0 && first + (uint64_t)count <= c->calls, "no such calls");
+    HB_CHECK(first + hb_cache::kRing >= c->calls, "calls too old: their records have been overwritten");
+    if (count)
+        HB_CUDA(cudaEventSynchronize(c->ev_end[(first + count - 1) % hb_cache::kRing]));
+    for (int k = 0; k < count; k++) {
+        fill_perf(c, first + k, &out[k]);
+        if (kinds)
+            kinds[k] = (int)c->ring[(first + k) % hb_cache::kRing].kind;
     }
     HB_API_END();
 }
@@ -2770,10 +2920,11 @@ int hb_cache_touch(hb_cache *c, uint64_t key, int *found, int64_t *version, floa
     HB_API_BEGIN();
     Guard g(c->device);
     ensure_batch(c, 1);
+    sync_all(c);
     cudaStream_t st = c->stream;
-    KeyWorkspace &ws = c->ws[0];
+    KeyWorkspace &ws = c->ws[c->cur];
     // a batched lookup of one key without the insert/sync half: CacheBase::lookup via python
-    begin_call(c);
+    begin_call(c, false, c->cur);
     ws.sorted_valid = false;
     HB_LAUNCH(single_key_kernel, 1, 1, 0, st, ws.uniq, ws.num_unique, key);
     HB_LAUNCHED();
@@ -2807,8 +2958,9 @@ int hb_cache_insert(hb_cache *c, uint64_t key, int64_t version, const float *dat
     Guard g(c->device);
     ensure_batch(c, 1);
     maybe_rebuild_index(c, 1);
+    sync_all(c);
     cudaStream_t st = c->stream;
-    float *ddata = rows_stage(c, 1, 1);
+    float *ddata = rows_stage(c, 1, 2);
     HB_CUDA(cudaMemcpyAsync(ddata, data, c->width * sizeof(float), cudaMemcpyDefault, st));
     PeekResult r = peek(c, key);
     if (r.slot >= 0) {
@@ -2819,8 +2971,8 @@ int hb_cache_insert(hb_cache *c, uint64_t key, int64_t version, const float *dat
             HB_LAUNCHED();
         }
     } else {
-        KeyWorkspace &ws = c->ws[0];
-        begin_call(c);
+        KeyWorkspace &ws = c->ws[c->cur];
+        begin_call(c, false, c->cur);
         ws.sorted_valid = false;
         HB_LAUNCH(single_key_kernel, 1, 1, 0, st, ws.uniq, ws.num_unique, key);
         HB_LAUNCHED();

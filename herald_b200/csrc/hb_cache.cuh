@@ -237,7 +237,22 @@ struct hb_cache {
     hb::i64 pull_bound = 5, push_bound = 5;
     bool bypass = false;
     hb_table *table = nullptr;
-    cudaStream_t stream = nullptr;
+    // Streams.  `stream` (main) orders every kernel that touches the cache; `side` runs the sort +
+    // unique of a batch (it depends on the keys only) while the main stream still works on the
+    // previous call; `h2d` / `d2h` move host callers' gradients in and gathered rows out, so that
+    // an upload, a download and the kernels of a third call can overlap (PCIe is full duplex).
+    cudaStream_t stream = nullptr, side = nullptr, h2d = nullptr, d2h = nullptr;
+    int cur = 0;                                // workspace that holds the most recent lookup batch
+    cudaEvent_t ev_ws_free[2] = {nullptr, nullptr}; // main: the readers of ws[i] enqueued so far are done
+    cudaEvent_t ev_sorted[2] = {nullptr, nullptr};  // side: ws[i] holds uniq / inverse / segments
+    cudaEvent_t ev_up = nullptr;                // h2d: the gradients of the running update have arrived
+    cudaEvent_t ev_grads_free = nullptr;        // main: the gradient staging buffer has been consumed
+    cudaEvent_t ev_gathered[2] = {nullptr, nullptr}; // main: dest staging buffer k is complete
+    cudaEvent_t ev_dl[2] = {nullptr, nullptr};       // d2h: download out of staging buffer k is done
+    int dl_next = 0;                            // dest staging buffer of the next host-dest lookup
+    int dl_of_call[1024] = {};                  // [kRing] 1 + staging buffer a call downloads from, 0 = none
+    uint64_t dl_seq[2] = {0, 0};                // call whose download ev_dl[k] stands for (+1)
+    uint64_t err_checked = 0;                   // calls whose error word has been reported
     hb::CacheView view{};
     size_t ht_size = 0;
     size_t slack = 0;
@@ -250,8 +265,8 @@ struct hb_cache {
     // staging for host-memory callers
     void *keys_stage[2] = {nullptr, nullptr};
     size_t keys_stage_cap = 0;
-    float *rows_stage[2] = {nullptr, nullptr};
-    size_t rows_stage_cap[2] = {0, 0};
+    float *rows_stage[3] = {nullptr, nullptr, nullptr}; // [0], [1]: gathered rows (ping-pong); [2]: gradients
+    size_t rows_stage_cap[3] = {0, 0, 0};
     void *push_keys_stage = nullptr;
     size_t push_keys_stage_cap = 0;
     // perf ring (pinned host) + events

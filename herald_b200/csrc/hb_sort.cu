@@ -398,6 +398,8 @@ void KeyWorkspace::reserve(size_t n) {
     ntile_cap = (c + kScanBlock - 1) / kScanBlock + 1;
     dev_alloc(scan_arena, arena_words());
     HB_CUDA(cudaMemset(scan_arena, 0, arena_words() * sizeof(u64)));
+    dev_alloc(side_arena, side_words());
+    HB_CUDA(cudaMemset(side_arena, 0, side_words() * sizeof(u64)));
     sorted_valid = false;
     dev_alloc(hot_a, c);
     dev_alloc(hot_b, c);
@@ -422,6 +424,7 @@ void KeyWorkspace::release() {
     dev_free(seg_start);
     dev_free(num_unique);
     dev_free(scan_arena);
+    dev_free(side_arena);
     dev_free(hot_a);
     dev_free(hot_b);
     dev_free(medium);
@@ -433,9 +436,20 @@ void KeyWorkspace::release() {
     cap = 0;
 }
 
-void KeyWorkspace::reset_scans(cudaStream_t st) {
+void KeyWorkspace::reset_main(cudaStream_t st) {
     HB_CUDA(cudaMemsetAsync(scan_arena, 0, arena_words() * sizeof(u64), st));
     scan_next = 0;
+}
+
+void KeyWorkspace::reset_side(cudaStream_t st) {
+    HB_CUDA(cudaMemsetAsync(side_arena, 0, side_words() * sizeof(u64), st));
+}
+
+ScanState KeyWorkspace::side_scan() const {
+    ScanState s;
+    s.ticket = reinterpret_cast<u32 *>(side_arena);
+    s.status = side_arena + 1;
+    return s;
 }
 
 ScanState KeyWorkspace::next_scan() {
@@ -514,7 +528,7 @@ void unique_from_sorted(KeyWorkspace &ws, const SortedKeys &sk, size_t n, cudaSt
     }
     u32 ntiles = (u32)ceil_div(n, UNIQ_TILE);
     HB_LAUNCH(unique_kernel, ntiles, kScanBlock, 0, st, sk.keys, sk.perm, n, ws.uniq, ws.inverse,
-                                                 ws.seg_start, ws.num_unique, ws.next_scan(),
+                                                 ws.seg_start, ws.num_unique, ws.side_scan(),
                                                  ntiles, mismatch);
     HB_LAUNCHED();
 }

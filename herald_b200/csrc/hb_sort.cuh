@@ -34,12 +34,17 @@ struct KeyWorkspace {
     u32 *seg_start = nullptr; // [cap+1] first sorted position of each unique key
     u32 *num_unique = nullptr; // device scalar
     // segment-reduce work lists and work items (see hb_rows.cuh); the control words live behind the
-    // scan arena so that reset_scans() zeroes them with the same memset
+    // main scan arena so that reset_main() zeroes them with the same memset
     u32 *hot_a = nullptr, *hot_b = nullptr, *medium = nullptr; // [cap] item indices
     void *seg_items = nullptr; // [cap + 32] x 32 B, ticket order
-    // scan arena: kScanSlots x (ticket + status[ntile_cap]), then 4 control words (work lists),
-    // then the sort's digit totals [kMaxSortPasses][RADIX] and its per-pass tile tickets
+    // main arena (zeroed by reset_main): kScanSlots x (ticket + status[ntile_cap]), then 4 control
+    // words (work lists of the segment reduce)
     u64 *scan_arena = nullptr;
+    // side arena (zeroed by reset_side): everything the sort + unique kernels count in — the unique
+    // scan's slot, the sort's digit totals [kMaxSortPasses][RADIX], its per-pass tile tickets and
+    // the same-keys mismatch counter.  Separate from the main arena because the cache runs sort +
+    // unique on a side stream while the main stream still works on the previous batch.
+    u64 *side_arena = nullptr;
     size_t ntile_cap = 0;
     int scan_next = 0;
 
@@ -49,14 +54,16 @@ struct KeyWorkspace {
         return ntile_cap + 1;
     }
     size_t arena_words() const {
-        return (size_t)kScanSlots * scan_slot_words() + 4 + (kMaxSortPasses * kSortRadix) / 2 +
-               kMaxSortPasses / 2 + 1;
+        return (size_t)kScanSlots * scan_slot_words() + 4;
+    }
+    size_t side_words() const {
+        return scan_slot_words() + (kMaxSortPasses * kSortRadix) / 2 + kMaxSortPasses / 2 + 1;
     }
     u32 *hot_ctrl() const { // 8 x u32
         return reinterpret_cast<u32 *>(scan_arena + (size_t)kScanSlots * scan_slot_words());
     }
     u32 *sort_totals() const {
-        return hot_ctrl() + 8;
+        return reinterpret_cast<u32 *>(side_arena + scan_slot_words());
     }
     u32 *sort_tickets() const {
         return sort_totals() + kMaxSortPasses * kSortRadix;
@@ -73,9 +80,15 @@ struct KeyWorkspace {
             sort_epoch = 1;
         return sort_epoch;
     }
-    // zero every scan slot (one memset) — call once at the start of an op
-    void reset_scans(cudaStream_t st);
+    // zero the scan slots / the sort's counters — once per op, before the kernels that use them
+    void reset_main(cudaStream_t st);
+    void reset_side(cudaStream_t st);
+    void reset_scans(cudaStream_t st) { // both, for single-stream callers
+        reset_main(st);
+        reset_side(st);
+    }
     ScanState next_scan();
+    ScanState side_scan() const; // the unique kernel's scan state
 };
 
 struct SortedKeys {

@@ -49,6 +49,10 @@ def _proto():
                                                  _sz, _vp]
     L.hb_cache_push_pull.argtypes = [_vp, _vp, ctypes.c_int, _sz, _vp, _vp, ctypes.c_int, _sz, _vp]
     L.hb_cache_wait.argtypes = [_vp, ctypes.POINTER(hb_perf)]
+    L.hb_cache_last_call.argtypes = [_vp, ctypes.POINTER(ctypes.c_uint64)]
+    L.hb_cache_wait_call.argtypes = [_vp, ctypes.c_uint64, ctypes.POINTER(hb_perf)]
+    L.hb_cache_perf_range.argtypes = [_vp, ctypes.c_uint64, ctypes.c_int, ctypes.POINTER(hb_perf),
+                                      ctypes.POINTER(ctypes.c_int)]
     L.hb_cache_perf_history.argtypes = [_vp, ctypes.POINTER(hb_perf), ctypes.POINTER(ctypes.c_int),
                                         ctypes.c_int, ctypes.POINTER(ctypes.c_int)]
     L.hb_cache_size.argtypes = [_vp, ctypes.POINTER(_sz)]
@@ -72,16 +76,18 @@ def _check_c_contiguous(arr, what):
 
 
 class _waittype(object):
-    """Handle of an enqueued cache call (python_api.cc:16-19): ``wait()`` blocks until it — and
-    everything enqueued on the cache before it — has finished, then records the perf entry."""
+    """Handle of ONE enqueued cache call (python_api.cc:16-19): ``wait()`` blocks until that call
+    (for a lookup into host memory: including the download of its rows) has finished and records
+    the perf entries up to it.  Calls enqueued after it keep running, so a host caller can overlap
+    update(t+1)'s upload with lookup(t+1)'s download."""
 
-    def __init__(self, cache, keepalive):
+    def __init__(self, cache, keepalive, seq):
         self._cache = cache
         self._keep = keepalive
-        self._seq = cache._issued
+        self._seq = seq
 
     def wait(self):
-        self._cache._drain()
+        self._cache._drain(self._seq)
         self._keep = None
 
 
@@ -120,8 +126,7 @@ class CacheBase(object):
                                         self._width, self._node_id, ctypes.byref(self._h)))
         self._perf = []
         self._perf_enabled = False
-        self._issued = 0    # calls enqueued
-        self._recorded = 0  # calls whose perf entry has been collected
+        self._recorded = 0  # device calls [0, _recorded) have had their perf entry collected
 
     def __del__(self):
         h = getattr(self, "_h", None)
@@ -192,9 +197,9 @@ class CacheBase(object):
         lines) — not in the reference, whose ParamSave loses the updates still held in worker
         caches.  Call before SaveParam.  Synchronous."""
         self._drain()
+        first = self._last_call() + 1
         check_call(_LIB.hb_cache_flush(self._h))
-        self._issued += 1      # the flush runs one (empty) update call on the device
-        self._drain()
+        self._drain(skip_from=first)   # the flush runs one (empty) update call on the device
 
     @property
     def stream(self):
@@ -204,21 +209,37 @@ class CacheBase(object):
         return s.value
 
     # ---- completion / perf -------------------------------------------------------------
-    def _drain(self):
-        """Synchronise and collect the perf entries of finished calls (cache.cc:89-106,179-196)."""
-        if self._recorded == self._issued and self._issued:
+    def _last_call(self):
+        """Sequence number of the device call enqueued last, -1 if there is none."""
+        seq = ctypes.c_uint64()
+        if _LIB.hb_cache_last_call(self._h, ctypes.byref(seq)) != 0:
+            return -1
+        return int(seq.value)
+
+    def _drain(self, upto=None, skip_from=None):
+        """Wait for device call `upto` (default: everything enqueued) and collect the perf entries
+        of the calls finished by then (cache.cc:89-106,179-196).  Calls from `skip_from` on are
+        internal (flush) and leave no entry."""
+        if upto is None:
+            check_call(_LIB.hb_cache_wait(self._h, None))
+            upto = self._last_call()
+        else:
+            check_call(_LIB.hb_cache_wait_call(self._h, int(upto), None))
+        pending = upto + 1 - self._recorded
+        if pending <= 0:
             return
-        last = hb_perf()
-        check_call(_LIB.hb_cache_wait(self._h, ctypes.byref(last)))
-        pending = self._issued - self._recorded
-        if pending and self._perf_enabled:
+        if self._perf_enabled:
+            first = self._recorded
+            if pending > 1024:          # hb_cache::kRing records are kept
+                first, pending = upto + 1 - 1024, 1024
             buf = (hb_perf * pending)()
             kinds = (ctypes.c_int * pending)()
-            got = ctypes.c_int()
-            check_call(_LIB.hb_cache_perf_history(self._h, buf, kinds, pending, ctypes.byref(got)))
-            for k in range(got.value):
+            check_call(_LIB.hb_cache_perf_range(self._h, first, pending, buf, kinds))
+            for k in range(pending):
                 p = buf[k]
                 if kinds[k] == 2:   # push_pull records nothing in the reference
+                    continue
+                if skip_from is not None and first + k >= skip_from:
                     continue
                 d = {"type": "Pull" if kinds[k] == 0 else "Push", "is_full": bool(p.is_full),
                      "num_all": int(p.num_all), "num_unique": int(p.num_unique),
@@ -233,11 +254,10 @@ class CacheBase(object):
                     d["num_evict"] = int(p.num_evict)
                     d["cleanup_time"] = 0.0
                 self._perf.append(d)
-        self._recorded = self._issued
+        self._recorded = upto + 1
 
     def _issue(self, *keepalive):
-        self._issued += 1
-        return _waittype(self, keepalive)
+        return _waittype(self, keepalive, self._last_call())
 
     # ---- numpy entry points (uint64 keys) ------------------------------------------------
     def embedding_lookup(self, keys, dest):
@@ -323,10 +343,12 @@ class CacheBase(object):
     def lookup(self, k):
         """Policy lookup of one key (touches replacement state, like the reference)."""
         self._drain()
+        first = self._last_call() + 1
         found, ver = ctypes.c_int(), ctypes.c_int64()
         data = np.zeros(self._width, np.float32)
         check_call(_LIB.hb_cache_touch(self._h, int(k), ctypes.byref(found), ctypes.byref(ver),
                                        data.ctypes.data))
+        self._drain(skip_from=first)   # single-key calls leave no perf entry (as in the reference)
         return Embedding(k, ver.value, data) if found.value else None
 
     def peek(self, k):
@@ -342,7 +364,9 @@ class CacheBase(object):
     def insert(self, e):
         self._drain()
         assert e.data.size == self._width
+        first = self._last_call() + 1
         check_call(_LIB.hb_cache_insert(self._h, e.key, e.version, e.data.ctypes.data))
+        self._drain(skip_from=first)
 
     def __repr__(self):
         pull, push = self._bounds()

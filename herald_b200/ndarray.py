@@ -143,6 +143,14 @@ class NDArray(object):
         del keep
         return out
 
+    def host_view(self):
+        """numpy view (no copy) of a HOST NDArray's pinned memory — herald_b200 extension, used to
+        read a result where it landed instead of copying it again."""
+        assert not is_gpu_ctx(self.ctx)
+        n = int(np.prod(self.shape))
+        buf = (ctypes.c_float * n).from_address(self.data_ptr)
+        return np.frombuffer(buf, dtype=np.float32).reshape(self.shape)
+
     def copyto(self, target):
         if isinstance(target, DLContext):
             target = empty(self.shape, target)

@@ -256,8 +256,18 @@ int hb_cache_push_pull(hb_cache *c, const void *pull_keys, int pull_kind, size_t
                        float *dest, const void *push_keys, int push_kind, size_t n_push,
                        const float *grads);
 /* Block until every call enqueued so far has completed; *perf receives the counters of the
- * most recent call.  Returns -1 if any of them failed on the device. */
+ * most recent call.  Returns -1 if any of them failed on the device (each failure is reported
+ * once; the cache stays usable). */
 int hb_cache_wait(hb_cache *c, hb_perf *perf);
+/* Per-call completion — what the reference's wait_t of ONE call is (python_api.cc:16-19,
+ * cache.h:14).  hb_cache_last_call: sequence number of the call enqueued last.
+ * hb_cache_wait_call: block until call `seq` (and, for a lookup into host memory, the download of
+ * its rows) has completed; later calls keep running.  A host caller can so overlap the upload of
+ * update(t+1)'s gradients with the download of lookup(t+1)'s rows (separate copy streams). */
+int hb_cache_last_call(hb_cache *c, uint64_t *seq);
+int hb_cache_wait_call(hb_cache *c, uint64_t seq, hb_perf *perf);
+/* Counters of calls [first, first + count) (waits for the last of them), oldest first. */
+int hb_cache_perf_range(hb_cache *c, uint64_t first, int count, hb_perf *out, int *kinds);
 /* Push every dirty line (pending victims and resident lines with updates != 0) to its owner,
  * whatever the bound, and mark it clean: call before hb_table_save so that the checkpoint holds
  * every update (the reference lacks this: SURVEY section 5).  Synchronous; collective in a group. */
