@@ -52,6 +52,10 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-steps", type=int, default=8)
+    ap.add_argument("--parity-steps", type=int, default=3,
+                    help="steps at the start of the run whose counters / gathered rows / owner rows are "
+                         "compared with the oracle (N = 1: on the benchmarked table; N > 1: whole-group "
+                         "replay on a 1M-row side table); 0 = off")
     ap.add_argument("--ids", default="permuted", choices=["permuted", "folded"],
                     help="Zipf rank -> row: fixed permutation (default, SURVEY 8d) or rank == row")
     ap.add_argument("--seg-trace", default=None,
@@ -186,10 +190,27 @@ def host_mem_available_gb():
     return 0.0
 
 
-def run_cpu_reference(args, steps, warmup):
-    """-> dict(value, ms_per_step, kind, cores, sample, vocab).  One pool thread does each call
-    (ps-lite/src/thread_pool.cc:4 has 5 threads but a call runs on one; the cache PSFs are serial
-    on the server: ps-lite/src/PSFhandle_embedding.cc:23-27)."""
+def crc_rows(a):
+    import zlib
+    return zlib.crc32(np.ascontiguousarray(a, np.float32).view(np.uint8).reshape(-1))
+
+
+COUNTERS = ("num_unique", "num_miss", "num_evict", "num_transfered")
+
+
+def counters_of(perf_entry):
+    return [int(perf_entry[k]) if k in perf_entry else 0 for k in COUNTERS]
+
+
+def run_cpu_reference(args, steps, warmup, mirror=None):
+    """-> dict(value, ms_per_step, kind, cores, sample, vocab[, parity]).  One pool thread does each
+    call (ps-lite/src/thread_pool.cc:4 has 5 threads but a call runs on one; the cache PSFs are
+    serial on the server: ps-lite/src/PSFhandle_embedding.cc:23-27).
+
+    mirror (from the GPU arm, N = 1): {"touched", "rows0"} = the rows of the GPU's table this run
+    will touch, as they were before the first call, and {"steps", "crc", "pull", "push",
+    "keys_after", "rows_after", "ver_after"} = what the GPU arm observed on its first steps.  The
+    oracle then starts from the same table, runs the same calls and the two are compared."""
     from oracle import port, ref
     kind = "reference" if ref.available() else "port"
     impl = ref if kind == "reference" else port
@@ -199,7 +220,13 @@ def run_cpu_reference(args, steps, warmup):
     if host_mem_available_gb() < need_gb:
         vocab, folded = 4_000_000, True
     limit = cache_limit(vocab, args.ratio)
-    if kind == "reference":
+    if mirror is not None and (folded or kind != "reference"):
+        mirror = dict(skipped="host RAM too small for the full table" if folded else "oracle/_ref not built")
+    if mirror is not None and "skipped" not in mirror:
+        srv = impl.Server(vocab, D)                              # zeros; then the GPU table's rows
+        srv.load_rows_at(mirror["touched"], mirror["rows0"])
+        mirror["rows0"] = None
+    elif kind == "reference":
         srv = impl.Server(vocab, D, init=(2, 0.0, 0.01, 123))   # Normal(0, 0.01): wdl_criteo.py:13-14
     else:
         srv = impl.Server(vocab, D)
@@ -211,10 +238,17 @@ def run_cpu_reference(args, steps, warmup):
         cache.embedding_lookup(hottest_ids(lo, min(lo + chunk, limit), vocab, np.uint64))
     fill_s = time.perf_counter() - t0
     N = B * FIELDS
-    grads = (np.random.default_rng(7).normal(0, 1e-3, (N, D)) * 1e-2).astype(np.float32)
+    grads = make_grads(B, D, 0)
     dest = np.empty((N, D), np.float32)
     ids = [make_ids(s, B, vocab).reshape(-1).astype(np.uint64) for s in range(steps + warmup + 1)]
     cache.embedding_lookup(ids[0], dest)
+    parity = None
+    check = mirror is not None and "skipped" not in mirror
+    P = mirror["steps"] if check else 0
+    if check:
+        parity = {"steps": P, "counters_equal": True, "rows_crc_equal": crc_rows(dest) == mirror["crc"][0]}
+    elif mirror is not None:
+        parity = {"steps": 0, "skipped": mirror["skipped"]}
     times = []
     for s in range(steps + warmup):
         t0 = time.perf_counter()
@@ -223,6 +257,20 @@ def run_cpu_reference(args, steps, warmup):
         dt = time.perf_counter() - t0
         if s >= warmup:
             times.append(dt)
+        if s < P:
+            push, pull = counters_of(cache.perf[-2]), counters_of(cache.perf[-1])
+            parity["counters_equal"] &= push == mirror["push"][s] and pull == mirror["pull"][s]
+            parity["rows_crc_equal"] &= crc_rows(dest) == mirror["crc"][s + 1]
+            if s == P - 1:
+                rows, ver = srv.rows_at(mirror["keys_after"])
+                parity["owner_rows_equal"] = bool(np.array_equal(rows.view(np.uint32),
+                                                                 mirror["rows_after"].view(np.uint32)))
+                parity["owner_versions_equal"] = bool(np.array_equal(ver, mirror["ver_after"]))
+                parity["owner_rows_checked"] = int(rows.shape[0])
+                parity["oracle"] = kind
+                parity["scope"] = ("the benchmarked table and cache (V=%d, limit %d), pre-filled, first %d "
+                                   "update+lookup steps: per-call counters, CRC32 of the gathered rows, owner "
+                                   "rows + versions of every key touched, all bit-exact" % (vocab, limit, P))
     total = float(np.sum(times))
     sample = ("%d timed + %d warm-up steps of the same workload (B=%d, 26 fields, D=%d, V=%d%s, "
               "%s limit %d, bound %d) after filling the cache with the %d hottest ids (%.1f s); "
@@ -230,7 +278,13 @@ def run_cpu_reference(args, steps, warmup):
               (steps, warmup, B, D, vocab, " folded: host RAM" if folded else "", args.policy,
                limit, args.bound, limit, fill_s, 1e3 * float(np.median(times))))
     return dict(value=B * steps / total, ms_per_step=1e3 * total / steps, kind=kind, cores=1,
-                sample=sample, vocab=vocab)
+                sample=sample, vocab=vocab, parity=parity)
+
+
+def make_grads(B, D, rank):
+    """Gradient rows of one batch, already multiplied by -lr (ParameterServerCommunicate.py:58-59)."""
+    rng = np.random.default_rng(7 + rank)
+    return (rng.normal(0, 1e-3, (B * FIELDS, D)) * 1e-2).astype(np.float32)
 
 
 def reference_main(args, rank, world):
@@ -312,6 +366,89 @@ def seg_trace(path, run_step):
         json.dump(out, f)
 
 
+def group_parity(args, rank, world, local_rank, dist, comm):
+    """N > 1: whole-group parity run BEFORE the benchmark, on a side table small enough to mirror
+    on the host (1 000 003 rows) but with the benchmark's call shape (B x 26 keys per rank, D,
+    policy, bound) — so full-size batches travel through the owner mailboxes and the remote pulls.
+    Every rank drives its cache for P update+lookup steps; rank 0 replays the WHOLE group on the
+    oracle (one server, one cache per rank, calls in rank order: the order the owners apply the
+    mailboxes in) and compares every rank's counters, CRC32 of gathered rows, and final shard
+    rows + versions.  Returns the parity record on rank 0, None elsewhere."""
+    import herald_b200 as hb
+    from herald_b200 import ps, partition
+    from herald_b200.cstable import CacheSparseTable
+    B, D, P = args.batch, args.dim, args.parity_steps
+    V2, limit2, node = 1_000_003, 300_000, 7
+    r = np.arange(V2, dtype=np.int64)[:, None]
+    c = np.arange(D, dtype=np.int64)[None, :]
+    rows = (((r * 31 + c * 17) % 2003) - 1001).astype(np.float32) * np.float32(1e-5)
+    table = comm.InitTensor(node, ps.kCacheTable, V2, D, ps.Constant, 0.0)
+    table.load_rows(rows)                                      # clipped to this rank's shard
+    cst = CacheSparseTable(limit2, V2, D, node, args.policy, args.bound)
+    cst.cache.reserve(max(B * FIELDS, 1 << 20))
+    cst.perf_enabled(True)
+    comm.BarrierWorker()
+    host = hb.cpu(0)
+    ids = [[make_ids(5000 + s, B, V2, w) for s in range(P + 1)] for w in range(world)]
+    mine = {"crc": [], "pull": [], "push": []}
+    g_host, d_host = hb.array(make_grads(B, D, rank).reshape(B, FIELDS, D), host), hb.empty((B, FIELDS, D), host)
+    cst.embedding_lookup(hb.array(ids[rank][0], host), d_host, sync=True)
+    mine["crc"].append(crc_rows(d_host.host_view()))
+    for s in range(P):
+        cst.embedding_update(hb.array(ids[rank][s], host), g_host, sync=True)
+        comm.BarrierWorker()                                   # BSP: every push before any pull
+        cst.embedding_lookup(hb.array(ids[rank][s + 1], host), d_host, sync=True)
+        mine["push"].append(counters_of(cst.perf[-2]))
+        mine["pull"].append(counters_of(cst.perf[-1]))
+        mine["crc"].append(crc_rows(d_host.host_view()))
+    comm.BarrierWorker()
+    import zlib
+    mine["shard_rows_crc"] = crc_rows(table.read_rows())
+    mine["shard_ver_crc"] = zlib.crc32(np.ascontiguousarray(table.read_versions()).view(np.uint8))
+    everyone = [None] * world
+    dist.all_gather_object(everyone, mine)
+    comm.BarrierWorker()
+    del cst, g_host, d_host
+    comm.ClearTensor(node)
+    if rank != 0:
+        return None
+    from oracle import port, ref
+    kind = "reference" if ref.available() else "port"
+    impl = ref if kind == "reference" else port
+    srv = impl.Server(V2, D, rows)
+    caches = [impl.Cache(srv, args.policy, limit2, args.bound) for _ in range(world)]
+    grads = [make_grads(B, D, w) for w in range(world)]
+    rec = {"steps": P, "ranks": world, "counters_equal": True, "rows_crc_equal": True}
+    dest = np.empty((B * FIELDS, D), np.float32)
+
+    def lookups(s):
+        for w in range(world):
+            caches[w].embedding_lookup(ids[w][s].reshape(-1).astype(np.uint64), dest)
+            rec["rows_crc_equal"] &= crc_rows(dest) == everyone[w]["crc"][s]
+            if s:
+                rec["counters_equal"] &= counters_of(caches[w].perf[-1]) == everyone[w]["pull"][s - 1]
+
+    lookups(0)
+    for s in range(P):
+        for w in range(world):
+            caches[w].embedding_update(ids[w][s].reshape(-1).astype(np.uint64), grads[w])
+            rec["counters_equal"] &= counters_of(caches[w].perf[-1]) == everyone[w]["push"][s]
+        lookups(s + 1)
+    orows, over = srv.rows(), srv.versions()
+    ok_rows = ok_ver = True
+    for w in range(world):
+        b, n = partition.shard_range(w, world, V2)
+        ok_rows &= crc_rows(orows[b:b + n]) == everyone[w]["shard_rows_crc"]
+        ok_ver &= zlib.crc32(np.ascontiguousarray(over[b:b + n]).view(np.uint8)) == everyone[w]["shard_ver_crc"]
+    rec["owner_rows_equal"], rec["owner_versions_equal"] = bool(ok_rows), bool(ok_ver)
+    rec["oracle"] = kind
+    rec["scope"] = ("whole group of %d ranks on a %d-row side table (limit %d), benchmark call shape "
+                    "(%d keys per rank and call, D=%d, %s, bound %d), %d update+lookup steps replayed on the "
+                    "oracle in rank order: every rank's counters, CRC32 of gathered rows, final shard rows "
+                    "and versions, bit-exact" % (world, V2, limit2, B * FIELDS, D, args.policy, args.bound, P))
+    return rec
+
+
 def herald_main(args, rank, world, local_rank):
     import herald_b200 as hb
     from herald_b200 import ps, stream as hstream
@@ -349,6 +486,9 @@ def herald_main(args, rank, world, local_rank):
     N = B * FIELDS
     limit = cache_limit(V, args.ratio)
     comm = hb.worker_init(local_rank)
+    group_par = None
+    if world > 1 and args.parity_steps > 0:
+        group_par = group_parity(args, rank, world, local_rank, dist, comm)
     table = comm.InitTensor(0, ps.kCacheTable, V, D, ps.Normal, 0.0, 0.01, 123)
     cst = CacheSparseTable(limit, V, D, 0, args.policy, args.bound)
     cst.cache.reserve(max(N, 1 << 20))
@@ -357,14 +497,28 @@ def herald_main(args, rank, world, local_rank):
 
     # ---- inputs ----
     K, W = args.steps, args.warmup
-    total = K + W + 1
-    ids_np = [make_ids(s, B, V, rank) for s in range(total)]
-    ids_dev = [hb.array(a, dev) for a in ids_np]
-    rng = np.random.default_rng(7 + rank)
+    # N = 1: the first P steps are the parity steps (compared with the oracle in the cpu_baseline
+    # leg, which replays them from the same table rows); warm-up and timed steps follow
+    P = args.parity_steps if (world == 1 and not args.no_cpu_baseline) else 0
+    cpu_total = args.cpu_steps + 2
+    P = min(P, cpu_total)
+    total = P + K + W + 1
+    ids_np = [make_ids(s, B, V, rank) for s in range(max(total, cpu_total + 1))]
+    ids_dev = [hb.array(a, dev) for a in ids_np[:total]]
     R = 3
-    grads_np = (rng.normal(0, 1e-3, (B, FIELDS, D)) * 1e-2).astype(np.float32)   # already x(-lr)
+    grads_np = make_grads(B, D, rank).reshape(B, FIELDS, D)                      # already x(-lr)
     grads_dev = [hb.array(grads_np, dev) for _ in range(R)]
     dest_dev = [hb.empty((B, FIELDS, D), dev) for _ in range(R)]
+    mirror = None
+    if P:
+        # rows the oracle's run will touch, as they are before the first call
+        chunk = 1 << 20
+        fill = [hottest_ids(lo, min(lo + chunk, limit), V, np.uint64) for lo in range(0, limit, chunk)]
+        touched = np.unique(np.concatenate(fill + [a.reshape(-1).astype(np.uint64)
+                                                   for a in ids_np[:cpu_total + 1]]))
+        mirror = {"steps": P, "touched": touched, "rows0": table.read_rows_at(touched)[0],
+                  "crc": [], "pull": [], "push": []}
+        del fill
 
     # ---- fill the cache with the hottest ids (setup, untimed) ----
     chunk = 1 << 20
@@ -374,7 +528,26 @@ def herald_main(args, rank, world, local_rank):
         d = hb.empty((k.shape[0], D), dev)
         cst.embedding_lookup(k, d, sync=True)
         del k, d
-    cst.embedding_lookup(ids_dev[0], dest_dev[0], sync=True)
+    if P:
+        # parity steps: synchronous calls with host (pinned) buffers, everything observable recorded
+        host = hb.cpu(0)
+        g_host, d_host = hb.array(grads_np, host), hb.empty((B, FIELDS, D), host)
+        cst.perf_enabled(True)
+        cst.embedding_lookup(hb.array(ids_np[0], host), d_host, sync=True)
+        mirror["crc"].append(crc_rows(d_host.host_view()))
+        for s in range(P):
+            cst.embedding_update(hb.array(ids_np[s], host), g_host, sync=True)
+            cst.embedding_lookup(hb.array(ids_np[s + 1], host), d_host, sync=True)
+            mirror["push"].append(counters_of(cst.perf[-2]))
+            mirror["pull"].append(counters_of(cst.perf[-1]))
+            mirror["crc"].append(crc_rows(d_host.host_view()))
+        mirror["keys_after"] = np.unique(np.concatenate([a.reshape(-1).astype(np.uint64)
+                                                         for a in ids_np[:P + 1]]))
+        mirror["rows_after"], mirror["ver_after"] = table.read_rows_at(mirror["keys_after"])
+        cst.perf_enabled(False)
+        del g_host, d_host
+    else:
+        cst.embedding_lookup(ids_dev[0], dest_dev[0], sync=True)
 
     def step(s, keys, grads, dests, sync):
         w1 = cst.embedding_update(keys[s], grads[s % len(grads)], sync=sync)
@@ -387,7 +560,7 @@ def herald_main(args, rank, world, local_rank):
             dist.barrier()
 
     # ---- warm-up (untimed) ----
-    for s in range(W):
+    for s in range(P, P + W):
         step(s, ids_dev, grads_dev, dest_dev, False)
     if not os.environ.get("HB_BENCH_NOPERF"):       # diagnostics: cost of the phase events
         cst.perf_enabled(True)
@@ -405,7 +578,7 @@ def herald_main(args, rank, world, local_rank):
     barrier()
     ev[0].record(stream)
     last = None
-    for s in range(W, W + K):
+    for s in range(P + W, P + W + K):
         last = step(s, ids_dev, grads_dev, dest_dev, False)
     ev[1].record(stream)
     last[1].wait()
@@ -419,7 +592,7 @@ def herald_main(args, rank, world, local_rank):
     perf = list(cst.perf)[-2 * K:]
 
     if args.seg_trace and rank == 0:
-        seg_trace(args.seg_trace, lambda: step(W + K - 1, ids_dev, grads_dev, dest_dev, True))
+        seg_trace(args.seg_trace, lambda: step(P + W + K - 1, ids_dev, grads_dev, dest_dev, True))
 
     # ---- end to end with host buffers (pinned NDArrays: the reference's calling convention) ----
     e2e = None
@@ -427,7 +600,7 @@ def herald_main(args, rank, world, local_rank):
         cst.perf_enabled(False)
         Ke = min(K, 20)
         host = hb.cpu(0)
-        ids_host = [hb.array(ids_np[W + s], host) for s in range(Ke + 1)]
+        ids_host = [hb.array(ids_np[P + W + s], host) for s in range(Ke + 1)]
         grads_host = [hb.array(grads_np, host) for _ in range(2)]
         dest_host = [hb.empty((B, FIELDS, D), host) for _ in range(2)]
         cst.embedding_lookup(ids_host[0], dest_host[0], sync=True)
@@ -476,7 +649,10 @@ def herald_main(args, rank, world, local_rank):
         U_pull = float(np.mean([p["num_unique"] for p in pulls]))
         U_push = float(np.mean([p["num_unique"] for p in pushes]))
         t_gather = float(np.mean([p["copy_time"] for p in timed_pulls]))   # ms, gather kernel
-        t_accum = float(np.mean([p["copy_time"] for p in timed_pushes]))   # ms, accumulate+push kernel
+        # the accumulate+push kernel alone (events right around segment_reduce_kernel; copy_time also
+        # holds its plan kernel, reported as seg_plan_ms)
+        t_accum = float(np.mean([p.get("kernel_time") or p["copy_time"] for p in timed_pushes]))
+        t_plan = float(np.mean([p["copy_time"] for p in timed_pushes])) - t_accum
         row = D * 4
         gather_bytes = (U_pull + N) * row
         accum_bytes = (N + 2 * U_push) * row                              # SURVEY §8(d), bound 0
@@ -486,7 +662,7 @@ def herald_main(args, rank, world, local_rank):
             "gather_rows_kernel": {"ms": t_gather, "algorithmic_bytes": gather_bytes,
                                    "gbs": gather_bytes / t_gather / 1e6 if t_gather else None},
             "segment_reduce_kernel<AccumulatePush>": {
-                "ms": t_accum, "algorithmic_bytes": accum_bytes,
+                "ms": t_accum, "seg_plan_ms": t_plan, "algorithmic_bytes": accum_bytes,
                 "gbs": accum_bytes / t_accum / 1e6 if t_accum else None,
                 "algorithmic_bytes_with_owner_row_rmw": accum_bytes_owner,
                 "gbs_with_owner_row_rmw": accum_bytes_owner / t_accum / 1e6 if t_accum else None},
@@ -519,9 +695,13 @@ def herald_main(args, rank, world, local_rank):
                            "h2d_bytes_per_step": 2 * N * 4 + N * D * 4, "d2h_bytes_per_step": N * D * 4,
                            "ms_per_step": e2e["ms"] / e2e["steps"]}
         if world == 1 and not args.no_cpu_baseline:
-            cpu = run_cpu_reference(args, args.cpu_steps, 2)
+            cpu = run_cpu_reference(args, args.cpu_steps, 2, mirror)
             line["cpu_baseline"] = {"value": cpu["value"], "unit": "samples/s", "cores": cpu["cores"],
                                     "kind": cpu["kind"], "sample": cpu["sample"]}
+            if cpu["parity"] is not None:
+                line["parity"] = cpu["parity"]
+        if group_par is not None:
+            line["parity"] = group_par
         print(json.dumps(line), flush=True)
 
     del cst

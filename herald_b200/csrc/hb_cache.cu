@@ -1475,6 +1475,33 @@ __global__ void init_slots_kernel(CacheView c) {
     }
 }
 
+// new slots [old_cap, c.capacity) of a grown row store: free, at the BOTTOM of the free stack (the
+// stack keeps handing out the lowest never-used slot first, which slot_hw relies on); the old
+// stack's `top` entries move up by the number of new slots
+__global__ void grow_slots_kernel(CacheView c, u32 old_cap, const u32 *old_stack, u32 top) {
+    pdl_enter();
+    const u32 delta = c.capacity - old_cap;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < c.capacity;
+         i += (size_t)gridDim.x * blockDim.x) {
+        if (i >= old_cap) {
+            const size_t s = i;
+            c.slot_prio[s] = PRIO_NONE;
+            c.slot_state[s] = S_FREE;
+            c.slot_flags[s] = 0;
+            c.slot_updates[s] = 0;
+            c.slot_use[s] = 0;
+            c.slot_version[s] = -1;
+            c.slot_key[s] = HT_EMPTY;
+        }
+        if (i < delta)
+            c.free_stack[i] = (u32)(c.capacity - 1 - i);
+        else if (i - delta < top)
+            c.free_stack[i] = old_stack[i - delta];
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        c.regs->free_top = top + delta;
+}
+
 __global__ void rebuild_index_kernel(CacheView c) {
     pdl_enter();
     u32 fresh = 0;
@@ -1560,6 +1587,24 @@ __global__ void single_key_kernel(u64 *uniq, u32 *num_unique, u64 key) {
 __global__ void read_slot_kernel(const i32 *uslot, i32 *out) {
     pdl_enter();
     *out = uslot[0];
+}
+
+// ---- sparse read of an owner shard: out[i,:] = rows[keys[i] - row_begin,:], ver likewise ----
+struct IndexFromShardKeys {
+    const u64 *keys;
+    u64 row_begin, nrows;
+    __device__ long long operator()(size_t n) const {
+        const u64 r = keys[n] - row_begin; // wraps for keys below the shard
+        return r < nrows ? (long long)r : -1;
+    }
+};
+__global__ void gather_versions_kernel(const i64 *ver, const u64 *keys, size_t n, u64 row_begin,
+                                       u64 nrows, i64 *out) {
+    pdl_enter();
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const u64 r = keys[i] - row_begin;
+        out[i] = r < nrows ? ver[r] : -1;
+    }
 }
 
 // ---- table init: counter-based generator (splitmix64 of (seed, element index)) -----------
@@ -1781,6 +1826,80 @@ void maybe_rebuild_index(hb_cache *c, size_t incoming) {
     } else {
         c->occ_upper = regs.ht_occupied + incoming;
     }
+}
+
+// Grow the row store to `new_cap` slots (rare: the slack is sized by hb_cache_reserve / the first
+// calls).  Synchronises; every slot array is reallocated and copied.
+template <typename T>
+void regrow(T *&p, size_t old_count, size_t new_count, bool keep) {
+    T *q = nullptr;
+    dmalloc(q, new_count);
+    if (keep && p && old_count)
+        HB_CUDA(cudaMemcpy(q, p, old_count * sizeof(T), cudaMemcpyDeviceToDevice));
+    dfree(p);
+    p = q;
+}
+
+void grow_store(hb_cache *c, size_t new_cap) {
+    CacheView &v = c->view;
+    const size_t old_cap = v.capacity;
+    HB_CHECK(new_cap > old_cap && new_cap < (1ull << 31), "row store cannot grow that far");
+    sync_all(c);
+    CacheRegs regs;
+    HB_CUDA(cudaMemcpy(&regs, v.regs, sizeof(regs), cudaMemcpyDeviceToHost));
+    regrow(v.slot_key, old_cap, new_cap, true);
+    regrow(v.slot_version, old_cap, new_cap, true);
+    regrow(v.slot_updates, old_cap, new_cap, true);
+    regrow(v.slot_prio, old_cap, new_cap, true);
+    regrow(v.slot_use, old_cap, new_cap, true);
+    regrow(v.slot_state, old_cap, new_cap, true);
+    regrow(v.slot_flags, old_cap, new_cap, true);
+    regrow(v.data, old_cap * c->width, new_cap * c->width, true);
+    regrow(v.grad, old_cap * c->width, new_cap * c->width, true);
+    regrow(v.pending_list, old_cap, new_cap, true);
+    regrow(v.victims, old_cap, new_cap, false);
+    regrow(v.cand_prio, 2 * old_cap, 2 * new_cap, false);
+    regrow(v.cand_slot, 2 * old_cap, 2 * new_cap, false);
+    u32 *old_stack = v.free_stack;
+    v.free_stack = nullptr;
+    dmalloc(v.free_stack, new_cap);
+    v.capacity = (u32)new_cap;
+    HB_LAUNCH(grow_slots_kernel, lin_grid(new_cap), 256, 0, c->stream, v, (u32)old_cap, old_stack, regs.free_top);
+    HB_LAUNCHED();
+    HB_CUDA(cudaStreamSynchronize(c->stream));
+    dfree(old_stack);
+    c->slack = new_cap - c->limit;
+}
+
+// The calls enqueued so far may hold up to `pending_upper` dirty victims in slots (evict_, flushed
+// by the next pushing call) and the new call needs up to `n` fresh lines: make sure the store's
+// slack covers both.  The reference's transient lines and evict_ vector are heap-backed and
+// unbounded (cache.cc:140-166); here the store grows instead (a synchronising reallocation, which
+// hb_cache_reserve avoids by sizing the slack up front).
+void ensure_slack(hb_cache *c, size_t n) {
+    if (c->pending_upper + n <= c->slack)
+        return;
+    // tighten the bound from the newest finished call's record: pending then + keys looked up since
+    for (uint64_t back = 1; back <= std::min<uint64_t>(c->calls, 64); back++) {
+        const uint64_t call = c->calls - back;
+        const int idx = (int)(call % hb_cache::kRing);
+        if (cudaEventQuery(c->ev_end[idx]) != cudaSuccess)
+            continue;
+        size_t bound = c->ring[idx].pending;
+        for (uint64_t k = call + 1; k < c->calls; k++)
+            bound += c->incoming_ring[k % hb_cache::kRing];
+        c->pending_upper = std::min(c->pending_upper, bound);
+        break;
+    }
+    (void)cudaGetLastError();
+    if (c->pending_upper + n <= c->slack)
+        return;
+    sync_all(c);
+    if (c->calls)
+        c->pending_upper = c->ring[(c->calls - 1) % hb_cache::kRing].pending;
+    if (c->pending_upper + n <= c->slack)
+        return;
+    grow_store(c, c->limit + 2 * (c->pending_upper + n));
 }
 
 // phase boundary k of the running call (only when perf is enabled: cache.cc:89-106 timings)
@@ -2008,7 +2127,10 @@ void run_accumulate(hb_cache *c, size_t n, int batch, int wsi, const float *dev_
         AccumulatePush<4> f4{c->view, ws.uniq, c->uslot[batch], c->push_bound, plan, plan_n,
                              defer_cleanup};
         run_segment_reduce(ws, p, dev_grads, c->width, n, vec4(c, dev_grads), c->hot_threshold, st,
-                           f1, f4);
+                           f1, f4, [&] {
+                               if (batch == 0)
+                                   mark(c, 3);
+                           });
     }
     if (batch == 0)
         mark(c, 2);
@@ -2088,6 +2210,7 @@ void do_update(hb_cache *c, const void *keys, int kind, size_t n, const float *g
     Guard g(c->device);
     ensure_batch(c, n);
     ensure_keys_stage(c, n);
+    ensure_slack(c, n);
     const int w = c->cur; // the workspace of the most recent lookup: usually this very batch
     const void *dkeys = stage_keys(c, keys, kind, n, 0);
     presort(c, dkeys, kind, n, w, /*check=*/true);
@@ -2226,6 +2349,41 @@ int hb_table_read_versions(hb_table *t, size_t row_begin, size_t nrows, int64_t 
     if (lo < hi)
         HB_CUDA(cudaMemcpy(versions + (lo - row_begin), t->ver + (lo - t->row_begin),
                            (hi - lo) * sizeof(i64), cudaMemcpyDefault));
+    HB_API_END();
+}
+
+int hb_table_read_rows_at(hb_table *t, const uint64_t *keys, size_t n, float *rows, int64_t *versions) {
+    HB_API_BEGIN();
+    Guard g(t->device);
+    HB_CUDA(cudaDeviceSynchronize());
+    if (n) {
+        u64 *dkeys = nullptr;
+        float *drows = nullptr;
+        i64 *dver = nullptr;
+        dmalloc(dkeys, n);
+        HB_CUDA(cudaMemcpy(dkeys, keys, n * sizeof(u64), cudaMemcpyDefault));
+        if (rows) {
+            dmalloc(drows, n * t->width);
+            IndexFromShardKeys idx{dkeys, t->row_begin, t->nrows};
+            int grid = row_grid((n + 3) / 4);
+            if (t->width % 4 == 0)
+                HB_LAUNCH((gather_rows_kernel<4, 4, IndexFromShardKeys>), grid, kRowBlock, 0, 0, t->rows, drows, n, t->width, idx);
+            else
+                HB_LAUNCH((gather_rows_kernel<1, 4, IndexFromShardKeys>), grid, kRowBlock, 0, 0, t->rows, drows, n, t->width, idx);
+            HB_LAUNCHED();
+            HB_CUDA(cudaMemcpy(rows, drows, n * t->width * sizeof(float), cudaMemcpyDefault));
+        }
+        if (versions) {
+            dmalloc(dver, n);
+            HB_LAUNCH(gather_versions_kernel, lin_grid(n), 256, 0, 0, t->ver, dkeys, n, (u64)t->row_begin,
+                      (u64)t->nrows, dver);
+            HB_LAUNCHED();
+            HB_CUDA(cudaMemcpy(versions, dver, n * sizeof(i64), cudaMemcpyDefault));
+        }
+        dfree(dkeys);
+        dfree(drows);
+        dfree(dver);
+    }
     HB_API_END();
 }
 
@@ -2477,6 +2635,9 @@ int hb_cache_reserve(hb_cache *c, size_t max_keys) {
     HB_API_BEGIN();
     Guard g(c->device);
     ensure_batch(c, max_keys);
+    // transient lines of one call + dirty victims of a few lookups without a push in between
+    if (3 * max_keys > c->slack)
+        grow_store(c, c->limit + 3 * max_keys);
     if (c->view.pv.world > 1 && max_keys > c->mailbox_cap) {
         sync_all(c);
         setup_mailbox(c, max_keys); // collective
@@ -2522,6 +2683,7 @@ int hb_cache_lookup(hb_cache *c, const void *keys, int key_kind, size_t n, float
     HB_CHECK(n < (1ull << 31), "too many keys in one call");
     ensure_batch(c, n);
     ensure_keys_stage(c, n);
+    ensure_slack(c, n);
     maybe_rebuild_index(c, n);
     // a lookup sorts into the workspace the previous lookup did NOT use: that one usually still
     // serves the update of its batch (same keys, no second sort)
@@ -2568,6 +2730,7 @@ int hb_cache_push_pull(hb_cache *c, const void *pull_keys, int pull_kind, size_t
     HB_CHECK(n_pull < (1ull << 31) && n_push < (1ull << 31), "too many keys in one call");
     ensure_batch(c, std::max(n_pull, n_push));
     ensure_keys_stage(c, std::max(n_pull, n_push));
+    ensure_slack(c, n_pull + n_push);
     maybe_rebuild_index(c, n_pull);
     cudaStream_t st = c->stream;
     // the push batch is usually the previous call's pull batch (ASP prefetch,
@@ -2730,8 +2893,10 @@ static void fill_perf(hb_cache *c, uint64_t call, hb_perf *perf) {
             perf->copy_ms = span(ph[2], ph[3]);     // gather into dest
             perf->insert_ms = span(ph[3], c->ev_end[idx]);
         } else if (r.kind == 1 && (mask & 4u)) {
-            perf->copy_ms = span(ph[1], ph[2]);     // accumulate (+ fused push)
+            perf->copy_ms = span(ph[1], ph[2]);     // accumulate (+ fused push): plan + data kernel
             perf->transfer_ms = span(ph[2], c->ev_end[idx]); // flush of evicted lines + cleanup
+            if (mask & 8u)
+                perf->kernel_ms = span(ph[3], ph[2]); // the data kernel alone (segment_reduce)
         }
     }
 }

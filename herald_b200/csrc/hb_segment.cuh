@@ -3,6 +3,7 @@
 #pragma once
 
 #include <cstdlib>
+#include <functional>
 
 #include "hb_rows.cuh"
 #include "hb_sort.cuh"
@@ -58,7 +59,8 @@ void launch_segment_reduce(KeyWorkspace &ws, const u32 *perm, const float *vals,
 // path.  `n` = number of values (upper bound of any segment length).
 template <class F1, class F4>
 void run_segment_reduce(KeyWorkspace &ws, const u32 *perm, const float *vals, size_t D, size_t n,
-                        bool v4, u32 hot_threshold, cudaStream_t st, F1 f1, F4 f4) {
+                        bool v4, u32 hot_threshold, cudaStream_t st, F1 f1, F4 f4,
+                        const std::function<void()> &after_plan = nullptr) {
     if (n == 0)
         return;
     const bool hot = n > hot_threshold;
@@ -72,6 +74,8 @@ void run_segment_reduce(KeyWorkspace &ws, const u32 *perm, const float *vals, si
                                                         hl, f4);
         HB_LAUNCHED();
     }
+    if (after_plan)
+        after_plan(); // (timing mark between the plan kernel and the data kernel)
     const bool r4 = seg_rows() == 4;
     if (v4 && r4)
         launch_segment_reduce<4, 4>(ws, perm, vals, D, n, hot, thr, hl, st, f4, f1);

@@ -27,7 +27,8 @@ class hb_perf(ctypes.Structure):
                 ("size", ctypes.c_int64), ("error", ctypes.c_int64),
                 ("time_ms", ctypes.c_float), ("sort_ms", ctypes.c_float),
                 ("lookup_ms", ctypes.c_float), ("transfer_ms", ctypes.c_float),
-                ("copy_ms", ctypes.c_float), ("insert_ms", ctypes.c_float)]
+                ("copy_ms", ctypes.c_float), ("insert_ms", ctypes.c_float),
+                ("kernel_ms", ctypes.c_float)]
 
 
 def _proto():
@@ -253,6 +254,7 @@ class CacheBase(object):
                 else:
                     d["num_evict"] = int(p.num_evict)
                     d["cleanup_time"] = 0.0
+                    d["kernel_time"] = float(p.kernel_ms)   # accumulate kernel alone (extension)
                 self._perf.append(d)
         self._recorded = upto + 1
 

@@ -24,6 +24,7 @@ _LIB.hb_table_init.argtypes = [_vp, ctypes.c_int, ctypes.c_double, ctypes.c_doub
 _LIB.hb_table_load_rows.argtypes = [_vp, _sz, _sz, _vp]
 _LIB.hb_table_read_rows.argtypes = [_vp, _sz, _sz, _vp]
 _LIB.hb_table_read_versions.argtypes = [_vp, _sz, _sz, _vp]
+_LIB.hb_table_read_rows_at.argtypes = [_vp, _vp, _sz, _vp, _vp]
 _LIB.hb_table_shard.argtypes = [_vp, ctypes.POINTER(_sz), ctypes.POINTER(_sz),
                                 ctypes.POINTER(_vp), ctypes.POINTER(_vp)]
 _LIB.hb_table_save.argtypes = [_vp, ctypes.c_char_p]
@@ -56,6 +57,15 @@ class Table(object):
         out = np.zeros((nrows, self.width), np.float32)
         check_call(_LIB.hb_table_read_rows(self.h, row_begin, nrows, out.ctypes.data))
         return out
+
+    def read_rows_at(self, keys):
+        """(rows, versions) of the given global rows — sparse pull from this rank's shard."""
+        keys = np.ascontiguousarray(keys, np.uint64).reshape(-1)
+        rows = np.zeros((keys.size, self.width), np.float32)
+        ver = np.zeros(keys.size, np.int64)
+        check_call(_LIB.hb_table_read_rows_at(self.h, keys.ctypes.data, keys.size, rows.ctypes.data,
+                                              ver.ctypes.data))
+        return rows, ver
 
     def read_versions(self, row_begin=None, nrows=None):
         sb, sn, _, _ = self.shard()

@@ -182,6 +182,11 @@ int hb_table_init(hb_table *t, int init_type, double a, double b, unsigned long 
 int hb_table_load_rows(hb_table *t, size_t row_begin, size_t nrows, const float *rows);
 int hb_table_read_rows(hb_table *t, size_t row_begin, size_t nrows, float *rows);
 int hb_table_read_versions(hb_table *t, size_t row_begin, size_t nrows, int64_t *versions);
+/* Sparse read — the owner side of ps-lite's SparsePull (ps-lite/include/ps/psf/sparse.h:9-20, ps-lite/include/ps/worker/PSAgent.h:205-230) without
+ * a cache in front: rows[i,:] / versions[i] of GLOBAL row keys[i], n keys in host or device
+ * memory, results to host or device memory (either may be NULL).  Keys outside this rank's shard
+ * yield zeros / version -1.  Synchronous. */
+int hb_table_read_rows_at(hb_table *t, const uint64_t *keys, size_t n, float *rows, int64_t *versions);
 /* local shard geometry */
 /* Checkpoint of this rank's shard in the reference's on-disk format
  * (ps-lite/include/ps/worker/PSAgent.h:447-476 ParameterSave/ParameterLoad,
@@ -217,6 +222,8 @@ typedef struct {
     int64_t error;          /* non-zero: device-side failure code (see hb_cache.cu) */
     float time_ms;          /* device time of the call (CUDA events)                */
     float sort_ms, lookup_ms, transfer_ms, copy_ms, insert_ms; /* phase split      */
+    float kernel_ms;        /* Push: the accumulate kernel alone (copy_ms minus its plan
+                               kernel); 0 when the call carried no phase events        */
 } hb_perf;
 
 /* limit/len/width/node_id as the reference constructors (python_api.cc:54-76).
