@@ -690,6 +690,24 @@ def herald_main(args, rank, world, local_rank):
                          "peak_source": peak_src, "kernels": kernels},
             "phases": phase,
         }
+        if world > 1:
+            # NVLink 5: 900 GB/s per direction per GPU (nominal).  Pull = rows this rank's sync kernel
+            # reads out of peers' shards (inbound); push = lines its accumulate kernel deposits in
+            # peers' mailboxes (outbound).  Bytes are the algorithmic row bytes, times are the CUDA-event
+            # times of the kernels that move them (which also do their local work in that time).
+            rp = float(np.mean([p.get("num_remote", 0) for p in pulls])) * row
+            rq = float(np.mean([p.get("num_remote", 0) for p in pushes])) * row
+            t_sync = float(np.mean([p["transfer_time"] for p in timed_pulls]))
+            pull_gbs = rp / t_sync / 1e6 if t_sync else None
+            push_gbs = rq / t_accum / 1e6 if t_accum else None
+            line["roofline"]["nvlink"] = {
+                "peak_gbs_per_direction": 900.0,
+                "pull": {"kernel": "sync_kernel", "remote_bytes": rp, "ms": t_sync, "gbs": pull_gbs,
+                         "frac_of_900": pull_gbs / 900.0 if pull_gbs else None},
+                "push": {"kernel": "segment_reduce_kernel<AccumulatePush>", "remote_bytes": rq,
+                         "ms": t_accum, "gbs": push_gbs,
+                         "frac_of_900": push_gbs / 900.0 if push_gbs else None},
+                "step": {"remote_bytes_in_plus_out": rp + rq, "gbs_over_whole_step": (rp + rq) / (ms / K) / 1e6}}
         if e2e:
             line["e2e"] = {"value": world * B * e2e["steps"] / (e2e["ms"] / 1e3), "unit": "samples/s",
                            "h2d_bytes_per_step": 2 * N * 4 + N * D * 4, "d2h_bytes_per_step": N * D * 4,

@@ -121,6 +121,35 @@ __device__ __forceinline__ u32 *block_counter() {
     __shared__ u32 s_counter;
     return &s_counter;
 }
+__device__ __forceinline__ u32 *block_counter2() {
+    __shared__ u32 s_counter2;
+    return &s_counter2;
+}
+
+// Split barriers over peer-mapped flags (no launch of their own): a kernel that is about to read
+// what peers wrote spins, one lane per peer, until every flag has reached `epoch`; the flags are
+// raised by the kernel that finished the writes.  Bounded: a peer that never shows up fails the
+// call (E_BARRIER) instead of hanging the GPU.
+__device__ __forceinline__ void wait_flags(const CacheView &c, const u64 *flags, u64 epoch) {
+    if (threadIdx.x < (unsigned)c.pv.world && epoch) {
+        const u64 t0 = global_timer_ns();
+        u64 seen = 0;
+        unsigned spins = 0;
+        while (true) {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(flags + threadIdx.x) : "memory");
+            if (seen >= epoch)
+                break;
+            if ((++spins & 1023u) == 0 && global_timer_ns() - t0 > c.pv.timeout_ns) {
+                atomicMax(&c.regs->error, (u32)E_BARRIER);
+                break;
+            }
+        }
+    }
+    __syncthreads();
+}
+__device__ __forceinline__ void raise_flag(u64 *flag, u64 epoch) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flag), "l"(epoch) : "memory");
+}
 
 __device__ __forceinline__ int class_use_of(int policy) {
     return policy == HB_POLICY_LFU ? 1 : 0;
@@ -144,6 +173,7 @@ __global__ void op_begin_kernel(CacheRegs *r, u64 *clk, int flush) {
     clk[1] = clk[2] = clk[3] = r->clock;
     r->U = r->M = r->alloc_base = 0;
     r->pulled = r->pushed = 0;
+    r->pulled_remote = r->pushed_remote = 0;
     r->flushed = flush ? r->pending : 0;
     r->E = r->k_old = r->n_drop = r->need_min = r->nv = r->nc = 0;
     r->U2 = r->M2 = r->alloc_base2 = 0;
@@ -176,6 +206,7 @@ __global__ void op_end_kernel(CacheView c, const u64 *clk, int last_stage, PerfR
         rec->num_evict = r->flushed;
         rec->num_transfered = r->pulled;
     }
+    rec->num_remote = kind == 0 ? r->pulled_remote : r->pushed_remote;
     rec->size = r->size;
     rec->error = r->error;
     rec->ht_occupied = r->ht_occupied;
@@ -312,19 +343,23 @@ __global__ void alloc_kernel(CacheView c, const u64 *uniq, i32 *uslot, const u32
 template <int VEC, int ROWS>
 __global__ void __launch_bounds__(kRowBlock)
     sync_kernel(CacheView c, const u64 *__restrict__ uniq, const i32 *__restrict__ uslot,
-                i64 pull_bound) {
+                i64 pull_bound, u64 applied_epoch) {
     pdl_enter();
+    // multi-GPU, BSP: every owner has applied the pushes of the exchanges enqueued before this
+    // lookup (the role of BarrierWorker, ParameterServerCommunicate.py:48-52)
+    if (c.pv.world > 1)
+        wait_flags(c, c.pv.ctrl + kMaxWorld, applied_epoch);
     using V = RowVec<VEC>;
     const unsigned lane = lane_id();
     const size_t warp_global = (size_t)blockIdx.x * kRowWarps + (threadIdx.x >> 5);
     const size_t nwarps = (size_t)gridDim.x * kRowWarps;
     const size_t D = c.width, nvec = D / VEC;
     const u32 U = c.regs->U;
-    u32 *cnt = block_counter();
+    u32 *cnt = block_counter(), *cnt_remote = block_counter2();
     if (threadIdx.x == 0)
-        *cnt = 0;
+        *cnt = *cnt_remote = 0;
     __syncthreads();
-    u32 pulled = 0;
+    u32 pulled = 0, pulled_remote = 0;
     for (size_t base = warp_global * 32; base < U; base += nwarps * 32) {
         const size_t i = base + lane;
         i32 s = -1;
@@ -355,6 +390,7 @@ __global__ void __launch_bounds__(kRowBlock)
         }
         unsigned m = __ballot_sync(FULL, need);
         pulled += __popc(m);
+        pulled_remote += __popc(__ballot_sync(FULL, need && owner != c.pv.rank));
         while (m) {
             int src[ROWS];
             i32 rs[ROWS];
@@ -397,9 +433,13 @@ __global__ void __launch_bounds__(kRowBlock)
     }
     if (lane == 0 && pulled)
         atomicAdd(cnt, pulled);
+    if (lane == 0 && pulled_remote)
+        atomicAdd(cnt_remote, pulled_remote);
     __syncthreads();
     if (threadIdx.x == 0 && *cnt)
         atomicAdd(&c.regs->pulled, *cnt);
+    if (threadIdx.x == 0 && *cnt_remote)
+        atomicAdd(&c.regs->pulled_remote, *cnt_remote);
 }
 
 struct IndexFromSlots {
@@ -1048,18 +1088,22 @@ struct AccumulatePush {
     // and adds the gradient again, and an eviction in between counts it as dirty — as the
     // reference does.
     bool defer_cleanup;
+    // every gradient value is multiplied by this first (exact fp32 product, then the exact add):
+    // the -lr fold of ParameterServerCommunicate.py:24,58-59, which the reference does on the host
+    // over the whole gradient before the push; 1 = the gradient arrives scaled (x * 1.0f == x)
+    float scale;
 
     __device__ void kernel_begin() const {
-        u32 *cnt = block_counter();
         if (threadIdx.x == 0)
-            *cnt = 0;
+            *block_counter() = *block_counter2() = 0;
         __syncthreads();
     }
     __device__ void kernel_end() const {
-        u32 *cnt = block_counter();
         __syncthreads();
-        if (threadIdx.x == 0 && *cnt)
-            atomicAdd(&c.regs->pushed, *cnt);
+        if (threadIdx.x == 0 && *block_counter())
+            atomicAdd(&c.regs->pushed, *block_counter());
+        if (threadIdx.x == 0 && *block_counter2())
+            atomicAdd(&c.regs->pushed_remote, *block_counter2());
     }
     __device__ bool in_plan(u64 key) const {
         u32 lo = 0, hi = n_push;
@@ -1131,6 +1175,8 @@ struct AccumulatePush {
             if (local)
                 c.tver[trow] += upd; // PSFhandle_embedding.cc:24
             atomicAdd(block_counter(), 1u);
+            if (c.pv.world > 1 && x.owner != c.pv.rank)
+                atomicAdd(block_counter2(), 1u);
         }
         if (defer_cleanup) {
             c.slot_updates[x.s] = upd;
@@ -1157,8 +1203,9 @@ struct AccumulatePush {
     }
     __device__ Acc step(const Acc &a, const typename V::T &g) const {
         Acc r; // embedding.h:78-91: grad_ += g; data_ += g  (per occurrence, in order)
-        r.g = V::add(a.g, g);
-        r.d = V::add(a.d, g);
+        const typename V::T gs = V::mul(g, scale);
+        r.g = V::add(a.g, gs);
+        r.d = V::add(a.d, gs);
         r.t = a.t;
         return r;
     }
@@ -1213,9 +1260,12 @@ struct FlushPending {
 // ---- multi-GPU exchange -----------------------------------------------------------------
 // lo[o] = first unique index whose key belongs to owner o: the sorted uniques split into
 // contiguous per-owner slices exactly as PSAgent splits them with lower_bound (PSAgent.h:541-559)
+// Also the first kernel of an update that touches peer memory: it waits until every owner has
+// applied the previous exchange (`prev_epoch`), i.e. until the mailboxes may be overwritten.
 __global__ void owner_bounds_kernel(CacheView c, const u64 *__restrict__ uniq,
-                                    const u32 *__restrict__ num_unique) {
+                                    const u32 *__restrict__ num_unique, u64 prev_epoch) {
     pdl_enter();
+    wait_flags(c, c.pv.ctrl + kMaxWorld, prev_epoch);
     const int o = threadIdx.x;
     if (o > c.pv.world)
         return;
@@ -1344,8 +1394,10 @@ __global__ void __launch_bounds__(kRowBlock) flush_resident_kernel(CacheView c) 
         atomicAdd(&c.regs->pushed, flushed);
 }
 
-// Tell every owner how many slots of its two sections this rank filled.
-__global__ void publish_counts_kernel(CacheView c) {
+// End of the sending half of an exchange: tell every owner how many slots of its two sections this
+// rank filled, then raise this rank's `ready` flag at every owner (one launch, after the kernels
+// that wrote the mailboxes).
+__global__ void exchange_arrive_kernel(CacheView c, u64 epoch) {
     pdl_enter();
     const int o = threadIdx.x;
     if (o >= c.pv.world)
@@ -1353,67 +1405,150 @@ __global__ void publish_counts_kernel(CacheView c) {
     u32 *hdr = reinterpret_cast<u32 *>(c.pv.out[o]);
     hdr[0] = c.pv.lo[o + 1] - c.pv.lo[o];
     hdr[1] = min(c.pv.fl_count[o], c.pv.cap);
+    __threadfence_system(); // the mailbox stores of the earlier kernels and the header above
+    raise_flag(c.pv.ctrl_peer[o] + c.pv.rank, epoch);
 }
 
-// Owner side (PSFhandle_embedding.cc:5-28): row += pushed grad; ver += updates, one section of
-// one source rank per launch — the launches walk the sources in rank order, so the order of the
-// adds on a row does not depend on timing.  A warp takes 32 slots, tests them lane-parallel and
-// applies the pushed ones ROWS at a time.
-template <int VEC, int ROWS>
-__global__ void __launch_bounds__(kRowBlock) apply_mailbox_kernel(CacheView c, int src, int section) {
+// Owner side (PSFhandle_embedding.cc:5-28): row += pushed grad; ver += updates.  Several sources
+// push the same hot rows and fp32 adds do not commute, so the adds on one row must happen in a
+// fixed order: source rank, batch section before flush section, slot — the order a serial server
+// fed by the ranks in turn would apply them in.  Two kernels over ALL sources and sections:
+//   link   one thread per mailbox entry: the pushed ones are chained per row through an atomic
+//          exchange on head[row]; the entry that finds the row unclaimed will apply it;
+//   apply  the claiming entry's warp walks the row's chain (<= 2 x world entries unless one source
+//          flushed the same key twice), orders it, and does one read-modify-write of the row with
+//          the gradients added in that order; the last CTA raises `applied` at every peer.
+// An entry id is list * cap + slot with list = 2 * src + section, so ascending ids are the order.
+constexpr u32 kNotPushed = 0xffffffffu;
+constexpr int kMaxChain = 24; // 2 x 8 ranks + room for a key one source flushed more than once
+
+__global__ void __launch_bounds__(256) link_mailbox_kernel(CacheView c, u64 epoch) {
     pdl_enter();
-    using V = RowVec<VEC>;
-    const unsigned lane = lane_id();
-    const size_t warp_global = (size_t)blockIdx.x * kRowWarps + (threadIdx.x >> 5);
-    const size_t nwarps = (size_t)gridDim.x * kRowWarps;
-    const size_t D = c.width, nvec = D / VEC;
+    wait_flags(c, c.pv.ctrl, epoch); // every source has completed its mailbox here
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0)
+        reinterpret_cast<u32 *>(c.pv.ctrl + 2 * kMaxWorld)[0] = 0; // the apply kernel's CTA counter
+    const int list = blockIdx.y, src = list >> 1, section = list & 1;
     char *region = c.pv.in + (size_t)src * c.pv.region_bytes;
     const u32 count = min(reinterpret_cast<const u32 *>(region)[section], c.pv.cap);
-    const MailboxSection mb = mailbox_section(region, section, c.pv.cap, D);
+    const MailboxSection mb = mailbox_section(region, section, c.pv.cap, c.width);
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
+        const u32 e = (u32)list * c.pv.cap + i;
+        const u64 trow = mb.key[i];
+        u32 link = kNotPushed;
+        if (mb.upd[i] != 0 && trow < c.nrows_local)
+            link = atomicExch(&c.pv.head[trow], e + 1);
+        c.pv.next[e] = link;
+    }
+}
+
+template <int VEC, int ROWS>
+__global__ void __launch_bounds__(kRowBlock) apply_linked_kernel(CacheView c, u64 epoch) {
+    pdl_enter();
+    using V = RowVec<VEC>;
+    __shared__ u32 s_chain[kRowWarps][kMaxChain][32]; // [warp][position][lane]: a lane's chain, ascending ids
+    const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
+    const size_t warp_global = (size_t)blockIdx.x * kRowWarps + warp;
+    const size_t nwarps = (size_t)gridDim.x * kRowWarps;
+    const size_t D = c.width, nvec = D / VEC;
+    const u32 cap = c.pv.cap;
+    const int list = blockIdx.y, src0 = list >> 1, section0 = list & 1;
+    char *region0 = c.pv.in + (size_t)src0 * c.pv.region_bytes;
+    const u32 count = min(reinterpret_cast<const u32 *>(region0)[section0], cap);
+    const MailboxSection mb0 = mailbox_section(region0, section0, cap, D);
+    auto section_of = [&](u32 e, u32 &slot) {
+        const u32 l = e / cap;
+        slot = e - l * cap;
+        return mailbox_section(c.pv.in + (size_t)(l >> 1) * c.pv.region_bytes, (int)(l & 1), cap, D);
+    };
     for (size_t base = warp_global * 32; base < count; base += nwarps * 32) {
         const size_t i = base + lane;
-        i32 upd = 0;
-        u64 trow = 0;
-        if (i < count) {
-            upd = mb.upd[i];
-            trow = mb.key[i];
-            if (upd != 0 && trow < c.nrows_local)
-                c.tver[trow] += upd;
-            else
-                upd = 0;
+        // the entry that found its row unclaimed applies the row: every lane walks the chain of its
+        // own row (a handful of dependent loads), keeping the ids in ascending order
+        const bool mine = i < count && c.pv.next[(size_t)list * cap + i] == 0;
+        u64 my_row = 0;
+        u32 n = 0;
+        if (mine) {
+            my_row = mb0.key[i];
+            u32 e1 = c.pv.head[my_row];
+            i64 upd_sum = 0;
+            while (e1 != 0) {
+                const u32 e = e1 - 1;
+                if (n == (u32)kMaxChain) { // absurdly long chain: reported, the excess is not applied
+                    atomicMax(&c.regs->error, (u32)E_MAILBOX);
+                    break;
+                }
+                u32 j = n;
+                while (j > 0 && s_chain[warp][j - 1][lane] > e) {
+                    s_chain[warp][j][lane] = s_chain[warp][j - 1][lane];
+                    j--;
+                }
+                s_chain[warp][j][lane] = e;
+                n++;
+                u32 slot;
+                const MailboxSection mb = section_of(e, slot);
+                upd_sum += mb.upd[slot];
+                e1 = c.pv.next[e];
+            }
+            c.pv.head[my_row] = 0;
+            c.tver[my_row] += upd_sum;
         }
-        unsigned m = __ballot_sync(FULL, upd != 0);
+        __syncwarp();
+        unsigned m = __ballot_sync(FULL, mine);
         while (m) {
             int from[ROWS];
             u64 rt[ROWS];
+            u32 rn[ROWS];
+            u32 max_n = 0;
 #pragma unroll
             for (int r = 0; r < ROWS; r++) {
                 from[r] = m ? __ffs(m) - 1 : -1;
                 if (m)
                     m &= m - 1;
-                rt[r] = __shfl_sync(FULL, trow, from[r] < 0 ? 0 : from[r]);
+                const int f = from[r] < 0 ? 0 : from[r];
+                rt[r] = __shfl_sync(FULL, my_row, f);
+                rn[r] = from[r] < 0 ? 0u : __shfl_sync(FULL, n, f);
+                max_n = max(max_n, rn[r]);
             }
             for (size_t k = lane; k < nvec; k += 32) {
-                typename V::T t[ROWS], g[ROWS];
-#pragma unroll
-                for (int r = 0; r < ROWS; r++)
-                    if (from[r] >= 0) {
-                        t[r] = V::ld(c.trows + rt[r] * D + k * VEC);
-                        g[r] = V::ld(mb.grad + (base + from[r]) * D + k * VEC);
-                    }
+                typename V::T acc[ROWS], g[ROWS];
 #pragma unroll
                 for (int r = 0; r < ROWS; r++)
                     if (from[r] >= 0)
-                        V::st(c.trows + rt[r] * D + k * VEC, V::add(t[r], g[r]));
+                        acc[r] = V::ld(c.trows + rt[r] * D + k * VEC);
+                for (u32 j = 0; j < max_n; j++) {
+#pragma unroll
+                    for (int r = 0; r < ROWS; r++)
+                        if (j < rn[r]) {
+                            u32 slot;
+                            const MailboxSection mb = section_of(s_chain[warp][j][from[r]], slot);
+                            g[r] = V::ld(mb.grad + (size_t)slot * D + k * VEC);
+                        }
+#pragma unroll
+                    for (int r = 0; r < ROWS; r++)
+                        if (j < rn[r])
+                            acc[r] = V::add(acc[r], g[r]);
+                }
+#pragma unroll
+                for (int r = 0; r < ROWS; r++)
+                    if (from[r] >= 0)
+                        V::st(c.trows + rt[r] * D + k * VEC, acc[r]);
             }
         }
+        __syncwarp();
     }
-}
-
-__global__ void barrier_error_kernel(CacheRegs *r, const u32 *barrier_err) {
-    pdl_enter();
-    if (*barrier_err)
-        atomicMax(&r->error, (u32)E_BARRIER);
+    // the last CTA of the grid tells every peer that this shard is up to date
+    __shared__ u32 s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        u32 *done = reinterpret_cast<u32 *>(c.pv.ctrl + 2 * kMaxWorld);
+        s_last = atomicAdd(done, 1u) == gridDim.x * gridDim.y - 1;
+    }
+    __syncthreads();
+    if (s_last && threadIdx.x < (unsigned)c.pv.world) {
+        __threadfence_system();
+        raise_flag(c.pv.ctrl_peer[threadIdx.x] + kMaxWorld + c.pv.rank, epoch);
+    }
 }
 
 // dataless lines are dropped after the push (never inserted)
@@ -1717,13 +1852,25 @@ void setup_mailbox(hb_cache *c, size_t rows) {
     }
     pv.cap = (u32)rows;
     pv.region_bytes = mailbox_region_bytes(rows, c->width);
-    dmalloc_shared(c->mailbox, pv.region_bytes * pv.world);
-    HB_CUDA(cudaMemset(c->mailbox, 0, pv.region_bytes * pv.world));
+    const size_t bytes = kMailboxCtrlBytes + pv.region_bytes * pv.world;
+    dmalloc_shared(c->mailbox, bytes);
+    HB_CUDA(cudaMemset(c->mailbox, 0, bytes));
     c->mailbox_cap = rows;
+    c->xrows_upper = rows;
+    c->xepoch = 0; // the flags of the new control block start at zero on every rank
     ipc_share(c->mailbox, reinterpret_cast<void **>(c->peer_mailbox));
-    pv.in = c->mailbox;
-    for (int o = 0; o < pv.world; o++)
-        pv.out[o] = c->peer_mailbox[o] + (size_t)pv.rank * pv.region_bytes;
+    pv.ctrl = reinterpret_cast<u64 *>(c->mailbox);
+    pv.in = c->mailbox + kMailboxCtrlBytes;
+    for (int o = 0; o < pv.world; o++) {
+        pv.ctrl_peer[o] = reinterpret_cast<u64 *>(c->peer_mailbox[o]);
+        pv.out[o] = c->peer_mailbox[o] + kMailboxCtrlBytes + (size_t)pv.rank * pv.region_bytes;
+    }
+    dfree(pv.next);
+    dmalloc(pv.next, (size_t)2 * pv.world * rows);
+    if (!pv.head) {
+        dmalloc(pv.head, (size_t)c->view.nrows_local);
+        HB_CUDA(cudaMemset(pv.head, 0, std::max<size_t>(c->view.nrows_local, 1) * sizeof(u32)));
+    }
     HB_CHECK(hb_comm_barrier() == 0, "barrier failed"); // every mailbox is zeroed and mapped
 }
 
@@ -1734,6 +1881,7 @@ u64 *clk_of(hb_cache *c) {
 
 void sync_all(hb_cache *c) {
     HB_CUDA(cudaStreamSynchronize(c->side));
+    HB_CUDA(cudaStreamSynchronize(c->side2));
     HB_CUDA(cudaStreamSynchronize(c->h2d));
     HB_CUDA(cudaStreamSynchronize(c->stream));
     HB_CUDA(cudaStreamSynchronize(c->d2h));
@@ -2005,10 +2153,10 @@ void run_sync(hb_cache *c, size_t n, int wsi) {
     int grid = row_grid((n + 31) / 32);
     if (c->width % 4 == 0)
         HB_LAUNCH((sync_kernel<4, 4>), grid, kRowBlock, 0, c->stream, c->view, c->ws[wsi].uniq, c->uslot[0],
-                                                             c->pull_bound);
+                                                             c->pull_bound, (u64)c->xepoch);
     else
         HB_LAUNCH((sync_kernel<1, 4>), grid, kRowBlock, 0, c->stream, c->view, c->ws[wsi].uniq, c->uslot[0],
-                                                             c->pull_bound);
+                                                             c->pull_bound, (u64)c->xepoch);
     HB_LAUNCHED();
 }
 
@@ -2024,8 +2172,7 @@ void run_gather(hb_cache *c, size_t n, int wsi, float *dev_dest) {
     HB_LAUNCHED();
 }
 
-void run_insert(hb_cache *c, size_t n, int clk_stage) {
-    cudaStream_t st = c->stream;
+void run_insert(hb_cache *c, size_t n, int clk_stage, cudaStream_t st) {
     u64 *clk = clk_of(c);
     HB_LAUNCH(plan_insert_kernel, 1, 256, 0, st, c->view, c->bypass ? 1 : 0, clk + clk_stage,
                                           clk + clk_stage + 1);
@@ -2081,27 +2228,29 @@ void run_insert(hb_cache *c, size_t n, int clk_stage) {
     HB_LAUNCHED();
 }
 
-// Multi-GPU: the pushes of this call sit in the owners' mailboxes.  Publish the slot counts,
-// meet the other ranks, apply what this rank received as an owner (sources in rank order: the
-// result does not depend on arrival order), meet again so that no rank reads a shard that is
-// still being updated.  All on the cache's stream, nothing synchronises with the host.
+// Multi-GPU: the pushes of this call sit in the owners' mailboxes.  Three launches, no kernel of
+// their own for the barriers: arrive (counts + `ready` flags) -> link (waits for every source's
+// `ready`, chains the pushed entries per row) -> apply (one ordered read-modify-write per row; its
+// last CTA raises `applied` at every peer).  The next kernel that touches peer memory — the sync
+// of the following lookup, or the next update's owner_bounds — waits for `applied`, so the skew
+// between the ranks is absorbed by whatever runs in between.  Nothing synchronises with the host.
 void exchange_pushes(hb_cache *c) {
     cudaStream_t st = c->stream;
     const int world = c->view.pv.world;
-    HB_LAUNCH(publish_counts_kernel, 1, 32, 0, st, c->view);
+    const u64 epoch = ++c->xepoch;
+    HB_LAUNCH(exchange_arrive_kernel, 1, 32, 0, st, c->view, epoch);
     HB_LAUNCHED();
-    device_barrier(st);
-    const int grid = sm_count() * 4;
-    for (int src = 0; src < world; src++)
-        for (int section = 0; section < 2; section++) {
-            if (c->width % 4 == 0)
-                HB_LAUNCH((apply_mailbox_kernel<4, 4>), grid, kRowBlock, 0, st, c->view, src, section);
-            else
-                HB_LAUNCH((apply_mailbox_kernel<1, 4>), grid, kRowBlock, 0, st, c->view, src, section);
-            HB_LAUNCHED();
-        }
-    device_barrier(st);
-    HB_LAUNCH(barrier_error_kernel, 1, 1, 0, st, c->view.regs, g_comm.barrier_err);
+    const size_t per_list = std::max<size_t>(c->xrows_upper, 1);
+    const int lgrid = (int)std::max<size_t>(1, std::min<size_t>((per_list + 255) / 256, (size_t)sm_count()));
+    HB_LAUNCH(link_mailbox_kernel, dim3(lgrid, 2 * world), 256, 0, st, c->view, epoch);
+    HB_LAUNCHED();
+    const size_t groups = (per_list + 31) / 32;
+    const int agrid = (int)std::max<size_t>(1, std::min<size_t>((groups + kRowWarps - 1) / kRowWarps,
+                                                               (size_t)sm_count() * 8 / (2 * world) + 1));
+    if (c->width % 4 == 0)
+        HB_LAUNCH((apply_linked_kernel<4, 4>), dim3(agrid, 2 * world), kRowBlock, 0, st, c->view, epoch);
+    else
+        HB_LAUNCH((apply_linked_kernel<1, 4>), dim3(agrid, 2 * world), kRowBlock, 0, st, c->view, epoch);
     HB_LAUNCHED();
 }
 
@@ -2111,7 +2260,7 @@ void run_accumulate(hb_cache *c, size_t n, int batch, int wsi, const float *dev_
     cudaStream_t st = c->stream;
     KeyWorkspace &ws = c->ws[wsi];
     if (c->view.pv.world > 1) {
-        HB_LAUNCH(owner_bounds_kernel, 1, 32, 0, st, c->view, ws.uniq, ws.num_unique);
+        HB_LAUNCH(owner_bounds_kernel, 1, 32, 0, st, c->view, ws.uniq, ws.num_unique, (u64)c->xepoch);
         HB_LAUNCHED();
     }
     if (n) {
@@ -2123,9 +2272,9 @@ void run_accumulate(hb_cache *c, size_t n, int batch, int wsi, const float *dev_
             plan_n = 0;
         }
         AccumulatePush<1> f1{c->view, ws.uniq, c->uslot[batch], c->push_bound, plan, plan_n,
-                             defer_cleanup};
+                             defer_cleanup, c->grad_scale};
         AccumulatePush<4> f4{c->view, ws.uniq, c->uslot[batch], c->push_bound, plan, plan_n,
-                             defer_cleanup};
+                             defer_cleanup, c->grad_scale};
         run_segment_reduce(ws, p, dev_grads, c->width, n, vec4(c, dev_grads), c->hot_threshold, st,
                            f1, f4, [&] {
                                if (batch == 0)
@@ -2423,11 +2572,12 @@ int hb_cache_create(int policy, size_t limit, size_t length, size_t width, int n
     c->hot_threshold = default_hot_threshold();
     HB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     HB_CUDA(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
+    HB_CUDA(cudaStreamCreateWithFlags(&c->side2, cudaStreamNonBlocking));
     HB_CUDA(cudaStreamCreateWithFlags(&c->h2d, cudaStreamNonBlocking));
     HB_CUDA(cudaStreamCreateWithFlags(&c->d2h, cudaStreamNonBlocking));
     for (cudaEvent_t *e : {&c->ev_ws_free[0], &c->ev_ws_free[1], &c->ev_sorted[0], &c->ev_sorted[1],
                            &c->ev_up, &c->ev_grads_free, &c->ev_gathered[0], &c->ev_gathered[1],
-                           &c->ev_dl[0], &c->ev_dl[1]})
+                           &c->ev_dl[0], &c->ev_dl[1], &c->ev_producer, &c->ev_fork, &c->ev_join})
         HB_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
     // row store: limit resident lines + slack for the running call's fresh lines and for dirty
     // victims waiting for the next push
@@ -2497,6 +2647,9 @@ int hb_cache_create(int policy, size_t limit, size_t length, size_t width, int n
         pv.rows[0] = t->rows;
         pv.ver[0] = t->ver;
     }
+    pv.timeout_ns = 120ull * 1000000000ull;
+    if (const char *e = getenv("HERALD_PEER_TIMEOUT_S"))
+        pv.timeout_ns = std::max<u64>(1, strtoull(e, nullptr, 10)) * 1000000000ull;
     dmalloc(pv.lo, kMaxWorld + 1);
     dmalloc(pv.fl_count, kMaxWorld);
     HB_CUDA(cudaMemset(pv.lo, 0, (kMaxWorld + 1) * sizeof(u32)));
@@ -2562,6 +2715,8 @@ int hb_cache_destroy(hb_cache *c) {
         dfree(v.regs);
         dfree(v.pv.lo);
         dfree(v.pv.fl_count);
+        dfree(v.pv.head);
+        dfree(v.pv.next);
         if (c->mailbox) {
             hb_comm_barrier(); // nobody still writes into this rank's mailboxes
             ipc_unshare(reinterpret_cast<void **>(c->peer_mailbox));
@@ -2588,10 +2743,11 @@ int hb_cache_destroy(hb_cache *c) {
             cudaEventDestroy(e);
         for (cudaEvent_t e : {c->ev_ws_free[0], c->ev_ws_free[1], c->ev_sorted[0], c->ev_sorted[1],
                               c->ev_up, c->ev_grads_free, c->ev_gathered[0], c->ev_gathered[1],
-                              c->ev_dl[0], c->ev_dl[1]})
+                              c->ev_dl[0], c->ev_dl[1], c->ev_producer, c->ev_fork, c->ev_join})
             cudaEventDestroy(e);
         cudaStreamDestroy(c->stream);
         cudaStreamDestroy(c->side);
+        cudaStreamDestroy(c->side2);
         cudaStreamDestroy(c->h2d);
         cudaStreamDestroy(c->d2h);
         delete c;
@@ -2610,6 +2766,30 @@ int hb_cache_get_bounds(hb_cache *c, int64_t *pull_bound, int64_t *push_bound) {
     HB_API_BEGIN();
     *pull_bound = c->pull_bound;
     *push_bound = c->push_bound;
+    HB_API_END();
+}
+
+int hb_cache_set_grad_scale(hb_cache *c, float scale) {
+    HB_API_BEGIN();
+    c->grad_scale = scale;
+    HB_API_END();
+}
+
+int hb_cache_get_grad_scale(hb_cache *c, float *scale) {
+    HB_API_BEGIN();
+    *scale = c->grad_scale;
+    HB_API_END();
+}
+
+int hb_cache_after_stream(hb_cache *c, void *producer_stream) {
+    HB_API_BEGIN();
+    Guard g(c->device);
+    cudaStream_t ps = (cudaStream_t)producer_stream;
+    HB_CUDA(cudaEventRecord(c->ev_producer, ps));
+    // keys are read by the sort (side), gradients by the accumulate kernel (main) or staged by a
+    // device-to-device-free path: both streams order themselves behind the producer
+    HB_CUDA(cudaStreamWaitEvent(c->side, c->ev_producer, 0));
+    HB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_producer, 0));
     HB_API_END();
 }
 
@@ -2695,13 +2875,26 @@ int hb_cache_lookup(hb_cache *c, const void *keys, int key_kind, size_t n, float
     float *ddest = stage_dest(c, dest, n, &k);
     begin_call(c, false, w);
     resolve_batch(c, n, 0, w, /*dataless=*/false, 0);
+    // The insert phase (victim selection, evictions, index inserts) needs the resolve's results
+    // only: it works on slot scalars and the index, never on row data, and its victims are never
+    // lines of this batch — so it runs on its own stream NEXT TO sync + gather, which move the rows.
+    const bool fork = n >= 4096; // (a small call is launch-bound: keep it on one stream)
+    if (fork) {
+        HB_CUDA(cudaEventRecord(c->ev_fork, c->stream));
+        HB_CUDA(cudaStreamWaitEvent(c->side2, c->ev_fork, 0));
+        run_insert(c, n, 1, c->side2);
+        HB_CUDA(cudaEventRecord(c->ev_join, c->side2));
+    }
     run_sync(c, n, w);
     mark(c, 2);
     run_gather(c, n, w, ddest);
     mark(c, 3);
     release_ws(c, w); // the insert phase works on slots, not on the workspace
     download_dest(c, dest, ddest, n, k);
-    run_insert(c, n, 1);
+    if (fork)
+        HB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
+    else
+        run_insert(c, n, 1, c->stream);
     c->pending_upper += n;
     end_call(c, 2, 0, n, true);
     HB_API_END();
@@ -2755,7 +2948,7 @@ int hb_cache_push_pull(hb_cache *c, const void *pull_keys, int pull_kind, size_t
     run_gather(c, n_pull, wpull, ddest);
     release_ws(c, wpull);
     download_dest(c, dest, ddest, n_pull, k);
-    run_insert(c, n_pull, 2);
+    run_insert(c, n_pull, 2, st);
     if (n_push) {
         HB_LAUNCH(cleanup_pushed_kernel, lin_grid(n_push), 256, 0, st, c->view, c->uslot[1], c->push_bound);
         HB_LAUNCHED();
@@ -2866,6 +3059,7 @@ static void fill_perf(hb_cache *c, uint64_t call, hb_perf *perf) {
     perf->num_miss = r.num_miss;
     perf->num_evict = r.num_evict;
     perf->num_transfered = r.num_transfered;
+    perf->num_remote = r.num_remote;
     perf->is_full = r.limit_full;
     perf->size = r.size;
     perf->error = r.error;
@@ -3158,7 +3352,7 @@ int hb_cache_insert(hb_cache *c, uint64_t key, int64_t version, const float *dat
         HB_CHECK(hslot >= 0, "no free slot for insert");
         HB_LAUNCH(set_line_kernel, 1, 128, 0, st, c->view, hslot, version, ddata);
         HB_LAUNCHED();
-        run_insert(c, 1, 0);
+        run_insert(c, 1, 0, st);
         c->pending_upper += 1;
         end_call(c, 1, 0, 1, true);
     }

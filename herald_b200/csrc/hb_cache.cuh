@@ -89,7 +89,17 @@ struct PeerView {
     u32 cap;       // slots per section
     u32 *lo;       // [world + 1] first unique index of each owner's key range (per call)
     u32 *fl_count; // [world] flush slots taken per owner (per call)
+    // Exchange control block of THIS cache (one per rank, in front of its mailboxes, mapped into
+    // every peer): ready[src] = last exchange whose mailbox contents source `src` has completed
+    // here; applied[owner] = last exchange owner `owner` has applied to its shard.  Epochs count
+    // the exchanges of this cache, so several caches never share a flag.
+    u64 *ctrl;               // local: ready[kMaxWorld], applied[kMaxWorld], then 2 u32 scratch counters
+    u64 *ctrl_peer[kMaxWorld];
+    u32 *head; // [nrows_local] newest mailbox entry (+1) of each local row during an apply, 0 otherwise
+    u32 *next; // [2 * world * cap] entry -> the entry linked before it (+1), 0 = first, ~0 = not pushed
+    u64 timeout_ns; // a peer that does not show up within this fails the call (E_BARRIER)
 };
+constexpr size_t kMailboxCtrlBytes = 4096;
 
 struct MailboxSection {
     u64 *key;
@@ -161,6 +171,8 @@ struct CacheRegs {
     u32 sel_fallback; // the threshold was not inside the window: run the full-range pass
     u32 sel_use_log;  // LRU: this call selects its victims by walking the stamp log
     u64 sel_floor0;   // floor at the start of the selection (the log walk moves `floor` itself)
+    // multi-GPU traffic of the call (zeroed by op_begin): rows pulled from / lines pushed to a PEER
+    u32 pulled_remote, pushed_remote;
 };
 
 // Everything a kernel needs to address the cache (passed by value).
@@ -223,7 +235,7 @@ struct PerfRecord {
     u32 kind; // 0 pull, 1 push, 2 push_pull
     u32 num_all, num_unique, num_miss, num_evict, num_transfered;
     u32 size, error, ht_occupied, pending, limit_full;
-    u32 pad;
+    u32 num_remote; // Pull: rows read from a peer's shard; Push: lines deposited in a peer's mailbox
     u64 clock, floor; // replacement clock and victim-class floor after the call
 };
 
@@ -242,6 +254,8 @@ struct hb_cache {
     // previous call; `h2d` / `d2h` move host callers' gradients in and gathered rows out, so that
     // an upload, a download and the kernels of a third call can overlap (PCIe is full duplex).
     cudaStream_t stream = nullptr, side = nullptr, h2d = nullptr, d2h = nullptr;
+    cudaStream_t side2 = nullptr;               // a lookup's insert phase, next to its sync + gather
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     int cur = 0;                                // workspace that holds the most recent lookup batch
     cudaEvent_t ev_ws_free[2] = {nullptr, nullptr}; // main: the readers of ws[i] enqueued so far are done
     cudaEvent_t ev_sorted[2] = {nullptr, nullptr};  // side: ws[i] holds uniq / inverse / segments
@@ -249,6 +263,8 @@ struct hb_cache {
     cudaEvent_t ev_grads_free = nullptr;        // main: the gradient staging buffer has been consumed
     cudaEvent_t ev_gathered[2] = {nullptr, nullptr}; // main: dest staging buffer k is complete
     cudaEvent_t ev_dl[2] = {nullptr, nullptr};       // d2h: download out of staging buffer k is done
+    cudaEvent_t ev_producer = nullptr;          // a caller's stream: its device buffers are ready
+    float grad_scale = 1.0f;                    // gradients are multiplied by this (the -lr fold)
     int dl_next = 0;                            // dest staging buffer of the next host-dest lookup
     int dl_of_call[1024] = {};                  // [kRing] 1 + staging buffer a call downloads from, 0 = none
     uint64_t dl_seq[2] = {0, 0};                // call whose download ev_dl[k] stands for (+1)
@@ -292,4 +308,6 @@ struct hb_cache {
     char *mailbox = nullptr;              // this rank's regions as an owner
     char *peer_mailbox[hb::kMaxWorld] = {}; // every owner's regions, mapped
     size_t mailbox_cap = 0;
+    size_t xrows_upper = 0;   // most entries one mailbox section can hold (sizes the apply grids)
+    uint64_t xepoch = 0;      // exchanges of THIS cache enqueued so far (same on every rank)
 };

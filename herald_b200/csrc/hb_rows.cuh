@@ -21,6 +21,9 @@ struct RowVec<4> {
     static __device__ __forceinline__ T add(const T &a, const T &b) {
         return add4(a, b);
     }
+    static __device__ __forceinline__ T mul(const T &a, float s) { // exact fp32 products, never fused
+        return make_float4(__fmul_rn(a.x, s), __fmul_rn(a.y, s), __fmul_rn(a.z, s), __fmul_rn(a.w, s));
+    }
     static __device__ __forceinline__ T ld_nc(const float *p) {
         return ld_stream(reinterpret_cast<const float4 *>(p));
     }
@@ -49,6 +52,9 @@ struct RowVec<1> {
     }
     static __device__ __forceinline__ T add(const T &a, const T &b) {
         return __fadd_rn(a, b);
+    }
+    static __device__ __forceinline__ T mul(const T &a, float s) {
+        return __fmul_rn(a, s);
     }
     static __device__ __forceinline__ T ld_nc(const float *p) {
         return __ldg(p);

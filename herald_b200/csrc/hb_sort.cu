@@ -100,7 +100,7 @@ __device__ __forceinline__ u64 pack_status(u32 epoch, u32 flag, u32 value) {
 // the input / output of the pass is one packed word per key, key << 32 | original index (used
 // when the keys fit 32 bits: one scattered store per key instead of two).
 template <int KIND, bool FIRST, bool PIN, bool POUT>
-__global__ void __launch_bounds__(SORT_THREADS)
+__global__ void __launch_bounds__(SORT_THREADS, 1)
     sort_pass_kernel(const void *kin, const u32 *vin, u64 *kout, u32 *vout, size_t n, int shift,
                      const u32 *__restrict__ totals, u64 *status, u32 *counts, u32 *ticket, u32 epoch,
                      const u32 *mismatch) {

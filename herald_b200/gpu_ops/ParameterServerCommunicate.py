@@ -5,11 +5,13 @@ Keeps the three execution modes of the reference (table in SURVEY §9):
   bsp == 0, prefetch      _compute_bsp_prefetch : update -> wait -> barrier -> lookup(next batch)
   bsp != 0, prefetch      _compute_asp_prefetch : one fused push_pull
   no prefetch             _compute_no_prefetch  : update only (lookup happens in the forward op)
-The gradient is scaled by -lr before it reaches the cache, as the reference does on the host
-(:24, :58-59); here the values stay wherever they are (GPU or pinned host).
+The reference multiplies the sparse gradient by -lr on the host before every push (:24, :58-59).
+Here the factor is handed to the cache (`grad_scale`) and applied inside the accumulate kernel —
+one exact fp32 product per value, then the exact add: bit-identical to scaling first — so the
+gradient is never copied or rewritten, wherever it lives (GPU or pinned host).  `input_val.values`
+therefore keeps the RAW gradient.  When the executor passes its stream, the cache's streams are
+ordered behind it (the gradient may still be in flight there).
 """
-import numpy as np
-
 from .. import ndarray
 from ..cstable import CacheSparseTable
 from ..stream import CSEvent
@@ -24,12 +26,9 @@ class ParameterServerCommunicateOp(object):
         self.cache = None
 
     def _mult_lr_sparse(self, input_val, stream_handle):
-        vals = input_val.values
-        if ndarray.is_gpu_ctx(vals.ctx):
-            scaled = ndarray.array(vals.asnumpy() * np.float32(self.learning_rate), vals.ctx)
-            input_val.values = scaled
-        else:
-            vals[:] = vals.asnumpy() * np.float32(self.learning_rate)
+        # folded into the update kernel; ordered behind the stream that produces the gradient
+        self.cache.cache.grad_scale = self.learning_rate
+        self.cache.cache.after(stream_handle)
 
     def _push_cache(self, input_val, stream_handle):
         if input_val.push_indices is None:

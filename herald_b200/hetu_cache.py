@@ -28,7 +28,7 @@ class hb_perf(ctypes.Structure):
                 ("time_ms", ctypes.c_float), ("sort_ms", ctypes.c_float),
                 ("lookup_ms", ctypes.c_float), ("transfer_ms", ctypes.c_float),
                 ("copy_ms", ctypes.c_float), ("insert_ms", ctypes.c_float),
-                ("kernel_ms", ctypes.c_float)]
+                ("kernel_ms", ctypes.c_float), ("num_remote", ctypes.c_int64)]
 
 
 def _proto():
@@ -39,6 +39,9 @@ def _proto():
     L.hb_cache_get_bounds.argtypes = [_vp, ctypes.POINTER(ctypes.c_int64),
                                       ctypes.POINTER(ctypes.c_int64)]
     L.hb_cache_set_bypass.argtypes = [_vp, ctypes.c_int]
+    L.hb_cache_set_grad_scale.argtypes = [_vp, ctypes.c_float]
+    L.hb_cache_get_grad_scale.argtypes = [_vp, ctypes.POINTER(ctypes.c_float)]
+    L.hb_cache_after_stream.argtypes = [_vp, _vp]
     L.hb_cache_set_perf.argtypes = [_vp, ctypes.c_int]
     L.hb_cache_set_perf_sampling.argtypes = [_vp, ctypes.c_uint]
     L.hb_cache_reserve.argtypes = [_vp, _sz]
@@ -184,6 +187,26 @@ class CacheBase(object):
     def push_bound(self, v):
         check_call(_LIB.hb_cache_set_bounds(self._h, self._bounds()[0], int(v)))
 
+    @property
+    def grad_scale(self):
+        """Factor every gradient value is multiplied by inside the update kernel (herald_b200
+        extension: the -lr fold the reference does on the host, ParameterServerCommunicate.py:58-59)."""
+        v = ctypes.c_float()
+        check_call(_LIB.hb_cache_get_grad_scale(self._h, ctypes.byref(v)))
+        return v.value
+
+    @grad_scale.setter
+    def grad_scale(self, v):
+        check_call(_LIB.hb_cache_set_grad_scale(self._h, float(v)))
+
+    def after(self, stream_handle):
+        """Order the cache's work behind a caller's DLStream (device-pointer callers whose keys /
+        gradients are still being produced on that stream)."""
+        if stream_handle is None:
+            return
+        raw = ctypes.cast(stream_handle.handle.contents.handle, ctypes.POINTER(_vp)).contents
+        check_call(_LIB.hb_cache_after_stream(self._h, raw))
+
     def bypass(self):
         check_call(_LIB.hb_cache_set_bypass(self._h, 1))
 
@@ -247,7 +270,7 @@ class CacheBase(object):
                      "num_miss": int(p.num_miss), "num_transfered": int(p.num_transfered),
                      "time": float(p.time_ms), "sort_time": float(p.sort_ms),
                      "lookup_time": float(p.lookup_ms), "transfer_time": float(p.transfer_ms),
-                     "copy_time": float(p.copy_ms)}
+                     "copy_time": float(p.copy_ms), "num_remote": int(p.num_remote)}
                 if kinds[k] == 0:
                     d["prepare_time"] = 0.0
                     d["insert_time"] = float(p.insert_ms)

@@ -224,6 +224,7 @@ typedef struct {
     float sort_ms, lookup_ms, transfer_ms, copy_ms, insert_ms; /* phase split      */
     float kernel_ms;        /* Push: the accumulate kernel alone (copy_ms minus its plan
                                kernel); 0 when the call carried no phase events        */
+    int64_t num_remote;     /* multi-GPU: rows pulled from / lines pushed to a PEER GPU   */
 } hb_perf;
 
 /* limit/len/width/node_id as the reference constructors (python_api.cc:54-76).
@@ -234,6 +235,17 @@ int hb_cache_destroy(hb_cache *c);
 int hb_cache_set_bounds(hb_cache *c, int64_t pull_bound, int64_t push_bound);
 int hb_cache_get_bounds(hb_cache *c, int64_t *pull_bound, int64_t *push_bound);
 int hb_cache_set_bypass(hb_cache *c, int on);                   /* cache.cc:15-35 */
+/* Fold of -lr into the update (python/hetu/gpu_ops/ParameterServerCommunicate.py:24,58-59: the
+ * reference multiplies the whole sparse gradient by -lr ON THE HOST before every push).  With a
+ * scale set, hb_cache_update* / push_pull take the RAW gradient and every value is multiplied by
+ * (float)scale inside the accumulate kernel — one exact fp32 product, then the exact add: bit-
+ * identical to scaling first.  Default 1 (gradients arrive scaled). */
+int hb_cache_set_grad_scale(hb_cache *c, float scale);
+int hb_cache_get_grad_scale(hb_cache *c, float *scale);
+/* Device-pointer callers: order the cache's streams behind `producer_stream` (a cudaStream_t),
+ * i.e. behind the kernels that are still writing the keys / gradients of the next call — what the
+ * executor's stream_handle + event is for in ParameterServerCommunicate.py:27-35. */
+int hb_cache_after_stream(hb_cache *c, void *producer_stream);
 /* perf_enabled (python_api.cc:40-41): also records the per-phase CUDA events behind
  * hb_perf.sort_ms / lookup_ms / transfer_ms / copy_ms / insert_ms. */
 int hb_cache_set_perf(hb_cache *c, int on);

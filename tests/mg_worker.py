@@ -50,6 +50,14 @@ def main():
     gc.perf_enabled = True
     gc.pull_bound, gc.push_bound = bound, bound
     comm.BarrierWorker()
+    if os.environ.get("MG_TABLES", "1") == "2":
+        two_tables(rank, world, comm, oracle, gc, table, rows, policy, bound, V, D, limit, steps, max_n)
+        del gc
+        comm.ClearTensor(7001)
+        ps.group_finalize()
+        dist.destroy_process_group()
+        print("mg_worker rank %d/%d ok (%s bound %d, two tables)" % (rank, world, policy, bound), flush=True)
+        return
 
     osrv = oracle.Server(V, D, rows)
     ocs = [oracle.Cache(osrv, policy, limit) for _ in range(world)]
@@ -96,6 +104,81 @@ def main():
     ps.group_finalize()
     dist.destroy_process_group()
     print("mg_worker rank %d/%d ok (%s bound %d)" % (rank, world, policy, bound), flush=True)
+
+
+def two_tables(rank, world, comm, oracle, gc_a, table_a, rows_a, policy, bound, V, D, limit, steps, max_n):
+    """Two embedding tables, each with its own cache, driven INTERLEAVED and asynchronously (both
+    updates enqueued before either is waited for): every cache has its own exchange flags and
+    epochs, so the two exchanges may overlap in any order on the devices (with one
+    process-global barrier epoch this corrupted a mailbox or timed out)."""
+    import herald_b200 as hb
+    from herald_b200 import ps, hetu_cache
+    from common import assert_bits_equal, perf_subset, PULL_KEYS, PUSH_KEYS, zipf_keys
+    Vb, Db, limit_b = 777, 16, 90
+    rows_b = np.random.default_rng(5).normal(0, 0.01, (Vb, Db)).astype(np.float32)
+    table_b = comm.InitTensor(7002, ps.kCacheTable, Vb, Db, ps.Constant, 0.0)
+    table_b.load_rows(rows_b)
+    cls = {"lru": hetu_cache.LRUCache, "lfu": hetu_cache.LFUCache, "lfuopt": hetu_cache.LFUOptCache}[policy]
+    gc_b = cls(limit_b, Vb, Db, 7002)
+    gc_b.perf_enabled = True
+    gc_b.pull_bound, gc_b.push_bound = bound, bound
+    comm.BarrierWorker()
+    tabs = [dict(gc=gc_a, table=table_a, V=V, D=D, limit=limit, rows=rows_a, seed=0),
+            dict(gc=gc_b, table=table_b, V=Vb, D=Db, limit=limit_b, rows=rows_b, seed=500000)]
+    for tb in tabs:
+        tb["osrv"] = oracle.Server(tb["V"], tb["D"], tb["rows"])
+        tb["ocs"] = [oracle.Cache(tb["osrv"], policy, tb["limit"]) for _ in range(world)]
+        for oc in tb["ocs"]:
+            oc.set_bounds(bound, bound)
+
+    def batch(tb, w, t):
+        rng = np.random.default_rng(tb["seed"] + 1000 * t + w)
+        n = int(rng.integers(1, max_n))
+        return zipf_keys(rng, n, tb["V"], 1.2), rng.normal(0, 1e-3, (n, tb["D"])).astype(np.float32)
+
+    def lookups(t):
+        mine = []
+        for tb in tabs:                                        # enqueue both, then wait
+            keys, _ = batch(tb, rank, t)
+            dest = np.zeros((keys.size, tb["D"]), np.float32)
+            mine.append((tb["gc"].embedding_lookup(keys, dest), dest))
+        for (w8, dest), tb in zip(mine, tabs):
+            w8.wait()
+            for w in range(world):
+                keys, _ = batch(tb, w, t)
+                exp = tb["ocs"][w].embedding_lookup(keys)
+                if w == rank:
+                    assert_bits_equal(dest, exp, "rank %d step %d rows" % (rank, t))
+                    g, o = tb["gc"].perf[-1], tb["ocs"][w].perf[-1]
+                    assert perf_subset(g, PULL_KEYS) == perf_subset(o, PULL_KEYS), (rank, t, g, dict(o))
+
+    lookups(0)
+    for t in range(steps):
+        waits = []
+        for tb in tabs:
+            keys, grads = batch(tb, rank, t)
+            waits.append(tb["gc"].embedding_update(keys, grads))
+        for w8, tb in zip(waits, tabs):
+            w8.wait()
+            for w in range(world):
+                keys, grads = batch(tb, w, t)
+                tb["ocs"][w].embedding_update(keys, grads)
+                if w == rank:
+                    g, o = tb["gc"].perf[-1], tb["ocs"][w].perf[-1]
+                    assert perf_subset(g, PUSH_KEYS) == perf_subset(o, PUSH_KEYS), (rank, t, g, dict(o))
+        comm.BarrierWorker()
+        lookups(t + 1)
+    comm.BarrierWorker()
+    from herald_b200 import partition
+    for tb in tabs:
+        begin, n = partition.shard_range(rank, world, tb["V"])
+        assert_bits_equal(tb["table"].read_rows(), tb["osrv"].rows()[begin:begin + n], "owner rows")
+        assert np.array_equal(tb["table"].read_versions(), tb["osrv"].versions()[begin:begin + n])
+        assert np.array_equal(tb["gc"].keys(), tb["ocs"][rank].keys())
+    comm.BarrierWorker()
+    tabs[1]["gc"] = None
+    del gc_b
+    comm.ClearTensor(7002)
 
 
 if __name__ == "__main__":

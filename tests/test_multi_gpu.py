@@ -42,6 +42,20 @@ def test_group_of_two(policy, bound):
     _run(2, MG_POLICY=policy, MG_BOUND=bound)
 
 
+def test_two_tables_interleaved():
+    """Two caches per rank, their exchanges enqueued back to back (per-cache exchange flags)."""
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs")
+    _run(2, MG_POLICY="lru", MG_BOUND=0, MG_TABLES=2, MG_STEPS=15)
+
+
+def test_bench_shape_rows_through_the_mailbox():
+    """D = 128 rows and thousands of keys per call through the owner mailboxes and remote pulls."""
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs")
+    _run(2, MG_POLICY="lru", MG_BOUND=0, MG_V=50021, MG_D=128, MG_LIMIT=6000, MG_N=20000, MG_STEPS=8)
+
+
 def test_group_of_all_gpus():
     n = min(_ngpu(), 8)
     if n < 4:
