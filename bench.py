@@ -37,17 +37,33 @@ VOCAB = 33762577          # examples/ctr/models/wdl_criteo.py:9
 ZIPF_A = 1.05
 
 
+# BASELINE.json `configs`, in order.  The per-GPU call shape is what a preset fixes; --gpus picks
+# the group size (c3 / c4 are quoted on 8 GPUs, c5 is a sweep: scripts/sweep_c5.sh).
+CONFIGS = {
+    "c1": dict(batch=256, dim=128, vocab=VOCAB, policy="lru", bound=0, plan=False,
+               note="wdl_criteo, 1 worker + local PS, LRU 0.1, batch 256, emb 128 (examples/ctr/run_hetu.py)"),
+    "c2": dict(batch=8192, dim=128, vocab=VOCAB, policy="lru", bound=0, plan=False,
+               note="wdl_criteo single B200, LRU 0.1, batch 8192, emb 128, 26 fields, Zipf(1.05)"),
+    "c3": dict(batch=8192, dim=128, vocab=VOCAB, policy="lfu", bound=0, plan=False,
+               note="dcn_criteo 8 GPUs row-sharded, LFU, bound 0 (BSP); same 26-field / V sparse side"),
+    "c4": dict(batch=8192, dim=512, vocab=VOCAB, policy="lru", bound=10, plan=True,
+               note="run_laia wdl_criteo 8 GPUs, Herald plans (update_with_push_keys), bound 10, emb 512"),
+    "c5": dict(batch=65536, dim=128, vocab=100_000_000, policy="lru", bound=0, plan=False,
+               note="scaling sweep point: 1e8-row table, emb 128/512 (--dim), batch 2k-64k (--batch)"),
+}
+
+
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="herald_b200", choices=["herald_b200", "reference"])
-    ap.add_argument("--batch", type=int, default=8192)
-    ap.add_argument("--dim", type=int, default=128)
-    ap.add_argument("--vocab", type=int, default=VOCAB)
-    ap.add_argument("--policy", default="lru")
-    ap.add_argument("--bound", type=int, default=0)
+    ap.add_argument("--batch", type=int, default=None)
+    ap.add_argument("--dim", type=int, default=None)
+    ap.add_argument("--vocab", type=int, default=None)
+    ap.add_argument("--policy", default=None)
+    ap.add_argument("--bound", type=int, default=None)
     ap.add_argument("--ratio", type=float, default=0.1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -58,9 +74,19 @@ def parse_args():
                          "replay on a 1M-row side table); 0 = off")
     ap.add_argument("--ids", default="permuted", choices=["permuted", "folded"],
                     help="Zipf rank -> row: fixed permutation (default, SURVEY 8d) or rank == row")
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS),
+                    help="BASELINE.json configs[0..4] presets (c2 = the headline config, default); the "
+                         "individual flags are filled from the preset unless given")
+    ap.add_argument("--plan", action="store_true", default=None,
+                    help="drive the updates with Laia / Herald communication plans "
+                         "(embedding_update_with_push_keys, run_laia.py): c4")
     ap.add_argument("--seg-trace", default=None,
                     help="diagnostics: write the per-CTA timeline of one segment_reduce launch here")
     args = ap.parse_args()
+    for k, v in CONFIGS[args.config].items():
+        if k != "note" and getattr(args, k, None) is None:
+            setattr(args, k, v)
+    args.plan = bool(args.plan)
     global _IDS_MODE
     _IDS_MODE = args.ids
     return args
@@ -107,6 +133,39 @@ def hottest_ids(lo, hi, vocab, dtype):
     ids = rank_to_id(np.arange(lo, hi), vocab).astype(np.float32)
     _, first = np.unique(ids, return_index=True)
     return ids[np.sort(first)].astype(dtype)
+
+
+def rotating_buffers(args):
+    """Gradient / destination buffer pairs the timed loop rotates through: at least 3, and enough
+    that one round of them exceeds twice the 126 MB L2 (small batches: c1)."""
+    pair = 2 * args.batch * FIELDS * args.dim * 4
+    return int(min(64, max(3, -(-2 * 126_000_000 // pair))))
+
+
+def laia_schedule(args, rank, world, nbatch):
+    """Herald / Laia workload (run_laia.py): the planner — replicated on every rank, as in the
+    reference — assigns the samples of each global batch to the workers and emits per worker the
+    keys it must push so that its peers find them fresh in the NEXT batch (laia_scheduler.cc:115-271).
+    -> (ids[b] float32 [B, 26] of this rank, plans[b] uint64 ascending) for b in [0, nbatch).
+    plans[b + 1] is the push_keys argument of update(batch b) (laia_dataloader.py:108-114: the
+    first plan is dropped).  Planning runs ahead of training in the reference (its own thread and a
+    queue); here it is done before the timed region."""
+    from herald_b200.laia import LaiaScheduler
+    B, V = args.batch, args.vocab
+    embs = np.concatenate([make_ids(b, B * world, V, 0).astype(np.uint64) for b in range(nbatch)])
+    sched = LaiaScheduler()
+    sched.start(embs, embs.shape[0], FIELDS, 1, B, nbatch, world, rank, cache_limit(V, args.ratio), 16)
+    ids, plans = [], []
+    t0 = time.perf_counter()
+    for b in range(nbatch):
+        if not sched.step():
+            break
+        plans.append(sched.plan_of(rank).copy())
+        ids.append(embs[sched.dist_of(rank).astype(np.int64)].astype(np.float32))
+    planner_ms = (time.perf_counter() - t0) * 1e3 / max(1, len(ids))
+    sched.close()
+    assert len(ids) == nbatch, "the planner ended early"
+    return ids, plans, planner_ms
 
 
 def cache_limit(vocab, ratio):
@@ -240,7 +299,14 @@ def run_cpu_reference(args, steps, warmup, mirror=None):
     N = B * FIELDS
     grads = make_grads(B, D, 0)
     dest = np.empty((N, D), np.float32)
-    ids = [make_ids(s, B, vocab).reshape(-1).astype(np.uint64) for s in range(steps + warmup + 1)]
+    plans = None
+    if args.plan:
+        saved, args.vocab = args.vocab, vocab
+        ids_f, plans, _ = laia_schedule(args, 0, 1, steps + warmup + 2)
+        args.vocab = saved
+        ids = [a.reshape(-1).astype(np.uint64) for a in ids_f]
+    else:
+        ids = [make_ids(s, B, vocab).reshape(-1).astype(np.uint64) for s in range(steps + warmup + 1)]
     cache.embedding_lookup(ids[0], dest)
     parity = None
     check = mirror is not None and "skipped" not in mirror
@@ -252,7 +318,7 @@ def run_cpu_reference(args, steps, warmup, mirror=None):
     times = []
     for s in range(steps + warmup):
         t0 = time.perf_counter()
-        cache.embedding_update(ids[s], grads)
+        cache.embedding_update(ids[s], grads, None if plans is None else plans[s + 1])
         cache.embedding_lookup(ids[s + 1], dest)
         dt = time.perf_counter() - t0
         if s >= warmup:
@@ -307,13 +373,17 @@ def reference_main(args, rank, world):
 
 
 def workload_config(args, vocab=None):
-    return {"workload": "wdl_criteo embedding step: update(batch t) + lookup(batch t+1), "
-                        "%s cache ratio %.2f, bound %d" % (args.policy.upper(), args.ratio, args.bound),
+    return {"workload": "%s: embedding step = update(batch t)%s + lookup(batch t+1), "
+                        "%s cache ratio %.2f, bound %d" % (
+                            args.config, " with Herald plans (push_keys)" if args.plan else "",
+                            args.policy.upper(), args.ratio, args.bound),
+            "preset": CONFIGS[args.config]["note"],
             "batch_per_gpu": args.batch, "fields": FIELDS, "emb_dim": args.dim,
             "table_rows": vocab or args.vocab, "cache_limit": cache_limit(vocab or args.vocab, args.ratio),
             "ids": "Zipf(%.2f) unified, %s, float32-carried" % (ZIPF_A, "rank -> row by a fixed permutation" if _IDS_MODE == "permuted" else "rank == row"),
-            "l2": "inputs larger than L2: 3 rotating grads/dest buffer pairs of 2x%.0f MB, "
-                  "17 GB table" % (args.batch * FIELDS * args.dim * 4 / 1e6),
+            "l2": "inputs larger than L2: %d rotating grads/dest buffer pairs of 2x%.1f MB, "
+                  "%.0f GB table" % (rotating_buffers(args), args.batch * FIELDS * args.dim * 4 / 1e6,
+                                     (vocab or args.vocab) * args.dim * 4 / 1e9),
             "parallelism": "dp%d row-sharded" % args.gpus}
 
 
@@ -503,9 +573,14 @@ def herald_main(args, rank, world, local_rank):
     cpu_total = args.cpu_steps + 2
     P = min(P, cpu_total)
     total = P + K + W + 1
-    ids_np = [make_ids(s, B, V, rank) for s in range(max(total, cpu_total + 1))]
+    plans_np, planner_ms = None, None
+    if args.plan:
+        P = 0                                      # (parity of the plan path: tests/test_cache_gpu.py, test_scale_gpu.py)
+        ids_np, plans_np, planner_ms = laia_schedule(args, rank, world, total + 1)
+    else:
+        ids_np = [make_ids(s, B, V, rank) for s in range(max(total, cpu_total + 1))]
     ids_dev = [hb.array(a, dev) for a in ids_np[:total]]
-    R = 3
+    R = rotating_buffers(args)
     grads_np = make_grads(B, D, rank).reshape(B, FIELDS, D)                      # already x(-lr)
     grads_dev = [hb.array(grads_np, dev) for _ in range(R)]
     dest_dev = [hb.empty((B, FIELDS, D), dev) for _ in range(R)]
@@ -550,7 +625,10 @@ def herald_main(args, rank, world, local_rank):
         cst.embedding_lookup(ids_dev[0], dest_dev[0], sync=True)
 
     def step(s, keys, grads, dests, sync):
-        w1 = cst.embedding_update(keys[s], grads[s % len(grads)], sync=sync)
+        if plans_np is not None:
+            w1 = cst.embedding_update_with_push_keys(keys[s], plans_np[s + 1], grads[s % len(grads)], sync=sync)
+        else:
+            w1 = cst.embedding_update(keys[s], grads[s % len(grads)], sync=sync)
         w2 = cst.embedding_lookup(keys[s + 1], dests[s % len(dests)], sync=sync)
         return w1, w2
 
@@ -600,11 +678,12 @@ def herald_main(args, rank, world, local_rank):
         cst.perf_enabled(False)
         Ke = min(K, 20)
         host = hb.cpu(0)
-        ids_host = [hb.array(ids_np[P + W + s], host) for s in range(Ke + 1)]
+        g0 = P + W                                  # global index of the first e2e step (plans stay aligned)
+        ids_host = {g0 + s: hb.array(ids_np[g0 + s], host) for s in range(Ke + 1)}
         grads_host = [hb.array(grads_np, host) for _ in range(2)]
         dest_host = [hb.empty((B, FIELDS, D), host) for _ in range(2)]
-        cst.embedding_lookup(ids_host[0], dest_host[0], sync=True)
-        step(0, ids_host, grads_host, dest_host, True)          # warm the staging buffers
+        cst.embedding_lookup(ids_host[g0], dest_host[0], sync=True)
+        step(g0, ids_host, grads_host, dest_host, True)         # warm the staging buffers
         barrier()
         # Software-pipelined like the reference's prefetch loop (ParameterServerCommunicate.py:48-52:
         # the push is waited for, the pull is only waited for when its rows are consumed): the
@@ -614,7 +693,7 @@ def herald_main(args, rank, world, local_rank):
         prev = None
         t_host0 = time.perf_counter()
         ev[2].record(stream)
-        for s in range(1, Ke):
+        for s in range(g0 + 1, g0 + Ke):
             w1, w2 = step(s, ids_host, grads_host, dest_host, False)
             w1.wait()
             if prev is not None:
@@ -690,6 +769,10 @@ def herald_main(args, rank, world, local_rank):
                          "peak_source": peak_src, "kernels": kernels},
             "phases": phase,
         }
+        if planner_ms is not None:
+            line["planner"] = {"ms_per_global_batch": planner_ms, "threads": 16,
+                               "plan_keys_per_update": float(np.mean([len(p) for p in plans_np])),
+                               "note": "host planner (csrc/hb_laia.cu), run before the timed region"}
         if world > 1:
             # NVLink 5: 900 GB/s per direction per GPU (nominal).  Pull = rows this rank's sync kernel
             # reads out of peers' shards (inbound); push = lines its accumulate kernel deposits in

@@ -27,6 +27,11 @@
 #include <thread>
 #include <vector>
 
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
 #include "hb_common.cuh"
 
 namespace hb {
@@ -364,6 +369,12 @@ struct hb_laia {
     std::vector<u32> assigned;           // [batch] worker of each sample
     std::vector<u64> holders;            // [batch][T] bit z: the embedding is valid in worker z's snapshot
                                          // (W <= 64; the reference's sample_emb_dep_, as a bit set)
+    // TopkScheduler mode (laia/src/topk_scheduler.cc): scores count only the first `top_k` tables of a
+    // dataset-specific order; samples and worker slots are split over `parts` logical threads, each
+    // with its own workload counters (the reference's num_thread_: the result depends on it)
+    bool topk = false;
+    size_t top_k = 0, parts = 1;
+    std::vector<u32> table_order;
     u64 max_key = 0;                     // largest embedding id of the sample set
     std::vector<std::vector<u64>> seen;  // per worker: one bit per id (ids below kBitmapIds), all zero
                                          // between uses — ascending unique keys without a sort
@@ -551,9 +562,140 @@ void laia_plan_batch(hb_laia *s) {
     s->batch_id++;
 }
 
+// ---- TopkScheduler::get_dist + the snapshot update of TopkScheduler::launch ----------------------
+// laia/src/topk_scheduler.cc:362-502 and :291-318.  Restated, not translated:
+//  * scoring: a sample's score for worker z = how many of its first top_k tables (in the dataset's
+//    pre-profiled order) hold an id that is valid in z's snapshot; the candidate is the worker that
+//    FIRST reached the final maximum while the tables were walked in that order (:413-424);
+//  * assignment: logical thread t owns samples [lo, hi) and, of every worker's mini-batch, the slots
+//    [wstart, wend); it walks the workers from the candidate on and takes the best-scoring one that
+//    still has room in its slots, stopping at once if that is the candidate itself (:430-452);
+//  * plan of worker i: the sorted unique ids of its samples, walked cell by cell with an erase of
+//    every id that is not valid in i's snapshot — the reference erases from the flat_set INSIDE the
+//    range-for over it (:478-482), so with pointer iterators and a cached end the cell after an
+//    erased one is never examined and the stale copies at the tail are; that is part of the result
+//    (an empty snapshot keeps every other id) and is reproduced here cell by cell;
+//  * snapshots: the plan's ids are outdated, then every unique id of the worker's samples is
+//    touched in ascending order (:297-311).
+void topk_plan_batch(hb_laia *s) {
+    const size_t W = s->W, B = s->batch_size, T = s->num_table, S = s->num_sample, mini = s->mini;
+    const size_t P = s->parts;
+    const size_t start = (s->batch_id * B) % S;
+    auto pos_of = [&](size_t i) { return (start + i) % S; };
+    std::fill(s->dist.begin(), s->dist.end(), 0); // dist.reset(0)
+    parallel_for(P, s->threads, [&](size_t t) {
+        const size_t x = B / P, y = B % P;
+        const size_t lo = t == 0 ? 0 : y + t * x, hi = t == 0 ? x + y : lo + x;
+        const size_t wx = mini / P, wy = mini % P;
+        const size_t wstart = t == 0 ? 0 : wy + t * wx, wend = t == 0 ? wx + wy : wstart + wx;
+        const size_t room = wend - wstart;
+        std::vector<size_t> load(W, 0);
+        std::vector<u64> score(W);
+        for (size_t i = lo; i < hi; i++) {
+            const u64 *e = &s->embs[pos_of(i) * T];
+            std::fill(score.begin(), score.end(), 0);
+            u64 top = 0;
+            size_t candidate = 0;
+            for (size_t k = 0; k < s->top_k; k++) {
+                const u64 emb = e[s->table_order[k]];
+                const size_t hk = MiniLru::hash_of(emb);
+                for (size_t z = 0; z < W; z++)
+                    if (s->snaps[z].check(emb, hk) && ++score[z] > top) {
+                        top = score[z];
+                        candidate = z;
+                    }
+            }
+            long best = -1;
+            size_t best_w = W;
+            for (size_t j = 0; j < W; j++) {
+                const size_t w = (j + candidate) % W;
+                if (best < (long)score[w] && load[w] < room) {
+                    best = (long)score[w];
+                    best_w = w;
+                    if (w == candidate)
+                        break;
+                }
+            }
+            // (create() guarantees room for every sample: the reference indexes dist[-1] otherwise)
+            s->dist[best_w * mini + wstart + load[best_w]] = pos_of(i);
+            s->assigned[i] = (u32)best_w;
+            load[best_w]++;
+        }
+    });
+    parallel_for(W, s->threads, [&](size_t w) {
+        MiniLru &snap = s->snaps[w];
+        std::vector<u64> scratch, cells;
+        for (size_t i = 0; i < B; i++)
+            if (s->assigned[i] == w) {
+                const u64 *e = &s->embs[pos_of(i) * T];
+                cells.insert(cells.end(), e, e + T);
+            }
+        radix_sort_unique(cells, scratch);
+        std::vector<u64> uniq = cells; // the worker's unique ids, for the snapshot update below
+        // the erase-while-iterating walk over the ORIGINAL cells
+        size_t live = cells.size();
+        const size_t n0 = cells.size();
+        for (size_t p = 0; p < n0; p++) {
+            const u64 key = cells[p];
+            if (snap.check(key))
+                continue;
+            u64 *q = std::lower_bound(cells.data(), cells.data() + live, key);
+            if (q != cells.data() + live && *q == key) {
+                std::memmove(q, q + 1, (size_t)(cells.data() + live - (q + 1)) * sizeof(u64));
+                live--;
+            }
+        }
+        cells.resize(live);
+        s->plans[w].swap(cells);
+        for (u64 k : s->plans[w])
+            snap.outdate(k);
+        for_keys_prefetched(snap, uniq, [&](u64 k) { snap.get(k); });
+    });
+    s->batch_id++;
+}
+
+// pre-profiled table orders of the reference (topk_scheduler.cc:150-165)
+bool topk_table_order(const std::string &dataset, std::vector<u32> &order) {
+    if (dataset == "criteo")
+        order = {9, 13, 22, 20, 12, 21, 17, 14, 24, 3, 5, 10, 16, 15, 19, 2, 4, 11, 7, 25, 23, 18, 8, 1, 0, 6};
+    else if (dataset == "avazu")
+        order = {1, 2, 4, 5, 15, 7, 6, 16, 12, 0, 17, 8, 14, 10, 9, 11, 13, 3};
+    else if (dataset == "movie")
+        order = {0, 1};
+    else if (dataset == "criteosearch")
+        order = {0, 11, 3, 4, 5, 14, 1, 6, 2, 13, 16, 9, 8, 10, 12, 7, 15};
+    else
+        return false;
+    return true;
+}
+
 } // namespace
 
 extern "C" {
+
+int hb_laia_create_topk(hb_laia **out, const uint64_t *sample_embs, size_t num_sample, size_t num_table,
+                        size_t epoch_num, size_t mini_batch_size, size_t batch_num, size_t nrank, size_t rank,
+                        size_t cache_size, size_t num_threads, const char *dataset, size_t top_k_table) {
+    HB_API_BEGIN();
+    std::vector<u32> order;
+    HB_CHECK(dataset && topk_table_order(dataset, order), "dataset not supported"); // topk_scheduler.cc:162-165
+    for (u32 j : order)
+        HB_CHECK(j < num_table, "the dataset's table order names a table the samples do not have");
+    const size_t parts = std::max<size_t>(1, num_threads);
+    // the reference writes outside dist[] when a logical thread has more samples than slots
+    HB_CHECK(mini_batch_size % parts == 0,
+             "mini_batch_size must be a multiple of num_threads (the reference's per-thread slot split)");
+    HB_CHECK(hb_laia_create(out, sample_embs, num_sample, num_table, epoch_num, mini_batch_size, batch_num, nrank,
+                            rank, cache_size, num_threads) == 0, "create failed");
+    hb_laia *s = *out;
+    s->topk = true;
+    s->parts = parts;
+    s->table_order = order;
+    if (!top_k_table)
+        top_k_table = num_table; // topk_scheduler.cc:121-123
+    s->top_k = std::min(top_k_table, order.size());
+    HB_API_END();
+}
 
 int hb_laia_create(hb_laia **out, const uint64_t *sample_embs, size_t num_sample, size_t num_table,
                    size_t epoch_num, size_t mini_batch_size, size_t batch_num, size_t nrank, size_t rank,
@@ -606,7 +748,10 @@ int hb_laia_next(hb_laia *s, int *done) {
         s->finished = true;
         *done = 1;
     } else {
-        laia_plan_batch(s);
+        if (s->topk)
+            topk_plan_batch(s);
+        else
+            laia_plan_batch(s);
         *done = 0;
     }
     HB_API_END();
@@ -646,6 +791,121 @@ int hb_laia_snapshot_keys(hb_laia *s, size_t worker, uint64_t *keys, size_t cap,
         if (!k.empty())
             std::memcpy(keys, k.data(), k.size() * sizeof(u64));
     }
+    HB_API_END();
+}
+
+/* ---- shared-memory message ring between the planning process and a local worker -----------------
+ * laia/include/share_mem.h:39-160 + ring_buffer.h: one POSIX shared-memory object per local worker
+ * ("laia_cache_<local rank>"), a single-producer single-consumer ring of uint64 words; a message is
+ * its length followed by its words (share_mem.h:126-139).  Indices are monotone word counts. */
+struct hb_shmring {
+    std::string name;
+    bool creator = false;
+    size_t words = 0; // capacity of the data region, a power of two
+    u64 *base = nullptr;
+    size_t map_bytes = 0;
+    std::atomic<u64> *rd = nullptr, *wr = nullptr;
+};
+
+int hb_shmring_open(hb_shmring **out, const char *name, int create, size_t data_bytes) {
+    HB_API_BEGIN();
+    HB_CHECK(out && name, "null argument");
+    auto *r = new hb_shmring();
+    r->name = std::string("/") + name;
+    r->creator = create != 0;
+    if (create)
+        shm_unlink(r->name.c_str()); // a ring left behind by a crashed run must not be read as this one
+    int fd = shm_open(r->name.c_str(), create ? (O_RDWR | O_CREAT | O_EXCL) : O_RDWR, 0644);
+    if (fd < 0) {
+        delete r;
+        throw Error(std::string("shm_open ") + name + ": " + strerror(errno));
+    }
+    size_t words = 1024;
+    if (create) {
+        while (words * 8 < data_bytes)
+            words <<= 1; // share_mem.h:60-66: rounded up to a power of two
+        r->map_bytes = words * 8 + 64;
+        if (ftruncate(fd, (off_t)r->map_bytes) != 0) {
+            close(fd);
+            delete r;
+            throw Error(std::string("ftruncate: ") + strerror(errno));
+        }
+    } else {
+        struct stat st;
+        fstat(fd, &st);
+        r->map_bytes = (size_t)st.st_size;
+        HB_CHECK(r->map_bytes > 64, "shared ring not sized yet (the creating rank starts first)");
+        words = (r->map_bytes - 64) / 8;
+    }
+    void *p = mmap(nullptr, r->map_bytes, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+    close(fd);
+    if (p == MAP_FAILED) {
+        delete r;
+        throw Error(std::string("mmap: ") + strerror(errno));
+    }
+    r->words = words;
+    r->base = static_cast<u64 *>(p);
+    r->rd = reinterpret_cast<std::atomic<u64> *>(r->base + words);
+    r->wr = reinterpret_cast<std::atomic<u64> *>(r->base + words + 1);
+    if (create) {
+        r->rd->store(0);
+        r->wr->store(0);
+    }
+    *out = r;
+    HB_API_END();
+}
+
+int hb_shmring_close(hb_shmring *r) {
+    if (r) {
+        if (r->base)
+            munmap(r->base, r->map_bytes);
+        if (r->creator)
+            shm_unlink(r->name.c_str());
+        delete r;
+    }
+    return 0;
+}
+
+/* -> n on success, -1 when the ring has no room for the message (share_mem.h:126-139) */
+int hb_shmring_send(hb_shmring *r, const uint64_t *data, size_t n, long long *sent) {
+    HB_API_BEGIN();
+    const u64 wr = r->wr->load(std::memory_order_relaxed), rd = r->rd->load(std::memory_order_acquire);
+    if (r->words - (wr - rd) < n + 1) {
+        *sent = -1;
+    } else {
+        const size_t mask = r->words - 1;
+        r->base[wr & mask] = n;
+        for (size_t i = 0; i < n; i++)
+            r->base[(wr + 1 + i) & mask] = data[i];
+        r->wr->store(wr + 1 + n, std::memory_order_release);
+        *sent = (long long)n;
+    }
+    HB_API_END();
+}
+
+/* Length of the next message (-1: ring empty); with `data` non-null and cap >= length, also
+ * consumes it. */
+int hb_shmring_recv(hb_shmring *r, uint64_t *data, size_t cap, long long *n) {
+    HB_API_BEGIN();
+    const u64 rd = r->rd->load(std::memory_order_relaxed), wr = r->wr->load(std::memory_order_acquire);
+    if (wr == rd) {
+        *n = -1;
+    } else {
+        const size_t mask = r->words - 1;
+        const u64 len = r->base[rd & mask];
+        *n = (long long)len;
+        if (data && cap >= len) {
+            for (size_t i = 0; i < len; i++)
+                data[i] = r->base[(rd + 1 + i) & mask];
+            r->rd->store(rd + 1 + len, std::memory_order_release);
+        }
+    }
+    HB_API_END();
+}
+
+int hb_shmring_used(hb_shmring *r, size_t *words) {
+    HB_API_BEGIN();
+    *words = (size_t)(r->wr->load(std::memory_order_acquire) - r->rd->load(std::memory_order_acquire));
     HB_API_END();
 }
 

@@ -4,6 +4,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <set>
 
 #include <algorithm>
 
@@ -212,6 +213,21 @@ int DLEventElapsedTime(DLEventHandle start, DLEventHandle ending, float *duratio
     HB_API_END();
 }
 
+namespace {
+// host arrays allocated without CUDA (no device on the box): freed with free()
+std::mutex g_plain_host_mtx;
+std::set<void *> g_plain_host;
+bool free_plain_host(void *p) {
+    std::lock_guard<std::mutex> lock(g_plain_host_mtx);
+    auto it = g_plain_host.find(p);
+    if (it == g_plain_host.end())
+        return false;
+    g_plain_host.erase(it);
+    free(p);
+    return true;
+}
+} // namespace
+
 int DLArrayAlloc(const index_t *shape, const index_t *stride, index_t ndim, DLContext ctx,
                  DLArrayHandle *out) {
     HB_API_BEGIN();
@@ -242,6 +258,17 @@ int DLArrayAlloc(const index_t *shape, const index_t *stride, index_t ndim, DLCo
     } else {
         // pinned: async H2D/D2H for the cache's host-buffer entry points
         err = cudaHostAlloc(&arr->data, bytes, cudaHostAllocPortable);
+        if (err == cudaErrorNoDevice || err == cudaErrorInsufficientDriver) {
+            // a box without any CUDA device (host-side planning / data loading only): plain host
+            // memory; nothing in this process can launch a kernel or start a copy engine anyway
+            (void)cudaGetLastError();
+            arr->data = nullptr;
+            if (posix_memalign(&arr->data, 64, bytes) == 0) {
+                std::lock_guard<std::mutex> lock(g_plain_host_mtx);
+                g_plain_host.insert(arr->data);
+                err = cudaSuccess;
+            }
+        }
     }
     if (err != cudaSuccess) {
         delete[] arr->shape;
@@ -259,7 +286,7 @@ int DLArrayFree(DLArrayHandle handle) {
         if (handle->data) {
             if (handle->ctx.device_type == kGPU)
                 HB_CUDA(cudaFree(handle->data));
-            else
+            else if (!free_plain_host(handle->data))
                 HB_CUDA(cudaFreeHost(handle->data));
         }
         delete[] handle->shape;
@@ -274,7 +301,9 @@ int DLArrayCopyFromTo(DLArrayHandle from, DLArrayHandle to, DLStreamHandle strea
     size_t n = numel(from);
     HB_CHECK(n == numel(to), "DLArrayCopyFromTo: size mismatch");
     cudaMemcpyKind kind = cudaMemcpyDefault;
-    if (stream) {
+    if (from->ctx.device_type != kGPU && to->ctx.device_type != kGPU) {
+        std::memcpy(to->data, from->data, n * sizeof(float)); // host to host: no CUDA involved
+    } else if (stream) {
         HB_CUDA(cudaMemcpyAsync(to->data, from->data, n * sizeof(float), kind, stream_of(stream)));
     } else {
         HB_CUDA(cudaMemcpy(to->data, from->data, n * sizeof(float), kind));

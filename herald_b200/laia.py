@@ -106,6 +106,150 @@ class LaiaScheduler(object):
             pass
 
 
+class _ShmRing(object):
+    """One worker's message ring in POSIX shared memory (laia/include/share_mem.h:39-160)."""
+
+    def __init__(self, name, create, data_bytes=1 << 30, wait_s=120.0):
+        import time
+        self._h = ctypes.c_void_p()
+        deadline = time.time() + (0 if create else wait_s)
+        while True:
+            # a reader waits for the creating rank instead of betting on the reference's fixed
+            # 3 s head start (laia_dataloader.py:77-78)
+            if _LIB.hb_shmring_open(ctypes.byref(self._h), name.encode(), int(create), _sz(data_bytes)) == 0:
+                break
+            if time.time() >= deadline:
+                check_call(-1)
+            time.sleep(0.05)
+
+    def send(self, words):
+        """Blocks (polling, as the reference does: topk_scheduler.cc:229-242) until there is room."""
+        import time
+        arr = np.ascontiguousarray(words, dtype=np.uint64)
+        sent = ctypes.c_longlong()
+        while True:
+            check_call(_LIB.hb_shmring_send(self._h, arr.ctypes.data_as(ctypes.c_void_p), _sz(arr.size),
+                                            ctypes.byref(sent)))
+            if sent.value >= 0:
+                return
+            time.sleep(1e-5)
+
+    def recv(self):
+        """Blocks until a message is there (topk_scheduler.cc:254-278)."""
+        import time
+        n = ctypes.c_longlong()
+        while True:
+            check_call(_LIB.hb_shmring_recv(self._h, None, _sz(0), ctypes.byref(n)))
+            if n.value >= 0:
+                out = np.empty(max(n.value, 1), np.uint64)
+                check_call(_LIB.hb_shmring_recv(self._h, out.ctypes.data_as(ctypes.c_void_p), _sz(out.size),
+                                                ctypes.byref(n)))
+                return out[:n.value].tolist()
+            time.sleep(1e-5)
+
+    def used(self):
+        w = _sz(0)
+        check_call(_LIB.hb_shmring_used(self._h, ctypes.byref(w)))
+        return w.value
+
+    def close(self):
+        if self._h:
+            _LIB.hb_shmring_close(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class TopkScheduler(LaiaScheduler):
+    """The reference's production planner (laia/src/topk_scheduler.cc, bound at
+    laia/src/python_binding.cc:16-22): scores over the dataset's pre-profiled top-k tables, per-thread
+    slot split, and the `local_shared` mode in which local rank 0 of a node plans for all
+    `local_size` local workers and hands each its messages through a shared-memory ring
+    ("laia_cache_<local rank>"); the others only read theirs (`pop_from_local_worker`)."""
+
+    def __init__(self):
+        super().__init__()
+        self.local_shared = False
+        self._rings, self._my_ring, self._thread = [], None, None
+
+    def start(self, sample_embs, num_sample, num_table, epoch_num, mini_batch_size, batch_num, nrank, rank,
+              cache_size, num_threads, dataset, top_k_table, local_shared=False, local_rank=0, local_size=1,
+              ring_bytes=1 << 30):
+        self.local_shared, self.local_rank, self.local_size = bool(local_shared), int(local_rank), int(local_size)
+        self.rank, self.nrank, self.mini_batch_size = int(rank), int(nrank), int(mini_batch_size)
+        self._queue, self._done = [], False
+        if self.local_shared:
+            if self.local_rank == 0:        # topk_scheduler.cc:70-80: creates every local ring, then opens its own
+                self._rings = [_ShmRing("laia_cache_%d" % i, True, ring_bytes) for i in range(self.local_size)]
+            self._my_ring = _ShmRing("laia_cache_%d" % self.local_rank, False)
+            if self.local_rank != 0:
+                return                      # no planner in this process (:181-185)
+        embs = np.ascontiguousarray(sample_embs, dtype=np.uint64)
+        if embs.ndim != 2:
+            raise RuntimeError("Input should be 2D numpy array")
+        assert embs.shape == (num_sample, num_table)
+        self.close_planner()
+        h = ctypes.c_void_p()
+        check_call(_LIB.hb_laia_create_topk(ctypes.byref(h), embs.ctypes.data_as(ctypes.c_void_p),
+                                            _sz(num_sample), _sz(num_table), _sz(epoch_num),
+                                            _sz(mini_batch_size), _sz(batch_num), _sz(nrank), _sz(rank),
+                                            _sz(cache_size), _sz(num_threads), str(dataset).encode(),
+                                            _sz(top_k_table)))
+        self._h = h
+        if self.local_shared:
+            import threading
+            self._thread = threading.Thread(target=self._serve_local, daemon=True)
+            self._thread.start()
+
+    def _serve_local(self):
+        """Plan batch after batch and push every local worker its plan and its sample positions
+        (topk_scheduler.cc:291-296: worker id = this rank + local index), then the terminator."""
+        while self.step():
+            for i, ring in enumerate(self._rings):
+                ring.send(self.plan_of(self.rank + i))
+                ring.send(self.dist_of(self.rank + i))
+        for ring in self._rings:
+            ring.send([0])
+
+    def pop(self):
+        if self.local_shared:
+            raise RuntimeError("local_shared: read with pop_from_local_worker()")
+        return super().pop()
+
+    def pop_from_local_worker(self):
+        assert self.local_shared
+        return self._my_ring.recv()
+
+    def length(self):
+        if self.local_shared:
+            return self._my_ring.used()     # words waiting, as SharedMemBuf::queue_length (share_mem.h:163-165)
+        return super().length()
+
+    def close_planner(self):
+        LaiaScheduler.close(self)
+
+    def close(self):
+        if self._thread is not None:
+            self._thread.join(timeout=30)
+            self._thread = None
+        self.close_planner()
+        if self._my_ring is not None:
+            self._my_ring.close()
+            self._my_ring = None
+        for r in self._rings:
+            r.close()
+        self._rings = []
+
+
+# top-k table counts the reference passes per dataset (python/hetu/laia/laia_dataloader.py:19-24)
+top_k_table = {"criteo": 20, "avazu": 17, "movie": 2, "criteosearch": 16}
+local_worker_num = 8
+
+
 class MiniLRUCache(object):
     """laia/include/mini_lru_cache.h:14-137 (the planner's simulated worker cache)."""
 
@@ -149,18 +293,16 @@ class LAIAScheduler(object):
     (sample indices of b, communication plan computed for b + 1): the very first plan is dropped
     (:108-114), so the keys a worker pushes after training b are the ones its peers need in b + 1.
     A slot is refilled once every dataset (train / validate / ...) has stepped past it (:150-169).
-    `config` supplies `nrank`, `rank`, `local_rank`, `cache_limit` (HetuConfig).  The reference's
-    `local_shared` mode (TopkScheduler over shared memory) is not provided."""
+    `config` supplies `nrank`, `rank`, `local_rank`, `cache_limit` (HetuConfig).  `local_shared`
+    selects the TopkScheduler over shared-memory rings (run_laia.py --local-shared)."""
 
     queue_size = 5
 
     def __init__(self, sparse_data, batch_size, drop_last=True, dataset="criteo", local_shared=False):
-        if local_shared:
-            raise NotImplementedError("the TopkScheduler (local_shared) variant is not provided")
         # ids arrive float32-carried (python/hetu/dataloader.py:14); the planner wants integers
         self.sparse_data = np.asarray(sparse_data, np.float32).astype(np.intc)
         self.batch_size, self.drop_last, self.dataset = batch_size, drop_last, dataset
-        self.local_shared = False
+        self.local_shared = bool(local_shared)
         self.init = False
 
     def start(self, config, dataset_num=3, epoch_num=-1):
@@ -171,11 +313,21 @@ class LAIAScheduler(object):
         assert self.batch_size > 0, "Batch size %d invalid." % self.batch_size
         whole, rest = divmod(self.samples_num, self.batch_size)
         self.batch_num = whole if (self.drop_last or rest == 0) else whole + 1
-        self.sched = LaiaScheduler()
-        self.sched.start(self.sparse_data, self.sparse_data.shape[0], self.sparse_data.shape[1],
-                         epoch_num if epoch_num >= 0 else (1 << 62),       # -1: until closed
-                         self.batch_size, self.batch_num, int(config.nrank), int(config.rank),
-                         int(config.cache_limit), 16, 24)
+        epochs = epoch_num if epoch_num >= 0 else (1 << 62)               # -1: until closed
+        if not self.local_shared:
+            self.sched = LaiaScheduler()
+            self.sched.start(self.sparse_data, self.sparse_data.shape[0], self.sparse_data.shape[1],
+                             epochs, self.batch_size, self.batch_num, int(config.nrank), int(config.rank),
+                             int(config.cache_limit), 16, 24)
+        else:
+            # laia_dataloader.py:72-96: local rank 0 plans for the node's workers (TopkScheduler, 80
+            # threads, the dataset's pre-profiled top-k tables); the others wait for its rings
+            self.sched = TopkScheduler()     # (a reader waits for its ring to appear: _ShmRing)
+            self.sched.start(self.sparse_data, self.sparse_data.shape[0], self.sparse_data.shape[1],
+                             epochs, self.batch_size, self.batch_num, int(config.nrank), int(config.rank),
+                             int(config.cache_limit), int(getattr(config, "laia_threads", 80)), self.dataset,
+                             int(top_k_table[self.dataset]), True, int(config.local_rank),
+                             int(getattr(config, "local_size", local_worker_num)))
         self.channel_close = False
         self._receive()                                   # the plan of batch 0: nothing was cached yet
         self._slots = {b: self._receive_pair() for b in range(self.queue_size)}
@@ -188,7 +340,7 @@ class LAIAScheduler(object):
         As in the reference (:137-139) a message that is exactly [0] ends the channel."""
         if self.channel_close:
             raise RuntimeError("the scheduler channel is closed")
-        msg = self.sched.pop()
+        msg = self.sched.pop_from_local_worker() if self.local_shared else self.sched.pop()
         assert isinstance(msg, list)
         if msg == [0]:
             self.channel_close = True
@@ -216,3 +368,70 @@ class LAIAScheduler(object):
             del self._slots[done]
             self._slots[(done + self.queue_size) % self.batch_num] = self._receive_pair()
             self.cur_min_step += 1
+
+
+class LAIADataloader(object):
+    """The "train" loader of a Laia run (python/hetu/laia/laia_dataloader.py:172-231): WHICH samples
+    make up batch b is the planner's decision (`sched.get_input_index(b)`), and a sparse loader hands
+    out the communication plan next to the ids — `(ids, plan)`, which CacheSparseTable /
+    ParameterServerCommunicateOp route to `embedding_update_with_push_keys`.  Every loader of a
+    step (sparse ids, labels, dense features) shares one LAIAScheduler and reports its progress
+    with its `sched_id`."""
+
+    def __init__(self, sched, sched_id, is_sparse, raw_data, batch_size, name="default", func=None,
+                 drop_last=True):
+        from . import ndarray
+        self._nd = ndarray
+        self.func = func if func else (lambda x: x)
+        self.raw_data = np.array(self.func(raw_data), np.float32)
+        self.sched, self.sched_id, self.is_sparse = sched, sched_id, is_sparse
+        self.batch_size, self.name, self.drop_last = batch_size, str(name), drop_last
+
+    def init_states(self, rank=None, nrank=None):
+        self.samples_num, self.batch_num = self.sched.samples_num, self.sched.batch_num
+        self.batch_size = self.sched.batch_size
+        self.batch_index, self.rank = 0, rank
+
+    def _get_arr(self, batch):
+        idx = np.asarray(self.sched.get_input_index(batch), np.int64)
+        rows = self._nd.array(self.raw_data[idx], ctx=self._nd.cpu(0))
+        if not self.is_sparse:
+            return rows
+        # (the reference wraps the plan in a float32 NDArray, :198-203; it stays integer here: ids
+        # above 2^24 would not survive the cast, and the cache wants uint64 push keys anyway)
+        return rows, np.asarray(self.sched.get_comm_plan(batch), np.uint64)
+
+    def get_arr(self):
+        res = self._get_arr(self.batch_index)
+        self.batch_index = (self.batch_index + 1) % self.batch_num
+        self.sched.step_forward(self.sched_id)      # after the reads of this batch (:150)
+        return res
+
+    def get_next_arr(self):
+        return self._get_arr(self.batch_index)
+
+    def get_cur_shape(self):
+        return (len(self.sched.get_input_index(self.batch_index)),) + tuple(self.raw_data.shape[1:])
+
+
+def laia_dataloader_op(dataloaders, sched, sched_id, is_sparse=False):
+    """laia_dataloader.py:234-259: the loader named "train" follows the planner, the others are
+    plain Dataloaders."""
+    from .dataloader import Dataloader, DataloaderOp
+    built = []
+    for dl in dataloaders:
+        if isinstance(dl, (Dataloader, LAIADataloader)):
+            built.append(dl)
+        elif isinstance(dl, list):
+            if len(dl) >= 3 and dl[2] == "train":
+                built.append(LAIADataloader(sched, sched_id, is_sparse, *dl))
+            else:
+                built.append(Dataloader(*dl))
+        elif isinstance(dl, dict):
+            if dl.get("name") == "train":
+                built.append(LAIADataloader(sched=sched, sched_id=sched_id, is_sparse=is_sparse, **dl))
+            else:
+                built.append(Dataloader(**dl))
+        else:
+            raise AssertionError("Dataloader parameter invalid.")
+    return DataloaderOp(built)

@@ -331,6 +331,15 @@ typedef struct hb_laia hb_laia;
 int hb_laia_create(hb_laia **out, const uint64_t *sample_embs, size_t num_sample, size_t num_table,
                    size_t epoch_num, size_t mini_batch_size, size_t batch_num, size_t nrank, size_t rank,
                    size_t cache_size, size_t num_threads);
+/* TopkScheduler::start (laia/src/topk_scheduler.cc:47-187), the planner run_laia.py uses with
+ * --local-shared: scores over the first top_k_table tables of the dataset's pre-profiled order
+ * ("criteo" / "avazu" / "movie" / "criteosearch", :150-165), samples and slots split over
+ * num_threads logical threads (the plan depends on that number, as in the reference).  Same
+ * hb_laia_next / _plan / _dist surface afterwards. */
+int hb_laia_create_topk(hb_laia **out, const uint64_t *sample_embs, size_t num_sample, size_t num_table,
+                        size_t epoch_num, size_t mini_batch_size, size_t batch_num, size_t nrank,
+                        size_t rank, size_t cache_size, size_t num_threads, const char *dataset,
+                        size_t top_k_table);
 int hb_laia_destroy(hb_laia *s);
 /* Plan the next global batch (laia_scheduler.cc:115-169 one iteration: get_dist :171-271, then the
  * snapshot update :146-161).  *done = 1 when the sequence (epochs x batches, one more batch in the
@@ -343,6 +352,17 @@ int hb_laia_plan(hb_laia *s, size_t worker, uint64_t *keys, size_t cap);
 int hb_laia_dist(hb_laia *s, size_t worker, uint64_t *sample_idx);
 /* MiniLRUCache::get_keys of a worker's snapshot: valid keys, ascending (keys may be NULL: count) */
 int hb_laia_snapshot_keys(hb_laia *s, size_t worker, uint64_t *keys, size_t cap, size_t *n);
+/* Shared-memory message ring between the planning process of a node and its local workers — the
+ * reference's SharedMemBuf (laia/include/share_mem.h:39-160, ring_buffer.h): POSIX shared memory
+ * "laia_cache_<local rank>", single producer / single consumer, a message = length word + words.
+ * send: *sent = n, or -1 when there is no room; recv: *n = length of the next message or -1 when
+ * empty, consumed when data != NULL and cap >= length. */
+typedef struct hb_shmring hb_shmring;
+int hb_shmring_open(hb_shmring **out, const char *name, int create, size_t data_bytes);
+int hb_shmring_close(hb_shmring *r);
+int hb_shmring_send(hb_shmring *r, const uint64_t *data, size_t n, long long *sent);
+int hb_shmring_recv(hb_shmring *r, uint64_t *data, size_t cap, long long *n);
+int hb_shmring_used(hb_shmring *r, size_t *words);
 /* The snapshot cache alone (laia/include/mini_lru_cache.h:14-137).  get returns -1 hit, -2 stale
  * hit, 0 miss, 1 miss that evicted a valid line (:69-105). */
 typedef struct hb_minilru hb_minilru;
