@@ -1667,6 +1667,62 @@ __global__ void collect_keys_kernel(CacheView c, u64 *out, u32 *count) {
     }
 }
 
+// ---- Laia / Herald scoring against the REAL cache index ----------------------------
+// The reference scores a sample for a worker by counting its embedding ids in a host-side SIMULATION
+// of that worker's cache (MiniLRUCache snapshots: laia_scheduler.cc:171-210, topk_scheduler.cc:
+// 405-428).  With the cache in HBM the worker can answer from the index itself: one warp takes one
+// sample row, lane j probes table order[j] (the first `top_k` tables of the planner's order), a
+// ballot counts the resident ids.  `fresh` != 0 counts only lines a lookup would NOT have to
+// re-pull (version within pull_bound of the owner's: the snapshots' "valid" bit).  Read-only.
+template <int KIND>
+__global__ void __launch_bounds__(256)
+    score_samples_kernel(CacheView c, const void *__restrict__ ids, size_t num_samples, u32 num_tables,
+                         const u32 *__restrict__ order, u32 top_k, int fresh, i64 pull_bound,
+                         u32 *__restrict__ scores) {
+    pdl_enter();
+    const unsigned lane = lane_id();
+    const size_t warp_global = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const size_t nwarps = (size_t)gridDim.x * (blockDim.x >> 5);
+    for (size_t i = warp_global; i < num_samples; i += nwarps) {
+        u32 count = 0;
+        for (u32 j0 = 0; j0 < top_k; j0 += 32) {
+            const u32 j = j0 + lane;
+            bool hit = false;
+            if (j < top_k) {
+                const u32 t = order ? order[j] : j;
+                const size_t e = i * num_tables + t;
+                const u64 key = KIND == HB_KEYS_F32 ? key_from_f32(reinterpret_cast<const float *>(ids)[e])
+                                                    : reinterpret_cast<const u64 *>(ids)[e];
+                const i32 sl = ht_find(c.ht, c.ht_mask, key);
+                hit = sl >= 0;
+                if (hit && fresh) {
+                    const i64 v = c.slot_version[sl];
+                    u64 trow = key - c.row_begin;
+                    int owner = 0;
+                    if (c.pv.world > 1)
+                        owner = owner_of(c.pv, key, trow);
+                    hit = v != -1 && key < c.table_len && __ldg(&c.pv.ver[owner][trow]) - v <= pull_bound;
+                }
+            }
+            count += __popc(__ballot_sync(FULL, hit));
+        }
+        if (lane == 0)
+            scores[i] = count;
+    }
+}
+
+// resident[i] = 1 if keys[i] has a line in the index (CacheBase::count, python_api.cc:56), else 0
+template <int KIND>
+__global__ void __launch_bounds__(256)
+    probe_keys_kernel(CacheView c, const void *__restrict__ keys, size_t n, u8 *__restrict__ resident) {
+    pdl_enter();
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const u64 key = KIND == HB_KEYS_F32 ? key_from_f32(reinterpret_cast<const float *>(keys)[i])
+                                            : reinterpret_cast<const u64 *>(keys)[i];
+        resident[i] = ht_find(c.ht, c.ht_mask, key) >= 0 ? 1 : 0;
+    }
+}
+
 struct PeekResult {
     i32 slot;
     i32 updates;
@@ -2733,6 +2789,8 @@ int hb_cache_destroy(hb_cache *c) {
             dfree(c->rows_stage[b]);
         if (c->push_keys_stage)
             cudaFree(c->push_keys_stage);
+        if (c->score_scratch)
+            cudaFree(c->score_scratch);
         cudaFree(c->dev_record);
         cudaFreeHost(c->ring);
         for (auto &e : c->ev_begin)
@@ -3270,6 +3328,87 @@ int hb_cache_peek(hb_cache *c, uint64_t key, int *found, int64_t *version, int64
                                    c->width * sizeof(float), cudaMemcpyDeviceToHost));
             else
                 std::memset(grad, 0, c->width * sizeof(float)); // logically zero after a push
+        }
+    }
+    HB_API_END();
+}
+
+// scratch device buffer of the scoring calls (grown on demand)
+static void *score_scratch(hb_cache *c, size_t bytes) {
+    if (bytes > c->score_scratch_cap) {
+        sync_all(c);
+        if (c->score_scratch)
+            cudaFree(c->score_scratch);
+        c->score_scratch = nullptr;
+        HB_CUDA(cudaMalloc(&c->score_scratch, bytes));
+        c->score_scratch_cap = bytes;
+    }
+    return c->score_scratch;
+}
+
+int hb_cache_score(hb_cache *c, const void *sample_ids, int key_kind, size_t num_samples, size_t num_tables,
+                   const uint32_t *table_order, size_t top_k, int fresh, uint32_t *scores) {
+    HB_API_BEGIN();
+    Guard g(c->device);
+    HB_CHECK(num_tables > 0 && top_k <= num_tables, "top_k must not exceed the number of tables");
+    if (num_samples) {
+        const size_t n = num_samples * num_tables, kb = key_kind == HB_KEYS_F32 ? 4 : 8;
+        const bool ids_host = !is_device_ptr(sample_ids), out_host = !is_device_ptr(scores);
+        // scratch layout: [order u32 x T][scores u32 x S (host callers)][ids (host callers)]
+        const size_t off_scores = (num_tables * 4 + 15) & ~(size_t)15;
+        const size_t off_ids = off_scores + ((num_samples * 4 + 15) & ~(size_t)15);
+        char *scr = static_cast<char *>(score_scratch(c, off_ids + (ids_host ? n * kb : 0)));
+        cudaStream_t st = c->stream;
+        u32 *dorder = nullptr;
+        if (table_order) {
+            dorder = reinterpret_cast<u32 *>(scr);
+            HB_CUDA(cudaMemcpyAsync(dorder, table_order, top_k * 4, cudaMemcpyHostToDevice, st));
+        }
+        const void *dids = sample_ids;
+        if (ids_host) {
+            HB_CUDA(cudaMemcpyAsync(scr + off_ids, sample_ids, n * kb, cudaMemcpyHostToDevice, st));
+            dids = scr + off_ids;
+        }
+        u32 *dscores = out_host ? reinterpret_cast<u32 *>(scr + off_scores) : scores;
+        const int grid = (int)std::max<size_t>(1, std::min<size_t>((num_samples + 7) / 8, (size_t)sm_count() * 8));
+        if (key_kind == HB_KEYS_F32)
+            HB_LAUNCH(score_samples_kernel<HB_KEYS_F32>, grid, 256, 0, st, c->view, dids, num_samples,
+                      (u32)num_tables, dorder, (u32)top_k, fresh, c->pull_bound, dscores);
+        else
+            HB_LAUNCH(score_samples_kernel<HB_KEYS_U64>, grid, 256, 0, st, c->view, dids, num_samples,
+                      (u32)num_tables, dorder, (u32)top_k, fresh, c->pull_bound, dscores);
+        HB_LAUNCHED();
+        if (out_host) {
+            HB_CUDA(cudaMemcpyAsync(scores, dscores, num_samples * 4, cudaMemcpyDeviceToHost, st));
+            HB_CUDA(cudaStreamSynchronize(st));
+        }
+    }
+    HB_API_END();
+}
+
+int hb_cache_probe(hb_cache *c, const void *keys, int key_kind, size_t n, uint8_t *resident) {
+    HB_API_BEGIN();
+    Guard g(c->device);
+    if (n) {
+        const size_t kb = key_kind == HB_KEYS_F32 ? 4 : 8;
+        const bool keys_host = !is_device_ptr(keys), out_host = !is_device_ptr(resident);
+        const size_t off_keys = (n + 15) & ~(size_t)15;
+        char *scr = static_cast<char *>(score_scratch(c, off_keys + (keys_host ? n * kb : 0)));
+        cudaStream_t st = c->stream;
+        const void *dkeys = keys;
+        if (keys_host) {
+            HB_CUDA(cudaMemcpyAsync(scr + off_keys, keys, n * kb, cudaMemcpyHostToDevice, st));
+            dkeys = scr + off_keys;
+        }
+        u8 *dres = out_host ? reinterpret_cast<u8 *>(scr) : resident;
+        if (key_kind == HB_KEYS_F32)
+            HB_LAUNCH(probe_keys_kernel<HB_KEYS_F32>, lin_grid(n), 256, 0, st, c->view, dkeys, n, dres);
+        else
+            HB_LAUNCH(probe_keys_kernel<HB_KEYS_U64>, lin_grid(n), 256, 0, st, c->view, dkeys, n, dres);
+        HB_LAUNCHED();
+        if (out_host) {
+            HB_CUDA(cudaMemcpyAsync(resident, dres, n, cudaMemcpyDeviceToHost, st));
+            HB_CUDA(cudaStreamSynchronize(st));
         }
     }
     HB_API_END();

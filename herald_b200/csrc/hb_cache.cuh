@@ -285,6 +285,8 @@ struct hb_cache {
     size_t rows_stage_cap[3] = {0, 0, 0};
     void *push_keys_stage = nullptr;
     size_t push_keys_stage_cap = 0;
+    void *score_scratch = nullptr; // hb_cache_score / hb_cache_probe staging
+    size_t score_scratch_cap = 0;
     // perf ring (pinned host) + events
     hb::PerfRecord *ring = nullptr;
     hb::PerfRecord *dev_record = nullptr;

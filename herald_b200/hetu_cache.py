@@ -59,6 +59,8 @@ def _proto():
                                       ctypes.POINTER(ctypes.c_int)]
     L.hb_cache_perf_history.argtypes = [_vp, ctypes.POINTER(hb_perf), ctypes.POINTER(ctypes.c_int),
                                         ctypes.c_int, ctypes.POINTER(ctypes.c_int)]
+    L.hb_cache_score.argtypes = [_vp, _vp, ctypes.c_int, _sz, _sz, _vp, _sz, ctypes.c_int, _vp]
+    L.hb_cache_probe.argtypes = [_vp, _vp, ctypes.c_int, _sz, _vp]
     L.hb_cache_size.argtypes = [_vp, ctypes.POINTER(_sz)]
     L.hb_cache_count.argtypes = [_vp, ctypes.c_uint64, ctypes.POINTER(ctypes.c_int)]
     L.hb_cache_keys.argtypes = [_vp, _vp, _sz, ctypes.POINTER(_sz)]
@@ -343,6 +345,32 @@ class CacheBase(object):
             self._h, keys_ptr, KEYS_F32, int(num_keys), push_keys_ptr, KEYS_F32,
             int(num_push_keys), grads_ptr))
         return self._issue()
+
+    # ---- Laia / Herald scoring against the real index (herald_b200 extension) --
+    def score_samples(self, sample_ids, table_order=None, top_k=None, fresh=False):
+        """uint32[num_samples]: per sample row of `sample_ids` ([S, T], uint64 or float32-carried),
+        how many of its first `top_k` tables (in `table_order`) hold an id resident in this cache."""
+        ids = np.ascontiguousarray(sample_ids)
+        assert ids.ndim == 2 and ids.dtype in (np.uint64, np.float32)
+        S, T = ids.shape
+        order = None if table_order is None else np.ascontiguousarray(table_order, np.uint32)
+        k = T if top_k is None else int(top_k)
+        if order is not None:
+            k = min(k, order.size)
+        out = np.zeros(S, np.uint32)
+        check_call(_LIB.hb_cache_score(self._h, ids.ctypes.data, KEYS_U64 if ids.dtype == np.uint64 else KEYS_F32,
+                                       S, T, None if order is None else order.ctypes.data, k, int(fresh),
+                                       out.ctypes.data))
+        return out
+
+    def resident(self, keys):
+        """bool[n]: which of `keys` have a line in this cache (no policy touch)."""
+        keys = np.ascontiguousarray(keys)
+        assert keys.dtype in (np.uint64, np.float32)
+        out = np.zeros(keys.size, np.uint8)
+        check_call(_LIB.hb_cache_probe(self._h, keys.ctypes.data, KEYS_U64 if keys.dtype == np.uint64 else KEYS_F32,
+                                       keys.size, out.ctypes.data))
+        return out.astype(bool).reshape(keys.shape)
 
     # ---- debug surface (python_api.cc:56-60) -----------------------------------------------
     def size(self):

@@ -435,3 +435,76 @@ def laia_dataloader_op(dataloaders, sched, sched_id, is_sparse=False):
         else:
             raise AssertionError("Dataloader parameter invalid.")
     return DataloaderOp(built)
+
+
+# top-k table orders the reference pre-profiled per dataset (laia/src/topk_scheduler.cc:150-165)
+TOPK_TABLE_ORDER = {
+    "criteo": [9, 13, 22, 20, 12, 21, 17, 14, 24, 3, 5, 10, 16, 15, 19, 2, 4, 11, 7, 25, 23, 18, 8, 1, 0, 6],
+    "avazu": [1, 2, 4, 5, 15, 7, 6, 16, 12, 0, 17, 8, 14, 10, 9, 11, 13, 3],
+    "movie": [0, 1],
+    "criteosearch": [0, 11, 3, 4, 5, 14, 1, 6, 2, 13, 16, 9, 8, 10, 12, 7, 15],
+}
+
+
+def assign_by_scores(scores, mini_batch_size, parts=1):
+    """The TopkScheduler assignment (laia/src/topk_scheduler.cc:430-452) on a finished score matrix
+    `scores[W, S]` (S = W * mini_batch_size samples of one global batch): logical thread t owns a
+    contiguous run of samples and, of every worker's mini-batch, a contiguous run of slots; a sample
+    goes to the best-scoring worker that still has room in the thread's slots, scanning from the
+    candidate (here: the lowest-ranked worker holding the maximum) and stopping at it if it has room.
+    -> int64[W, mini_batch_size] sample positions inside the batch.  Deterministic: every rank that
+    holds the same matrix computes the same assignment."""
+    scores = np.asarray(scores)
+    W, S = scores.shape
+    mini = int(mini_batch_size)
+    assert S == W * mini and mini % parts == 0
+    dist = np.zeros((W, mini), np.int64)
+    per, room = S // parts, mini // parts
+    for t in range(parts):
+        load = [0] * W
+        for i in range(t * per, (t + 1) * per):
+            col = scores[:, i]
+            cand = int(np.argmax(col))
+            best, best_w = -1, -1
+            for j in range(W):
+                w = (j + cand) % W
+                if best < int(col[w]) and load[w] < room:
+                    best, best_w = int(col[w]), w
+                    if w == cand:
+                        break
+            dist[best_w, t * room + load[best_w]] = i
+            load[best_w] += 1
+    return dist
+
+
+class GpuScoredPlanner(object):
+    """Herald planning against the REAL caches instead of simulated snapshots: every
+    rank scores the whole global batch against its own cache index on the GPU
+    (`hb_cache_score`), the W score columns are all-gathered, every rank runs the same assignment,
+    and a rank's communication plan is the set of ids of ITS samples that it already holds
+    (`hb_cache_probe`) — the TopkScheduler's rule (topk_scheduler.cc:476-483) without its
+    erase-while-iterating artefact.  `allgather(column) -> [W, S]` is supplied by the launcher
+    (torch.distributed / NCCL); None for a single worker."""
+
+    def __init__(self, cache, sample_embs, mini_batch_size, nrank, rank, dataset="criteo", top_k=None,
+                 parts=1, allgather=None, fresh=True):
+        self.cache = cache
+        self.embs = np.ascontiguousarray(sample_embs, dtype=np.uint64)
+        self.mini, self.W, self.rank, self.parts = int(mini_batch_size), int(nrank), int(rank), int(parts)
+        order = [t for t in TOPK_TABLE_ORDER[dataset] if t < self.embs.shape[1]]
+        k = len(order) if top_k is None else min(int(top_k), len(order))
+        self.order = np.asarray(order[:k], np.uint32)
+        self.allgather, self.fresh = allgather, fresh
+
+    def plan_batch(self, b):
+        """-> (sample positions of this rank in the sample matrix, ascending plan keys)."""
+        B, S = self.mini * self.W, self.embs.shape[0]
+        pos = (b * B + np.arange(B)) % S
+        ids = self.embs[pos]
+        mine = self.cache.score_samples(ids, self.order, len(self.order), fresh=self.fresh)
+        cols = mine[None, :] if self.allgather is None else np.asarray(self.allgather(mine))
+        assert cols.shape == (self.W, B)
+        dist = assign_by_scores(cols, self.mini, self.parts)
+        my_pos = pos[dist[self.rank]]
+        keys = np.unique(self.embs[my_pos].reshape(-1))
+        return my_pos, keys[self.cache.resident(keys)]

@@ -294,6 +294,22 @@ int hb_cache_flush(hb_cache *c);
 /* Counters of the last `max` completed calls, oldest first; returns how many were written. */
 int hb_cache_perf_history(hb_cache *c, hb_perf *out, int *kinds, int max, int *written);
 
+/* Laia / Herald scoring against the REAL cache.  The reference's planners score a
+ * sample for a worker by counting its embedding ids in a host-side simulation of that worker's cache
+ * (MiniLRUCache snapshots: laia/src/laia_scheduler.cc:171-210, topk_scheduler.cc:405-428); here the
+ * worker answers from its index in HBM.  sample_ids: [num_samples, num_tables] ids (host or device,
+ * encoding key_kind); scores[i] = how many of sample i's tables table_order[0..top_k) (NULL = tables
+ * 0..top_k-1) hold an id that has a line in this cache — with fresh != 0 only lines a lookup would
+ * not re-pull (owner version - line version <= pull_bound), the snapshots' "valid" bit.  Read-only;
+ * ordered on the cache's stream; with a host `scores` pointer the call completes before returning.
+ * Workers exchange their score columns (an all-gather of num_samples words) and run the greedy
+ * assignment on identical inputs. */
+int hb_cache_score(hb_cache *c, const void *sample_ids, int key_kind, size_t num_samples, size_t num_tables,
+                   const uint32_t *table_order, size_t top_k, int fresh, uint32_t *scores);
+/* resident[i] = 1 when keys[i] has a line in the cache (CacheBase::count for a batch of keys): the
+ * plan rule "ids of my samples that I hold" (topk_scheduler.cc:476-483) against the real index. */
+int hb_cache_probe(hb_cache *c, const void *keys, int key_kind, size_t n, uint8_t *resident);
+
 /* debug surface: python_api.cc:56-60 */
 int hb_cache_size(hb_cache *c, size_t *size);
 int hb_cache_count(hb_cache *c, uint64_t key, int *count);

@@ -198,3 +198,19 @@ def test_local_shared_front_end_two_processes():
             idx, plan = results[rank][b]
             assert idx == seq[b][1], (rank, b)
             assert plan == seq[b + 1][0], (rank, b)
+
+
+def test_assign_by_scores_respects_slots_and_prefers_the_best_worker():
+    from herald_b200.laia import assign_by_scores
+    rng = np.random.default_rng(9)
+    W, mini, parts = 4, 8, 2
+    scores = rng.integers(0, 6, (W, W * mini))
+    dist = assign_by_scores(scores, mini, parts)
+    assert sorted(dist.reshape(-1).tolist()) == list(range(W * mini))       # every sample exactly once
+    per, room = W * mini // parts, mini // parts
+    for t in range(parts):                                                   # slot runs hold the thread's samples
+        got = dist[:, t * room:(t + 1) * room].reshape(-1)
+        assert set(got.tolist()) == set(range(t * per, (t + 1) * per))
+    first = int(dist[int(np.argmax(scores[:, 0])), 0])
+    assert first == 0                                                        # sample 0: best worker, first slot
+    assert np.array_equal(dist, assign_by_scores(scores, mini, parts))
