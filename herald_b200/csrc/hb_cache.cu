@@ -391,6 +391,8 @@ __global__ void __launch_bounds__(kRowBlock)
         unsigned m = __ballot_sync(FULL, need);
         pulled += __popc(m);
         pulled_remote += __popc(__ballot_sync(FULL, need && owner != c.pv.rank));
+        if (VEC == 4 && need && (c.pv.world == 1 || owner == c.pv.rank)) // local rows: towards L2 now
+            prefetch_l2(c.pv.rows[owner] + trow * D, (unsigned)(D * sizeof(float)));
         while (m) {
             int src[ROWS];
             i32 rs[ROWS];
@@ -1206,6 +1208,18 @@ struct AccumulatePush {
         const typename V::T gs = V::mul(g, scale);
         r.g = V::add(a.g, gs);
         r.d = V::add(a.d, gs);
+        r.t = a.t;
+        return r;
+    }
+    // two-level reduction of the very hot rows (hb_rows.cuh, opt-in by hb_cache_set_reduce_mode)
+    static constexpr bool kSplit = true;
+    __device__ float pre(float g) const { // one occurrence's contribution
+        return __fmul_rn(g, scale);
+    }
+    __device__ Acc step_pre(const Acc &a, const typename V::T &p) const { // a run sum, already scaled
+        Acc r;
+        r.g = V::add(a.g, p);
+        r.d = V::add(a.d, p);
         r.t = a.t;
         return r;
     }
@@ -2335,7 +2349,7 @@ void run_accumulate(hb_cache *c, size_t n, int batch, int wsi, const float *dev_
                            f1, f4, [&] {
                                if (batch == 0)
                                    mark(c, 3);
-                           });
+                           }, c->reduce_split);
     }
     if (batch == 0)
         mark(c, 2);
@@ -2626,6 +2640,8 @@ int hb_cache_create(int policy, size_t limit, size_t length, size_t width, int n
     c->table = t;
     c->key_bits = bits_for(std::max<size_t>(length, t->length));
     c->hot_threshold = default_hot_threshold();
+    if (const char *e = getenv("HERALD_REDUCE")) // process-wide default of hb_cache_set_reduce_mode
+        c->reduce_split = std::string(e) == "split" || std::string(e) == "1";
     HB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     HB_CUDA(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
     HB_CUDA(cudaStreamCreateWithFlags(&c->side2, cudaStreamNonBlocking));
@@ -2830,6 +2846,19 @@ int hb_cache_get_bounds(hb_cache *c, int64_t *pull_bound, int64_t *push_bound) {
 int hb_cache_set_grad_scale(hb_cache *c, float scale) {
     HB_API_BEGIN();
     c->grad_scale = scale;
+    HB_API_END();
+}
+
+int hb_cache_set_reduce_mode(hb_cache *c, int mode) {
+    HB_API_BEGIN();
+    HB_CHECK(mode == 0 || mode == 1, "reduce mode: 0 = occurrence order, 1 = two-level for very hot rows");
+    c->reduce_split = mode == 1;
+    HB_API_END();
+}
+
+int hb_cache_get_reduce_mode(hb_cache *c, int *mode) {
+    HB_API_BEGIN();
+    *mode = c->reduce_split ? 1 : 0;
     HB_API_END();
 }
 

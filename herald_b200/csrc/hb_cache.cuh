@@ -264,6 +264,7 @@ struct hb_cache {
     cudaEvent_t ev_gathered[2] = {nullptr, nullptr}; // main: dest staging buffer k is complete
     cudaEvent_t ev_dl[2] = {nullptr, nullptr};       // d2h: download out of staging buffer k is done
     cudaEvent_t ev_producer = nullptr;          // a caller's stream: its device buffers are ready
+    bool reduce_split = false;                  // two-level reduction of rows with > 1024 occurrences
     float grad_scale = 1.0f;                    // gradients are multiplied by this (the -lr fold)
     int dl_next = 0;                            // dest staging buffer of the next host-dest lookup
     int dl_of_call[1024] = {};                  // [kRing] 1 + staging buffer a call downloads from, 0 = none

@@ -146,6 +146,23 @@ __device__ __forceinline__ float4 ld_row(const float4 *p) {
 __device__ __forceinline__ void st_row(float4 *p, const float4 &v) {
     *p = v;
 }
+// Ask the memory system to bring a row (`bytes` at `p`) into L2: one prefetch.global.L2 per 128-byte
+// line, no register or shared-memory destination.  The row movers know their next rows a few hundred
+// nanoseconds before they read them (the next ticket's work items, the 32 source rows of a gather
+// group), one row per LANE: prefetched, the demand loads pay L2 latency instead of HBM latency, so
+// the same loads in flight per warp sustain more bandwidth.  (cp.async.bulk.prefetch.L2 would take
+// the whole row in one instruction but issues from the uniform datapath — one address per WARP: the
+// compiler serialises 32 different lane addresses, measured slower here.)
+__device__ __forceinline__ void prefetch_l2(const void *p, unsigned bytes) {
+    const char *q = static_cast<const char *>(p);
+    for (unsigned o = 0; o < bytes; o += 128)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(q + o) : "memory");
+}
+// one whole row with a single instruction, for a WARP-UNIFORM address (sm_90+ bulk prefetch)
+__device__ __forceinline__ void prefetch_l2_bulk(const void *p, unsigned bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
 // exact (never contracted) fp32 add: keeps ((a+g1)+g2)... bit-identical to the CPU path
 __device__ __forceinline__ float4 add4(const float4 &a, const float4 &b) {
     return make_float4(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y), __fadd_rn(a.z, b.z),

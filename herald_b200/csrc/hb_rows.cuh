@@ -4,6 +4,7 @@
 #pragma once
 
 #include <algorithm>
+#include <type_traits>
 
 #include "hb_common.cuh"
 
@@ -104,6 +105,8 @@ __global__ void __launch_bounds__(kRowBlock)
     for (size_t base = warp_global * 32; base < n; base += nwarps * 32) {
         const long long mine = base + lane < n ? index(base + lane) : -1;
         const int rows_here = (int)min((size_t)32, n - base);
+        if (VEC == 4 && mine >= 0) // all 32 source rows of the group start moving towards L2 now
+            prefetch_l2(src + (size_t)mine * D, (unsigned)(D * sizeof(float)));
 #pragma unroll 1
         for (int r0 = 0; r0 < rows_here; r0 += ROWS) {
             long long srow[ROWS];
@@ -173,6 +176,20 @@ constexpr size_t hot_smem_bytes(int stages) {
     return (size_t)stages * kHotStageBytes + (size_t)2 * stages * 8 + 16;
 }
 constexpr u32 kVeryHot = 1024; // rows above this go first (longest-processing-time-first)
+// Two-level reduction of the very hot rows (opt-in, HotLists::split).  The add ORDER of a row is
+// part of the bit-parity contract, so a row with 11 000 occurrences is one 11 000-long dependent
+// FADD chain — at C2 that single chain, not HBM, bounds the whole kernel (70 of 78 us).  With the
+// split on, a row with more than kVeryHot occurrences is cut into kSplitTiles runs of
+// L = round_up(ceil(cnt / kSplitTiles), 128) consecutive occurrences; every run is summed in
+// occurrence order from 0 (independent chains, any CTA), then the run sums are added to the row in
+// run order.  The result depends on cnt only — deterministic, identical on every machine — but it is
+// not the serial order: updated rows then agree with the reference within fp32 re-association
+// (1e-5 relative, the north star's tolerance) instead of bit for bit.  Every other row keeps the
+// exact order.
+constexpr u32 kSplitTiles = 8;
+__host__ __device__ inline u32 split_run_length(u32 cnt) {
+    return (((cnt + kSplitTiles - 1) / kSplitTiles) + 127u) & ~127u;
+}
 constexpr u32 kMediumDefault = 4;
 
 // ring depth of the hot phase ($HERALD_HOT_STAGES, 2 .. 12): the bytes the producers keep in
@@ -242,6 +259,34 @@ struct HotLists {
     u32 ticket_rows; // uniques per cold ticket (<= 32)
     u32 med_threshold;
     u32 mode;        // diagnostics ($HERALD_SEG_MODE): bit 0 = cold work waits for every hot group
+    u32 split;       // two-level reduction of the very hot rows (functors that opt in)
+    float *partials; // [very hot row][kSplitTiles][D] run sums
+    u32 *split_done; // [very hot row] runs x column chunks finished (zero on entry)
+};
+
+// A functor opts in to the split with `static constexpr bool kSplit = true` and two members:
+// pre(g) = what one gradient value contributes (its scaled value), step_pre(acc, p) = step() for an
+// already-scaled contribution.
+template <class F, class = void>
+struct can_split : std::false_type {};
+template <class F>
+struct can_split<F, std::enable_if_t<F::kSplit>> : std::true_type {};
+
+// run sum of one tile: ((0 + pre(g0)) + pre(g1)) + ... into partials
+template <class F1>
+struct RunSum {
+    const F1 &f;
+    float *dst; // the run's row of partials
+    struct Ctx {};
+    __device__ float load(const Ctx &, size_t) const {
+        return 0.f;
+    }
+    __device__ float step(float acc, float g) const {
+        return __fadd_rn(acc, f.pre(g));
+    }
+    __device__ void store(const Ctx &, size_t col, float acc) const {
+        dst[col] = acc;
+    }
 };
 
 __device__ __forceinline__ u32 rows_warp_append(u32 *counter, bool pred) {
@@ -553,8 +598,14 @@ __global__ void __launch_bounds__(kRowBlock, 2)
         const u32 QB = (u32)((D + 31) / 32);
         const u32 QA = WIDE ? (u32)((D + 15) / 16) : QB;
         const u32 nA = hl.ctrl[0], nB = hl.ctrl[1];
-        const u32 itemsA = nA * QA;
-        const u32 total = itemsA + nB * QB;
+        constexpr bool kCanSplit = can_split<F1>::value;
+        const bool split = kCanSplit && hl.split != 0;
+        // item space.  exact: [very hot rows x QA chunks][hot rows x QB chunks]
+        //              split: [very hot rows x kSplitTiles runs x QA chunks][hot rows x QB][very hot rows x QB combines]
+        const u32 itemsA = split ? nA * kSplitTiles * QA : nA * QA;
+        const u32 itemsB = nB * QB;
+        const u32 itemsC = split ? nA * QB : 0u;
+        const u32 total = itemsA + itemsB + itemsC;
         HotRing hr{s_ring, s_full, s_empty, S, 0u, 0u};
         while (true) {
             hot_group_sync(); // s_item of the previous item has been read by everyone
@@ -568,14 +619,78 @@ __global__ void __launch_bounds__(kRowBlock, 2)
             if (trace && threadIdx.x == 0 && t < kTraceItems)
                 trace[2 + 4 * (size_t)kTraceCtas + 3 * t] = global_timer_ns();
             const bool very = t < itemsA;
-            const u32 h = very ? t / QA : (t - itemsA) / QB;
-            const u32 q = very ? t % QA : (t - itemsA) % QB;
-            const Item it = items[very ? hl.very_hot[h] : hl.hot[h]];
-            const u32 cnt = it.h.cnt;
+            const bool combine = t >= itemsA + itemsB;
+            u32 h, q, run = 0;
+            if (very && split) { // runs outer, chunks inner: neighbouring tickets share gradient rows
+                h = t / (kSplitTiles * QA);
+                const u32 r = t - h * (kSplitTiles * QA);
+                run = r / QA;
+                q = r - run * QA;
+            } else if (very) {
+                h = t / QA;
+                q = t % QA;
+            } else if (combine) {
+                h = (t - itemsA - itemsB) / QB;
+                q = (t - itemsA - itemsB) % QB;
+            } else {
+                h = (t - itemsA) / QB;
+                q = (t - itemsA) % QB;
+            }
+            const Item it = items[(very || combine) ? hl.very_hot[h] : hl.hot[h]];
+            u32 cnt = it.h.cnt;
+            u32 first = 0; // first occurrence of the chain this item runs
+            if (very && split) {
+                const u32 L = split_run_length(cnt);
+                first = min(run * L, cnt);
+                cnt = min(L, cnt - first);
+            }
             const u32 W = (very && WIDE) ? 16u : 32u;
-            const u32 ntiles = (cnt + kHotStageFloats / W - 1) / (kHotStageFloats / W);
+            u32 ntiles = (cnt + kHotStageFloats / W - 1) / (kHotStageFloats / W);
             u64 waited = 0;
-            if (warp == 0) {
+            if (combine) {
+                ntiles = 0; // nothing travels through the ring
+                if constexpr (kCanSplit) {
+                    if (warp == 0) {
+                        // every run of this row has been summed (the run items precede the combines in
+                        // ticket order and every earlier ticket is held by a resident group)
+                        const u32 need = kSplitTiles * QA;
+                        while (*reinterpret_cast<volatile u32 *>(&hl.split_done[h]) < need)
+                            __nanosleep(100);
+                        __threadfence();
+                        typename F1::Ctx ctx;
+                        memcpy(&ctx, &it.ctx, sizeof(ctx));
+                        const size_t col = (size_t)q * 32 + lane;
+                        if (col < D) {
+                            auto acc = f1.load(ctx, col);
+                            const u32 L = split_run_length(it.h.cnt);
+#pragma unroll
+                            for (u32 r = 0; r < kSplitTiles; r++)
+                                if (r * L < it.h.cnt) // (an empty run contributes nothing, not even + 0)
+                                    acc = f1.step_pre(acc, __ldcg(hl.partials + ((size_t)h * kSplitTiles + r) * D + col));
+                            f1.store(ctx, col, acc);
+                        }
+                    }
+                }
+            } else if (very && split) {
+                if constexpr (kCanSplit) {
+                    if (cnt) {
+                        constexpr int WS = WIDE ? 16 : 32;
+                        if (warp == 0) {
+                            const RunSum<F1> rs{f1, hl.partials + ((size_t)h * kSplitTiles + run) * D};
+                            typename RunSum<F1>::Ctx rc;
+                            hot_add<WS>(hr, rs, rc, D, cnt, q, waited);
+                        } else {
+                            hot_produce<WS, WIDE>(hr, warp - 1, perm + it.h.s0 + first, vals, D, cnt, q);
+                        }
+                    }
+                    if (warp == 0) {
+                        __syncwarp();
+                        __threadfence();
+                        if (lane == 0)
+                            atomicAdd(&hl.split_done[h], 1u);
+                    }
+                }
+            } else if (warp == 0) {
                 typename F1::Ctx ctx;
                 memcpy(&ctx, &it.ctx, sizeof(ctx));
                 if (very && WIDE)

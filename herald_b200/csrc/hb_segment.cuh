@@ -60,13 +60,26 @@ void launch_segment_reduce(KeyWorkspace &ws, const u32 *perm, const float *vals,
 template <class F1, class F4>
 void run_segment_reduce(KeyWorkspace &ws, const u32 *perm, const float *vals, size_t D, size_t n,
                         bool v4, u32 hot_threshold, cudaStream_t st, F1 f1, F4 f4,
-                        const std::function<void()> &after_plan = nullptr) {
+                        const std::function<void()> &after_plan = nullptr, bool split = false) {
     if (n == 0)
         return;
     const bool hot = n > hot_threshold;
     const u32 thr = hot ? hot_threshold : 0xffffffffu;
+    split = split && can_split<F1>::value && hot;
+    if (split) { // run sums of the very hot rows: at most n / kVeryHot rows qualify
+        const size_t need = std::min(ws.split_rows_cap(), n / kVeryHot + 1) * kSplitTiles * D;
+        if (need > ws.split_partials_cap) {
+            HB_CUDA(cudaStreamSynchronize(st));
+            if (ws.split_partials)
+                cudaFree(ws.split_partials);
+            ws.split_partials = nullptr;
+            HB_CUDA(cudaMalloc((void **)&ws.split_partials, need * sizeof(float)));
+            ws.split_partials_cap = need;
+        }
+    }
     HotLists hl{ws.hot_a, ws.hot_b, ws.medium, ws.hot_ctrl(), ws.seg_items, seg_trace_buffer(),
-                hot_stages(), ticket_rows(), medium_threshold(), seg_mode()};
+                hot_stages(), ticket_rows(), medium_threshold(), seg_mode(),
+                split ? 1u : 0u, ws.split_partials, ws.split_done()};
     {   // open every unique row and lay the work items out in ticket order
         const size_t total = n + ticket_rows();
         int g = (int)std::min<size_t>((total + 255) / 256, (size_t)sm_count() * 8);

@@ -382,6 +382,7 @@ void KeyWorkspace::reserve(size_t n) {
     release();
     size_t c = std::max<size_t>(n, 4096);
     c = (c + 4095) / 4096 * 4096;
+    cap = c; // (the arena sizes below depend on it)
     for (int i = 0; i < 2; i++) {
         dev_alloc(keys[i], c);
         dev_alloc(vals[i], c);
@@ -427,6 +428,8 @@ void KeyWorkspace::release() {
     dev_free(side_arena);
     dev_free(hot_a);
     dev_free(hot_b);
+    dev_free(split_partials);
+    split_partials_cap = 0;
     dev_free(medium);
     {
         char *p = reinterpret_cast<char *>(seg_items);

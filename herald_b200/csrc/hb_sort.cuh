@@ -37,6 +37,8 @@ struct KeyWorkspace {
     // main scan arena so that reset_main() zeroes them with the same memset
     u32 *hot_a = nullptr, *hot_b = nullptr, *medium = nullptr; // [cap] item indices
     void *seg_items = nullptr; // [cap + 32] x 32 B, ticket order
+    float *split_partials = nullptr; // [split_rows_cap()][kSplitTiles][D] tile sums of the two-level reduction
+    size_t split_partials_cap = 0;   // floats
     // main arena (zeroed by reset_main): kScanSlots x (ticket + status[ntile_cap]), then 4 control
     // words (work lists of the segment reduce)
     u64 *scan_arena = nullptr;
@@ -54,7 +56,14 @@ struct KeyWorkspace {
         return ntile_cap + 1;
     }
     size_t arena_words() const {
-        return (size_t)kScanSlots * scan_slot_words() + 4;
+        return (size_t)kScanSlots * scan_slot_words() + 4 + split_rows_cap() / 2 + 1;
+    }
+    // rows that can take the two-level reduction in one call: more than kVeryHot (1024) occurrences each
+    size_t split_rows_cap() const {
+        return cap / 1024 + 2;
+    }
+    u32 *split_done() const { // [split_rows_cap()] tiles finished per very hot row (zeroed by reset_main)
+        return hot_ctrl() + 8;
     }
     size_t side_words() const {
         return scan_slot_words() + (kMaxSortPasses * kSortRadix) / 2 + kMaxSortPasses / 2 + 1;

@@ -42,6 +42,8 @@ def _proto():
     L.hb_cache_set_grad_scale.argtypes = [_vp, ctypes.c_float]
     L.hb_cache_get_grad_scale.argtypes = [_vp, ctypes.POINTER(ctypes.c_float)]
     L.hb_cache_after_stream.argtypes = [_vp, _vp]
+    L.hb_cache_set_reduce_mode.argtypes = [_vp, ctypes.c_int]
+    L.hb_cache_get_reduce_mode.argtypes = [_vp, ctypes.POINTER(ctypes.c_int)]
     L.hb_cache_set_perf.argtypes = [_vp, ctypes.c_int]
     L.hb_cache_set_perf_sampling.argtypes = [_vp, ctypes.c_uint]
     L.hb_cache_reserve.argtypes = [_vp, _sz]
@@ -200,6 +202,19 @@ class CacheBase(object):
     @grad_scale.setter
     def grad_scale(self, v):
         check_call(_LIB.hb_cache_set_grad_scale(self._h, float(v)))
+
+    @property
+    def reduce_mode(self):
+        """"exact": every row's occurrences are added in order, bit-identical to the reference;
+        "split": rows with more than 1024 occurrences in a call use a fixed two-level order
+        (deterministic, within 1e-5 relative of the reference) — herald_b200 extension."""
+        m = ctypes.c_int()
+        check_call(_LIB.hb_cache_get_reduce_mode(self._h, ctypes.byref(m)))
+        return "split" if m.value else "exact"
+
+    @reduce_mode.setter
+    def reduce_mode(self, mode):
+        check_call(_LIB.hb_cache_set_reduce_mode(self._h, {"exact": 0, "split": 1}[mode]))
 
     def after(self, stream_handle):
         """Order the cache's work behind a caller's DLStream (device-pointer callers whose keys /

@@ -242,6 +242,18 @@ int hb_cache_set_bypass(hb_cache *c, int on);                   /* cache.cc:15-3
  * identical to scaling first.  Default 1 (gradients arrive scaled). */
 int hb_cache_set_grad_scale(hb_cache *c, float scale);
 int hb_cache_get_grad_scale(hb_cache *c, float *scale);
+/* Order in which one row's gradient occurrences are added by hb_cache_update*:
+ *   0 (default)  occurrence order, ((row + g0) + g1) + ... — the reference's loop
+ *                (src/hetu_cache/include/embedding.h:78-91): updated rows are BIT-IDENTICAL to it;
+ *   1            rows with more than 1024 occurrences in the call are summed in 8 fixed runs of
+ *                consecutive occurrences (each in occurrence order, from 0), the run sums added to
+ *                the row in run order.  Still deterministic — the shape depends on the occurrence
+ *                count only — but re-associated: those rows agree with the reference within 1e-5
+ *                relative (BASELINE north star), all others stay bit-identical.  At WDL-Criteo
+ *                batch 8192 one id occurs 11 000 times; in mode 0 that one dependent FADD chain,
+ *                not HBM, is what bounds the update kernel. */
+int hb_cache_set_reduce_mode(hb_cache *c, int mode);
+int hb_cache_get_reduce_mode(hb_cache *c, int *mode);
 /* Device-pointer callers: order the cache's streams behind `producer_stream` (a cudaStream_t),
  * i.e. behind the kernels that are still writing the keys / gradients of the next call — what the
  * executor's stream_handle + event is for in ParameterServerCommunicate.py:27-35. */

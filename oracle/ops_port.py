@@ -196,3 +196,44 @@ def indexedslices_oneside_add(ids, values, output):
 def embedding_lookup_gradient(grad_out, ids, table_shape):
     """src/ops/EmbeddingLookup.cu:54-73 — dense table gradient: zero, then scatter-add."""
     return indexedslices_oneside_add(ids, grad_out, np.zeros(table_shape, np.float32))
+
+
+# ---- the two-level reduction order of herald_b200's opt-in "split" mode ---------------------------
+# (csrc/hb_rows.cuh kSplitTiles / split_run_length; not a reference algorithm: the reference adds in
+# occurrence order, src/hetu_cache/include/embedding.h:78-91.  Restated here so that the GPU's
+# re-associated result can be checked BIT FOR BIT against a fixed, documented order.)
+SPLIT_TILES = 8
+VERY_HOT = 1024
+
+
+def split_run_length(cnt):
+    return (((cnt + SPLIT_TILES - 1) // SPLIT_TILES) + 127) & ~127
+
+
+def accumulate_in_order(row, grads, scale=1.0):
+    """((row + s*g0) + s*g1) + ... in float32 — the reference's order."""
+    acc = np.array(row, np.float32)
+    s = np.float32(scale)
+    for g in np.asarray(grads, np.float32):
+        acc = acc + g * s
+    return acc
+
+
+def accumulate_two_level(row, grads, scale=1.0):
+    """Rows with more than VERY_HOT occurrences: SPLIT_TILES runs of split_run_length(cnt)
+    consecutive occurrences, each summed in order from 0, the run sums added to the row in run order."""
+    grads = np.asarray(grads, np.float32)
+    cnt = len(grads)
+    if cnt <= VERY_HOT:
+        return accumulate_in_order(row, grads, scale)
+    L = split_run_length(cnt)
+    s = np.float32(scale)
+    acc = np.array(row, np.float32)
+    for r in range(SPLIT_TILES):
+        if r * L >= cnt:
+            break
+        part = np.zeros_like(acc)
+        for g in grads[r * L:(r + 1) * L]:
+            part = part + g * s
+        acc = acc + part
+    return acc

@@ -1,0 +1,16 @@
+set -x
+mkdir -p gpurun_out
+TAG=${TAG:-sp}
+timeout 900 python -m pytest tests/test_split_reduce_gpu.py tests/test_cache_gpu.py -m gpu -x -q 2>&1 | tail -15 > gpurun_out/${TAG}_pytest.log
+cat gpurun_out/${TAG}_pytest.log
+for mode in exact split; do
+HERALD_REDUCE=$mode timeout 600 python bench.py --steps 50 --warmup 20 --no-cpu-baseline --no-e2e --seg-trace gpurun_out/${TAG}_segtrace_$mode.json > gpurun_out/${TAG}_bench_$mode.json 2> gpurun_out/${TAG}_bench_$mode.err
+tail -3 gpurun_out/${TAG}_bench_$mode.err
+python - gpurun_out/${TAG}_bench_$mode.json gpurun_out/${TAG}_segtrace_$mode.json <<'PY'
+import json,sys
+d=json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
+print('ms/step',round(d['ms_per_step'],4),'roofline',round(d['roofline']['frac'],3),{k:round(v['ms'],4) for k,v in d['roofline']['kernels'].items()})
+t=json.load(open(sys.argv[2]))
+print('span',t['kernel_span_us'],'hot_end',[round(x,1) for x in t['cta_hot_end_us']],'end',[round(x,1) for x in t['cta_end_us']], 'last item', t['last_item_end_us'])
+PY
+done
