@@ -165,8 +165,19 @@ __device__ __forceinline__ u64 make_prio(u32 use, u64 stamp) {
 // clk[0..3]: the replacement clock as a chain — stage s of a call reads clk[s] and writes
 // clk[s+1], so no kernel reads a word that another block of the same kernel writes.
 // flush != 0: the call pushes, so it also flushes the dirty victims collected so far (evict_)
-__global__ void op_begin_kernel(CacheRegs *r, u64 *clk, int flush) {
+// It also zeroes the scan states / work-list counters of the workspaces the call uses (a memset
+// node between two kernels would cost their launch overlap).
+struct ZeroList {
+    KeyWorkspace::ZeroRange r[6];
+    int n;
+};
+__global__ void __launch_bounds__(256) op_begin_kernel(CacheRegs *r, u64 *clk, int flush, ZeroList z) {
     pdl_enter();
+    for (int k = 0; k < z.n; k++)
+        for (u32 w = threadIdx.x; w < z.r[k].words; w += blockDim.x)
+            z.r[k].p[w] = 0;
+    if (threadIdx.x != 0)
+        return;
     r->clock0 = r->clock;
     r->error = 0; // the previous call's failure has been reported in its own record
     clk[0] = r->clock;
@@ -2143,7 +2154,8 @@ void presort(hb_cache *c, const void *dev_keys, int kind, size_t n, int wsi, boo
     const u32 *same = check ? check_same_keys(ws, dev_keys, kind, n, sd) : nullptr;
     // the kernels below rewrite the workspace: its main-stream readers enqueued so far must be done
     // (the comparison above only reads it, and what it reads was written on this stream)
-    HB_CUDA(cudaStreamWaitEvent(sd, c->ev_ws_free[wsi], 0));
+    if (c->ev_ws_free[wsi])
+        HB_CUDA(cudaStreamWaitEvent(sd, c->ev_ws_free[wsi], 0));
     SortedKeys sk{nullptr, nullptr};
     if (n)
         sk = radix_sort_keys(ws, dev_keys, kind, n, c->key_bits, sd, same);
@@ -2157,33 +2169,44 @@ void presort(hb_cache *c, const void *dev_keys, int kind, size_t n, int wsi, boo
 // Call boundary on the main stream.  Everything that is not a kernel (memsets, event records and
 // waits) is gathered here: between two kernels it would cost their launch overlap (PDL).
 // ws_a / ws_b: workspaces the call's kernels read (their presort must have finished); -1 = none.
-void begin_call(hb_cache *c, bool flush, int ws_a, int ws_b = -1) {
+void begin_call(hb_cache *c, bool flush, size_t n, int ws_a, int ws_b = -1) {
     int idx = (int)(c->calls % hb_cache::kRing);
     c->phase_mask[idx] = 0;
     c->dl_of_call[idx] = 0;
+    ZeroList z;
+    z.n = 0;
     for (int w : {ws_a, ws_b})
         if (w >= 0) {
-            c->ws[w].reset_main(c->stream);
+            z.n += c->ws[w].main_ranges(n, 2, z.r + z.n);
             HB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_sorted[w], 0));
         }
-    HB_CUDA(cudaEventRecord(c->ev_begin[idx], c->stream));
-    HB_LAUNCH(op_begin_kernel, 1, 1, 0, c->stream, c->view.regs, clk_of(c), flush ? 1 : 0);
+    // the call's duration is only measured with perf enabled (python_api.cc:40-41), and with perf
+    // sampling only on the sampled calls
+    c->timed[idx] = c->perf_phases && !(c->perf_every > 1 && (c->calls / 2) % c->perf_every != 0);
+    if (c->timed[idx])
+        HB_CUDA(cudaEventRecord(c->ev_begin[idx], c->stream));
+    HB_LAUNCH(op_begin_kernel, 1, 256, 0, c->stream, c->view.regs, clk_of(c), flush ? 1 : 0, z);
     HB_LAUNCHED();
 }
 
 // the main-stream readers of workspace `wsi` enqueued so far end here
 void release_ws(hb_cache *c, int wsi) {
-    HB_CUDA(cudaEventRecord(c->ev_ws_free[wsi], c->stream));
+    HB_CUDA(cudaEventRecord(c->ev_ws_rel[wsi], c->stream));
+    c->ev_ws_free[wsi] = c->ev_ws_rel[wsi];
+}
+// ... the same when the call has just ended: its end event stands for the release
+void release_ws_at_end(hb_cache *c, int wsi) {
+    c->ev_ws_free[wsi] = c->ev_last_end;
 }
 
 void end_call(hb_cache *c, int last_stage, u32 kind, size_t n, bool inserted) {
     int idx = (int)(c->calls % hb_cache::kRing);
-    HB_LAUNCH(op_end_kernel, 1, 1, 0, c->stream, c->view, clk_of(c), last_stage, c->dev_record, kind, (u32)n,
+    // the record goes straight into the host's ring (mapped pinned memory): no copy node
+    HB_LAUNCH(op_end_kernel, 1, 1, 0, c->stream, c->view, clk_of(c), last_stage, c->ring_dev + idx, kind, (u32)n,
                                           inserted ? 1 : 0);
     HB_LAUNCHED();
-    HB_CUDA(cudaMemcpyAsync(&c->ring[idx], c->dev_record, sizeof(PerfRecord), cudaMemcpyDeviceToHost,
-                            c->stream));
     HB_CUDA(cudaEventRecord(c->ev_end[idx], c->stream));
+    c->ev_last_end = c->ev_end[idx];
     c->ticks_ring[idx] = c->cur_ticks + 4; // + the single-line paths (reinsert touch)
     c->cur_ticks = 0;
     c->calls++;
@@ -2435,11 +2458,11 @@ void do_update(hb_cache *c, const void *keys, int kind, size_t n, const float *g
     presort(c, dkeys, kind, n, w, /*check=*/true);
     const float *dgrads = stage_grads(c, grads, n);
     const u64 *dpush = use_plan ? stage_push_keys(c, push_keys, push_kind, n_push) : nullptr;
-    begin_call(c, /*flush=*/true, w);
+    begin_call(c, /*flush=*/true, n, w);
     resolve_batch(c, n, 0, w, /*dataless=*/true, 0);
     run_accumulate(c, n, 0, w, dgrads, dpush, n_push, use_plan);
     end_call(c, 1, 1, n, false);
-    release_ws(c, w);
+    release_ws_at_end(c, w);
     if (dgrads != grads)
         HB_CUDA(cudaEventRecord(c->ev_grads_free, c->stream));
 }
@@ -2647,7 +2670,7 @@ int hb_cache_create(int policy, size_t limit, size_t length, size_t width, int n
     HB_CUDA(cudaStreamCreateWithFlags(&c->side2, cudaStreamNonBlocking));
     HB_CUDA(cudaStreamCreateWithFlags(&c->h2d, cudaStreamNonBlocking));
     HB_CUDA(cudaStreamCreateWithFlags(&c->d2h, cudaStreamNonBlocking));
-    for (cudaEvent_t *e : {&c->ev_ws_free[0], &c->ev_ws_free[1], &c->ev_sorted[0], &c->ev_sorted[1],
+    for (cudaEvent_t *e : {&c->ev_ws_rel[0], &c->ev_ws_rel[1], &c->ev_sorted[0], &c->ev_sorted[1],
                            &c->ev_up, &c->ev_grads_free, &c->ev_gathered[0], &c->ev_gathered[1],
                            &c->ev_dl[0], &c->ev_dl[1], &c->ev_producer, &c->ev_fork, &c->ev_join})
         HB_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
@@ -2743,8 +2766,10 @@ int hb_cache_create(int policy, size_t limit, size_t length, size_t width, int n
     HB_CUDA(cudaMalloc((void **)&rec, 128));
     HB_CUDA(cudaMemset(rec, 0, 128));
     c->dev_record = reinterpret_cast<PerfRecord *>(rec);
-    HB_CUDA(cudaHostAlloc((void **)&c->ring, sizeof(PerfRecord) * hb_cache::kRing, cudaHostAllocDefault));
+    HB_CUDA(cudaHostAlloc((void **)&c->ring, sizeof(PerfRecord) * hb_cache::kRing,
+                          cudaHostAllocMapped | cudaHostAllocPortable));
     std::memset(c->ring, 0, sizeof(PerfRecord) * hb_cache::kRing);
+    HB_CUDA(cudaHostGetDevicePointer((void **)&c->ring_dev, c->ring, 0));
     c->ev_begin.resize(hb_cache::kRing);
     c->ev_end.resize(hb_cache::kRing);
     for (int i = 0; i < hb_cache::kRing; i++) {
@@ -2815,7 +2840,7 @@ int hb_cache_destroy(hb_cache *c) {
             cudaEventDestroy(e);
         for (auto &e : c->ev_phase)
             cudaEventDestroy(e);
-        for (cudaEvent_t e : {c->ev_ws_free[0], c->ev_ws_free[1], c->ev_sorted[0], c->ev_sorted[1],
+        for (cudaEvent_t e : {c->ev_ws_rel[0], c->ev_ws_rel[1], c->ev_sorted[0], c->ev_sorted[1],
                               c->ev_up, c->ev_grads_free, c->ev_gathered[0], c->ev_gathered[1],
                               c->ev_dl[0], c->ev_dl[1], c->ev_producer, c->ev_fork, c->ev_join})
             cudaEventDestroy(e);
@@ -2960,7 +2985,7 @@ int hb_cache_lookup(hb_cache *c, const void *keys, int key_kind, size_t n, float
     c->cur = w;
     int k;
     float *ddest = stage_dest(c, dest, n, &k);
-    begin_call(c, false, w);
+    begin_call(c, false, n, w);
     resolve_batch(c, n, 0, w, /*dataless=*/false, 0);
     // The insert phase (victim selection, evictions, index inserts) needs the resolve's results
     // only: it works on slot scalars and the index, never on row data, and its victims are never
@@ -3025,7 +3050,7 @@ int hb_cache_push_pull(hb_cache *c, const void *pull_keys, int pull_kind, size_t
     int k;
     float *ddest = stage_dest(c, dest, n_pull, &k);
     const float *dgrads = stage_grads(c, grads, n_push);
-    begin_call(c, /*flush=*/true, wpull, wpush);
+    begin_call(c, /*flush=*/true, std::max(n_pull, n_push), wpull, wpush);
     // cache.cc:360-391: pull-side lookup, then push-side lookup + accumulate
     resolve_batch(c, n_pull, 0, wpull, /*dataless=*/false, 0, false);
     resolve_batch(c, n_push, 1, wpush, /*dataless=*/true, 1, false);
@@ -3151,10 +3176,12 @@ static void fill_perf(hb_cache *c, uint64_t call, hb_perf *perf) {
     perf->size = r.size;
     perf->error = r.error;
     float ms = 0.f;
-    if (cudaEventElapsedTime(&ms, c->ev_begin[idx], c->ev_end[idx]) == cudaSuccess)
-        perf->time_ms = ms;
-    else
-        cudaGetLastError();
+    if (c->timed[idx]) {
+        if (cudaEventElapsedTime(&ms, c->ev_begin[idx], c->ev_end[idx]) == cudaSuccess)
+            perf->time_ms = ms;
+        else
+            cudaGetLastError();
+    }
     // phase split (reference perf dict: sort/lookup/transfer/copy/insert, cache.cc:99-104, :189-193)
     const uint32_t mask = c->phase_mask[idx];
     auto span = [&](cudaEvent_t a, cudaEvent_t b) {
@@ -3451,7 +3478,7 @@ int hb_cache_touch(hb_cache *c, uint64_t key, int *found, int64_t *version, floa
     cudaStream_t st = c->stream;
     KeyWorkspace &ws = c->ws[c->cur];
     // a batched lookup of one key without the insert/sync half: CacheBase::lookup via python
-    begin_call(c, false, c->cur);
+    begin_call(c, false, 1, c->cur);
     ws.sorted_valid = false;
     HB_LAUNCH(single_key_kernel, 1, 1, 0, st, ws.uniq, ws.num_unique, key);
     HB_LAUNCHED();
@@ -3499,7 +3526,7 @@ int hb_cache_insert(hb_cache *c, uint64_t key, int64_t version, const float *dat
         }
     } else {
         KeyWorkspace &ws = c->ws[c->cur];
-        begin_call(c, false, c->cur);
+        begin_call(c, false, 1, c->cur);
         ws.sorted_valid = false;
         HB_LAUNCH(single_key_kernel, 1, 1, 0, st, ws.uniq, ws.num_unique, key);
         HB_LAUNCHED();

@@ -257,7 +257,9 @@ struct hb_cache {
     cudaStream_t side2 = nullptr;               // a lookup's insert phase, next to its sync + gather
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     int cur = 0;                                // workspace that holds the most recent lookup batch
-    cudaEvent_t ev_ws_free[2] = {nullptr, nullptr}; // main: the readers of ws[i] enqueued so far are done
+    cudaEvent_t ev_ws_free[2] = {nullptr, nullptr}; // (handle) main: the readers of ws[i] enqueued so far are done
+    cudaEvent_t ev_ws_rel[2] = {nullptr, nullptr};  // owned events ev_ws_free may point at
+    cudaEvent_t ev_last_end = nullptr;              // end event of the call enqueued last
     cudaEvent_t ev_sorted[2] = {nullptr, nullptr};  // side: ws[i] holds uniq / inverse / segments
     cudaEvent_t ev_up = nullptr;                // h2d: the gradients of the running update have arrived
     cudaEvent_t ev_grads_free = nullptr;        // main: the gradient staging buffer has been consumed
@@ -289,7 +291,9 @@ struct hb_cache {
     void *score_scratch = nullptr; // hb_cache_score / hb_cache_probe staging
     size_t score_scratch_cap = 0;
     // perf ring (pinned host) + events
-    hb::PerfRecord *ring = nullptr;
+    hb::PerfRecord *ring = nullptr;      // [kRing] mapped pinned memory: op_end writes the record there
+    hb::PerfRecord *ring_dev = nullptr;  // the same ring as the device sees it
+    bool timed[1024] = {};               // [kRing] the call carries its begin event
     hb::PerfRecord *dev_record = nullptr;
     static constexpr int kRing = 1024;
     uint64_t calls = 0;

@@ -8,6 +8,8 @@
 // accumulates gradients in (src/hetu_cache/src/cache.cc:145-154).
 #pragma once
 
+#include <algorithm>
+
 #include "hb_common.cuh"
 
 namespace hb {
@@ -88,6 +90,22 @@ struct KeyWorkspace {
         if (sort_epoch == 0)
             sort_epoch = 1;
         return sort_epoch;
+    }
+    // The words of the main arena a call of `n` keys with at most `slots` grid scans can touch, as
+    // ranges a kernel zeroes (the cache's op_begin does, instead of a memset node between kernels).
+    struct ZeroRange {
+        u64 *p;
+        u32 words;
+    };
+    int main_ranges(size_t n, int slots, ZeroRange *out) {
+        const u32 tiles = (u32)std::min<size_t>(ntile_cap, n / kScanBlock + 2);
+        int k = 0;
+        for (int s = 0; s < slots; s++)
+            out[k++] = ZeroRange{scan_arena + (size_t)s * scan_slot_words(), tiles + 1};
+        out[k++] = ZeroRange{scan_arena + (size_t)kScanSlots * scan_slot_words(),
+                             (u32)(4 + std::min<size_t>(split_rows_cap(), n / 1024 + 2) / 2 + 1)};
+        scan_next = 0;
+        return k;
     }
     // zero the scan slots / the sort's counters — once per op, before the kernels that use them
     void reset_main(cudaStream_t st);
