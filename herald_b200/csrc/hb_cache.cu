@@ -183,6 +183,8 @@ __global__ void __launch_bounds__(256) op_begin_kernel(CacheRegs *r, u64 *clk, i
     clk[0] = r->clock;
     clk[1] = clk[2] = clk[3] = r->clock;
     r->U = r->M = r->alloc_base = 0;
+    r->alloc_top0 = r->alloc_top1 = r->free_top;
+    r->tail_done = 0;
     r->pulled = r->pushed = 0;
     r->pulled_remote = r->pushed_remote = 0;
     r->flushed = flush ? r->pending : 0;
@@ -190,9 +192,8 @@ __global__ void __launch_bounds__(256) op_begin_kernel(CacheRegs *r, u64 *clk, i
     r->U2 = r->M2 = r->alloc_base2 = 0;
 }
 
-__global__ void op_end_kernel(CacheView c, const u64 *clk, int last_stage, PerfRecord *rec, u32 kind,
-                              u32 num_all, int inserted_batch) {
-    pdl_enter();
+__device__ __forceinline__ void op_end_body(const CacheView &c, const u64 *clk, int last_stage, PerfRecord *rec,
+                                            u32 kind, u32 num_all, int inserted_batch) {
     CacheRegs *r = c.regs;
     r->clock = clk[last_stage];
     if (inserted_batch) {
@@ -227,6 +228,12 @@ __global__ void op_end_kernel(CacheView c, const u64 *clk, int last_stage, PerfR
     rec->floor = r->floor;
 }
 
+__global__ void op_end_kernel(CacheView c, const u64 *clk, int last_stage, PerfRecord *rec, u32 kind,
+                              u32 num_all, int inserted_batch) {
+    pdl_enter();
+    op_end_body(c, clk, last_stage, rec, kind, num_all, inserted_batch);
+}
+
 // =====================================================================================
 // resolve: policy lookup of every unique key (+ touch), ordered compaction of the misses
 // =====================================================================================
@@ -235,11 +242,15 @@ constexpr int kResolveItems = 1; // measured: 4 per thread is slower (the probes
 
 __global__ void __launch_bounds__(kScanBlock)
     resolve_kernel(CacheView c, const u64 *uniq, const u32 *num_unique, i32 *uslot, u32 *miss_list,
-                   int bypass, ScanState st, u32 ntiles, const u64 *clk_in, u64 *clk_out, int batch) {
+                   int bypass, ScanState st, u32 ntiles, const u64 *clk_in, u64 *clk_out, int batch,
+                   int dataless) {
     pdl_enter();
     const u32 tile = take_ticket(st.ticket);
     const u32 U = *num_unique;
     const u64 base = *clk_in;
+    // height of the free stack when this kernel starts (op_begin / the previous resolve of the call
+    // left it there: the last tile of THIS kernel lowers regs->free_top while other tiles still run)
+    const u32 top_in = batch == 0 ? c.regs->alloc_top0 : c.regs->alloc_top1;
     // kResolveItems consecutive uniques per thread
     const u32 i0 = (tile * kScanBlock + threadIdx.x) * kResolveItems;
     u64 key[kResolveItems];
@@ -293,54 +304,45 @@ __global__ void __launch_bounds__(kScanBlock)
     }
     ScanResult sr = grid_exclusive_scan<kScanBlock>(st, miss, tile);
     u32 pos = sr.excl;
+    // Every miss gets a fresh line right here (cache.cc:70-76 with data, :146-151 dataless): miss
+    // number j of the call takes the j-th slot from the top of the free stack — its rank is all a
+    // thread needs, so no second kernel has to wait for the total.
 #pragma unroll
     for (int j = 0; j < kResolveItems; j++)
-        if (i0 + j < U && sl[j] < 0)
-            miss_list[pos++] = i0 + j;
+        if (i0 + j < U && sl[j] < 0) {
+            const u32 jpos = pos++;
+            miss_list[jpos] = i0 + j;
+            if (jpos < top_in) {
+                const u32 s = c.free_stack[top_in - 1 - jpos];
+                uslot[i0 + j] = (i32)s;
+                c.slot_key[s] = key[j];
+                c.slot_version[s] = -1; // embedding.h:35,42
+                c.slot_updates[s] = 0;
+                c.slot_prio[s] = PRIO_NONE;
+                c.slot_use[s] = 0;
+                c.slot_state[s] = S_TRANSIENT;
+                c.slot_flags[s] = dataless ? F_DATALESS : 0;
+            }
+        }
     if (tile == ntiles - 1 && threadIdx.x == 0) {
         CacheRegs *r = c.regs;
         u32 M = sr.tile_prefix + sr.tile_total;
-        u32 top = r->free_top;
-        u32 alloc_base = 0;
-        if (M > top) {
+        if (M > top_in) {
             atomicMax(&r->error, (u32)E_NO_FREE_SLOT);
-            M = top; // keep memory safe; the call is reported as failed
+            M = top_in; // the misses beyond have no line (uslot -1); the call is reported as failed
         }
-        alloc_base = top - M;
-        r->free_top = alloc_base;
-        r->slot_hw = max(r->slot_hw, c.capacity - alloc_base); // the stack hands out 0, 1, 2, ...
+        const u32 new_top = top_in - M;
+        r->free_top = new_top;
+        r->alloc_top1 = new_top;
+        r->slot_hw = max(r->slot_hw, c.capacity - new_top); // the stack hands out 0, 1, 2, ...
         if (batch == 0) {
             r->U = U;
             r->M = M;
-            r->alloc_base = alloc_base;
         } else {
             r->U2 = U;
             r->M2 = M;
-            r->alloc_base2 = alloc_base;
         }
         *clk_out = base + U;
-    }
-}
-
-// Give every miss a fresh line (cache.cc:70-76 with data, :146-151 dataless).
-__global__ void alloc_kernel(CacheView c, const u64 *uniq, i32 *uslot, const u32 *miss_list,
-                             int batch, int dataless) {
-    pdl_enter();
-    const CacheRegs *r = c.regs;
-    const u32 M = batch == 0 ? r->M : r->M2;
-    const u32 alloc_base = batch == 0 ? r->alloc_base : r->alloc_base2;
-    u32 j = blockIdx.x * blockDim.x + threadIdx.x;
-    for (; j < M; j += gridDim.x * blockDim.x) {
-        const u32 i = miss_list[j];
-        const u32 s = c.free_stack[alloc_base + j];
-        uslot[i] = (i32)s;
-        c.slot_key[s] = uniq[i];
-        c.slot_version[s] = -1; // embedding.h:35,42
-        c.slot_updates[s] = 0;
-        c.slot_prio[s] = PRIO_NONE;
-        c.slot_use[s] = 0;
-        c.slot_state[s] = S_TRANSIENT;
-        c.slot_flags[s] = dataless ? F_DATALESS : 0;
     }
 }
 
@@ -1060,7 +1062,7 @@ __device__ __forceinline__ void insert_new(const CacheView &c, const i32 *uslot,
 // victims out of the index, the others put the new lines in.  The two may interleave on the
 // open-addressing index: an insert only fills EMPTY or TOMB entries and an erase only turns its
 // own key into TOMB, so no probe chain ever gains an EMPTY entry in front of a live key; the
-// slots of the new lines were taken from the free stack before (alloc_kernel), the victims'
+// slots of the new lines were taken from the free stack before (resolve_kernel), the victims'
 // slots return to it for later calls.
 __global__ void __launch_bounds__(256)
     evict_insert_kernel(CacheView c, const i32 *uslot, const u32 *miss_list, u32 evict_blocks) {
@@ -1590,6 +1592,51 @@ __global__ void free_transient_kernel(CacheView c, const i32 *uslot, const u32 *
         c.slot_updates[s] = 0;
         c.slot_flags[s] = 0;
         c.free_stack[atomicAdd(&r->free_top, 1u)] = s;
+    }
+}
+
+// The tail of a single-GPU update in ONE launch: flush of the dirty victims collected since the last
+// push (FlushPending), release of the dataless lines of this call's misses (free_transient), and —
+// by whichever CTA finishes last — the call's epilogue (op_end): three kernels and two launch gaps
+// less on the step's critical path.
+template <int VEC>
+__global__ void __launch_bounds__(kRowBlock)
+    update_tail_kernel(CacheView c, const i32 *uslot, const u32 *miss_list, const u64 *clk, int last_stage,
+                       PerfRecord *rec, u32 num_all) {
+    pdl_enter();
+    CacheRegs *r = c.regs;
+    const unsigned lane = lane_id();
+    {   // pending victims: one warp per line
+        FlushPending<VEC> f{c, 0};
+        const size_t warp_global = (size_t)blockIdx.x * kRowWarps + (threadIdx.x >> 5);
+        const size_t nwarps = (size_t)gridDim.x * kRowWarps;
+        const size_t nvec = c.width / VEC;
+        const size_t R = r->flushed;
+        for (size_t e = warp_global; e < R; e += nwarps) {
+            for (size_t k = lane; k < nvec; k += 32)
+                f.apply(e, k);
+            __syncwarp();
+            f.end(e);
+        }
+    }
+    const u32 M = r->M;
+    for (u32 j = blockIdx.x * blockDim.x + threadIdx.x; j < M; j += gridDim.x * blockDim.x) {
+        const u32 s = (u32)uslot[miss_list[j]];
+        c.slot_state[s] = S_FREE;
+        c.slot_updates[s] = 0;
+        c.slot_flags[s] = 0;
+        c.free_stack[atomicAdd(&r->free_top, 1u)] = s;
+    }
+    __shared__ u32 s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0)
+        s_last = atomicAdd(&r->tail_done, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (s_last && threadIdx.x == 0) {
+        __threadfence();
+        r->pending = 0; // the pending victims have just been pushed
+        op_end_body(c, clk, last_stage, rec, 1, num_all, 0);
     }
 }
 
@@ -2199,12 +2246,14 @@ void release_ws_at_end(hb_cache *c, int wsi) {
     c->ev_ws_free[wsi] = c->ev_last_end;
 }
 
-void end_call(hb_cache *c, int last_stage, u32 kind, size_t n, bool inserted) {
+void end_call(hb_cache *c, int last_stage, u32 kind, size_t n, bool inserted, bool epilogue_done = false) {
     int idx = (int)(c->calls % hb_cache::kRing);
     // the record goes straight into the host's ring (mapped pinned memory): no copy node
-    HB_LAUNCH(op_end_kernel, 1, 1, 0, c->stream, c->view, clk_of(c), last_stage, c->ring_dev + idx, kind, (u32)n,
-                                          inserted ? 1 : 0);
-    HB_LAUNCHED();
+    if (!epilogue_done) { // (a single-GPU update's tail kernel has already written it)
+        HB_LAUNCH(op_end_kernel, 1, 1, 0, c->stream, c->view, clk_of(c), last_stage, c->ring_dev + idx, kind,
+                  (u32)n, inserted ? 1 : 0);
+        HB_LAUNCHED();
+    }
     HB_CUDA(cudaEventRecord(c->ev_end[idx], c->stream));
     c->ev_last_end = c->ev_end[idx];
     c->ticks_ring[idx] = c->cur_ticks + 4; // + the single-line paths (reinsert touch)
@@ -2225,13 +2274,8 @@ void resolve_batch(hb_cache *c, size_t n, int batch, int wsi, bool dataless, int
     HB_LAUNCH(resolve_kernel, ntiles, kScanBlock, 0, st, c->view, ws.uniq, ws.num_unique, c->uslot[batch],
                                                   c->miss_list[batch], c->bypass ? 1 : 0,
                                                   ws.next_scan(), ntiles, clk + clk_stage,
-                                                  clk + clk_stage + 1, batch);
+                                                  clk + clk_stage + 1, batch, dataless ? 1 : 0);
     HB_LAUNCHED();
-    if (n) {
-        HB_LAUNCH(alloc_kernel, lin_grid(n), 256, 0, st, c->view, ws.uniq, c->uslot[batch],
-                                                  c->miss_list[batch], batch, dataless ? 1 : 0);
-        HB_LAUNCHED();
-    }
     if (marks)
         mark(c, 1);
 }
@@ -2349,7 +2393,8 @@ void exchange_pushes(hb_cache *c) {
 
 // accumulate + push of batch `batch`, then flush of pending victims, then drop dataless lines
 void run_accumulate(hb_cache *c, size_t n, int batch, int wsi, const float *dev_grads,
-                    const u64 *dev_push_keys, size_t n_push, bool use_plan, bool defer_cleanup = false) {
+                    const u64 *dev_push_keys, size_t n_push, bool use_plan, bool defer_cleanup = false,
+                    bool fuse_tail = false) {
     cudaStream_t st = c->stream;
     KeyWorkspace &ws = c->ws[wsi];
     if (c->view.pv.world > 1) {
@@ -2388,6 +2433,19 @@ void run_accumulate(hb_cache *c, size_t n, int batch, int wsi, const float *dev_
             HB_LAUNCHED();
         }
         exchange_pushes(c);
+    } else if (fuse_tail) {
+        // flush + release of the dataless lines + the call's epilogue in one launch
+        const int idx = (int)(c->calls % hb_cache::kRing);
+        const int grid = std::max(row_grid(pend), std::max(1, lin_grid(n) / 4));
+        if (c->width % 4 == 0)
+            HB_LAUNCH(update_tail_kernel<4>, grid, kRowBlock, 0, st, c->view, c->uslot[batch], c->miss_list[batch],
+                      clk_of(c), 1, c->ring_dev + idx, (u32)n);
+        else
+            HB_LAUNCH(update_tail_kernel<1>, grid, kRowBlock, 0, st, c->view, c->uslot[batch], c->miss_list[batch],
+                      clk_of(c), 1, c->ring_dev + idx, (u32)n);
+        HB_LAUNCHED();
+        c->pending_upper = 0;
+        return;
     } else if (pend) {
         int grid = row_grid(pend);
         if (c->width % 4 == 0) {
@@ -2460,8 +2518,9 @@ void do_update(hb_cache *c, const void *keys, int kind, size_t n, const float *g
     const u64 *dpush = use_plan ? stage_push_keys(c, push_keys, push_kind, n_push) : nullptr;
     begin_call(c, /*flush=*/true, n, w);
     resolve_batch(c, n, 0, w, /*dataless=*/true, 0);
-    run_accumulate(c, n, 0, w, dgrads, dpush, n_push, use_plan);
-    end_call(c, 1, 1, n, false);
+    const bool fuse_tail = c->view.pv.world == 1;
+    run_accumulate(c, n, 0, w, dgrads, dpush, n_push, use_plan, false, fuse_tail);
+    end_call(c, 1, 1, n, false, fuse_tail);
     release_ws_at_end(c, w);
     if (dgrads != grads)
         HB_CUDA(cudaEventRecord(c->ev_grads_free, c->stream));
@@ -3485,12 +3544,10 @@ int hb_cache_touch(hb_cache *c, uint64_t key, int *found, int64_t *version, floa
     u64 *clk = clk_of(c);
     HB_LAUNCH(resolve_kernel, 1, kScanBlock, 0, st, c->view, ws.uniq, ws.num_unique, c->uslot[0],
                                              c->miss_list[0], c->bypass ? 1 : 0, ws.next_scan(), 1,
-                                             clk, clk + 1, 0);
+                                             clk, clk + 1, 0, 0);
     HB_LAUNCHED();
     // a miss reserved a slot for a fresh line; materialise and hand it back (lookup() alone
     // allocates nothing)
-    HB_LAUNCH(alloc_kernel, 1, 32, 0, st, c->view, ws.uniq, c->uslot[0], c->miss_list[0], 0, 0);
-    HB_LAUNCHED();
     HB_LAUNCH(free_transient_kernel, 1, 32, 0, st, c->view, c->uslot[0], c->miss_list[0], 0, 0);
     HB_LAUNCHED();
     end_call(c, 1, 0, 1, false);
@@ -3533,9 +3590,7 @@ int hb_cache_insert(hb_cache *c, uint64_t key, int64_t version, const float *dat
         u64 *clk = clk_of(c);
         // bypass=1: resolve as a miss without touching anything, which allocates the fresh line
         HB_LAUNCH(resolve_kernel, 1, kScanBlock, 0, st, c->view, ws.uniq, ws.num_unique, c->uslot[0],
-                                                 c->miss_list[0], 1, ws.next_scan(), 1, clk, clk, 0);
-        HB_LAUNCHED();
-        HB_LAUNCH(alloc_kernel, 1, 32, 0, st, c->view, ws.uniq, c->uslot[0], c->miss_list[0], 0, 0);
+                                                 c->miss_list[0], 1, ws.next_scan(), 1, clk, clk, 0, 0);
         HB_LAUNCHED();
         i32 *dslot = nullptr, hslot = -1;
         dmalloc(dslot, 1);

@@ -143,7 +143,9 @@ struct CacheRegs {
     u64 clock0;     // clock at call start
     u32 U;          // unique keys of the batch being resolved
     u32 M;          // misses among them
-    u32 alloc_base; // free_stack[alloc_base + j] is the slot of miss j
+    u32 alloc_base; // (unused)
+    u32 alloc_top0, alloc_top1; // free-stack height at the start of the call / after its first resolve:
+                                // miss j of a resolve takes free_stack[top - 1 - j]
     u32 pulled;     // rows transferred by the sync
     u32 pushed;     // lines pushed by the update
     u32 flushed;    // pending victims flushed by the update
@@ -173,6 +175,7 @@ struct CacheRegs {
     u64 sel_floor0;   // floor at the start of the selection (the log walk moves `floor` itself)
     // multi-GPU traffic of the call (zeroed by op_begin): rows pulled from / lines pushed to a PEER
     u32 pulled_remote, pushed_remote;
+    u32 tail_done; // CTAs of update_tail_kernel that have finished (zeroed by op_begin)
 };
 
 // Everything a kernel needs to address the cache (passed by value).

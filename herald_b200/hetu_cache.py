@@ -299,7 +299,12 @@ class CacheBase(object):
         self._recorded = upto + 1
 
     def _issue(self, *keepalive):
-        return _waittype(self, keepalive, self._last_call())
+        seq = self._last_call()
+        # the library keeps the records of the last 1024 calls: with perf on, collect the old ones
+        # before they are overwritten (they belong to calls that finished long ago)
+        if self._perf_enabled and seq - self._recorded > 768:
+            self._drain(seq - 256)
+        return _waittype(self, keepalive, seq)
 
     # ---- numpy entry points (uint64 keys) ------------------------------------------------
     def embedding_lookup(self, keys, dest):

@@ -134,11 +134,18 @@ class _ShmRing(object):
                 return
             time.sleep(1e-5)
 
-    def recv(self):
-        """Blocks until a message is there (topk_scheduler.cc:254-278)."""
+    def recv(self, timeout_s=None):
+        """Blocks until a message is there (topk_scheduler.cc:254-278); the reference waits for
+        ever, here a planner that died is reported after `timeout_s` ($HERALD_LAIA_TIMEOUT_S, 600)."""
+        import os
         import time
+        if timeout_s is None:
+            timeout_s = float(os.environ.get("HERALD_LAIA_TIMEOUT_S", "600"))
+        deadline = time.time() + timeout_s
         n = ctypes.c_longlong()
         while True:
+            if time.time() > deadline:
+                raise RuntimeError("no message from the planning process within %.0f s" % timeout_s)
             check_call(_LIB.hb_shmring_recv(self._h, None, _sz(0), ctypes.byref(n)))
             if n.value >= 0:
                 out = np.empty(max(n.value, 1), np.uint64)
@@ -183,9 +190,15 @@ class TopkScheduler(LaiaScheduler):
         self.rank, self.nrank, self.mini_batch_size = int(rank), int(nrank), int(mini_batch_size)
         self._queue, self._done = [], False
         if self.local_shared:
-            if self.local_rank == 0:        # topk_scheduler.cc:70-80: creates every local ring, then opens its own
-                self._rings = [_ShmRing("laia_cache_%d" % i, True, ring_bytes) for i in range(self.local_size)]
-            self._my_ring = _ShmRing("laia_cache_%d" % self.local_rank, False)
+            # "laia_cache_<i>" in the reference (topk_scheduler.cc:70-80); here the name also carries
+            # the job (the launcher's pid, common to the node's workers, or $HERALD_LAIA_SESSION), so a
+            # ring left in /dev/shm by a crashed run is never mistaken for this run's
+            import os
+            job = os.environ.get("HERALD_LAIA_SESSION", str(os.getppid()))
+            name = lambda i: "laia_cache_%s_%d" % (job, i)
+            if self.local_rank == 0:        # creates every local ring, then opens its own
+                self._rings = [_ShmRing(name(i), True, ring_bytes) for i in range(self.local_size)]
+            self._my_ring = _ShmRing(name(self.local_rank), False)
             if self.local_rank != 0:
                 return                      # no planner in this process (:181-185)
         embs = np.ascontiguousarray(sample_embs, dtype=np.uint64)

@@ -382,7 +382,8 @@ def test_perf_sampling(oracle_impl):
         perf = list(h.gc.perf)[-32:]
         timed = [p for p in perf if p["lookup_time"] > 0]
         assert 0 < len(timed) < len(perf)
-        assert all(p["num_all"] == 40 and p["time"] > 0 for p in perf)
+        assert all(p["num_all"] == 40 for p in perf)             # counters on every call
+        assert all(p["time"] > 0 for p in timed)                 # durations on the sampled calls
     finally:
         h.close()
 

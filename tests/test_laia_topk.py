@@ -140,7 +140,7 @@ def test_shm_ring_between_processes():
     ring = _ShmRing(name, True, 4096)            # 512 words: the writer has to wait for the reader
     msgs = [list(range(i, i + 1 + (37 * i) % 300)) for i in range(40)] + [[0]]
     q = mp.get_context("spawn").Queue()
-    proc = mp.get_context("spawn").Process(target=_ring_reader, args=(name, len(msgs), q))
+    proc = mp.get_context("spawn").Process(target=_ring_reader, args=(name, len(msgs), q), daemon=True)
     proc.start()
     for m in msgs:
         ring.send(m)
@@ -178,7 +178,7 @@ def test_local_shared_front_end_two_processes():
     limit = 60
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_local_worker, args=(lr, sparse, batch, limit, q)) for lr in range(2)]
+    procs = [ctx.Process(target=_local_worker, args=(lr, sparse, batch, limit, q), daemon=True) for lr in range(2)]
     for p in procs:
         p.start()
     results = dict(q.get(timeout=120) for _ in procs)
