@@ -173,9 +173,11 @@ struct ZeroList {
 };
 __global__ void __launch_bounds__(256) op_begin_kernel(CacheRegs *r, u64 *clk, int flush, ZeroList z) {
     pdl_enter();
-    for (int k = 0; k < z.n; k++)
-        for (u32 w = threadIdx.x; w < z.r[k].words; w += blockDim.x)
-            z.r[k].p[w] = 0;
+#pragma unroll
+    for (int k = 0; k < 6; k++) // (unrolled: a run-time index into the parameter array would go through local memory)
+        if (k < z.n)
+            for (u32 w = threadIdx.x; w < z.r[k].words; w += blockDim.x)
+                z.r[k].p[w] = 0;
     if (threadIdx.x != 0)
         return;
     r->clock0 = r->clock;
