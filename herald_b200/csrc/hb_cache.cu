@@ -459,6 +459,130 @@ __global__ void __launch_bounds__(kRowBlock)
         atomicAdd(&c.regs->pulled_remote, *cnt_remote);
 }
 
+// The sync with the stale rows fetched by BULK asynchronous copies (cp.async.bulk, the 1-D TMA path):
+// one elected lane issues one copy per row — 512 bytes (D = 128) or 2 KB (D = 512) per instruction —
+// into a per-warp shared-memory stage and the copies complete on an mbarrier (complete_tx); the warp
+// then moves the stage into the cache rows.  A bulk copy holds no register while it is in flight and is
+// one fabric-level request stream per row instead of 32 lanes' 16-byte loads, which is what the pull
+// over NVLink wants.  Rows of 16-byte multiples only.
+template <int DUMMY>
+__global__ void __launch_bounds__(kRowBlock)
+    sync_bulk_kernel(CacheView c, const u64 *__restrict__ uniq, const i32 *__restrict__ uslot,
+                     i64 pull_bound, u64 applied_epoch, int kBulkRows /* rows per round and warp */) {
+    pdl_enter();
+    if (c.pv.world > 1)
+        wait_flags(c, c.pv.ctrl + kMaxWorld, applied_epoch);
+    extern __shared__ __align__(128) float s_stage[]; // [kRowWarps][kBulkRows][D], then kRowWarps mbarriers
+    using V = RowVec<4>;
+    const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
+    const size_t warp_global = (size_t)blockIdx.x * kRowWarps + warp;
+    const size_t nwarps = (size_t)gridDim.x * kRowWarps;
+    const size_t D = c.width, nvec = D / 4;
+    const unsigned row_bytes = (unsigned)(D * sizeof(float));
+    const u32 U = c.regs->U;
+    float *stage = s_stage + (size_t)warp * kBulkRows * D;
+    u64 *bar = reinterpret_cast<u64 *>(s_stage + (size_t)kRowWarps * kBulkRows * D) + warp;
+    const unsigned bar_a = (unsigned)__cvta_generic_to_shared(bar);
+    if (lane == 0)
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a) : "memory");
+    u32 *cnt = block_counter(), *cnt_remote = block_counter2();
+    if (threadIdx.x == 0)
+        *cnt = *cnt_remote = 0;
+    __syncthreads(); // (also publishes the mbarrier inits)
+    unsigned phase = 0;
+    u32 pulled = 0, pulled_remote = 0;
+    for (size_t base = warp_global * 32; base < U; base += nwarps * 32) {
+        const size_t i = base + lane;
+        i32 s = -1;
+        u64 trow = 0;
+        bool need = false, addup = false, live_grad = false;
+        int owner = 0;
+        if (i < U) {
+            s = uslot[i];
+            bool have;
+            if (c.pv.world > 1) {
+                owner = owner_of(c.pv, uniq[i], trow);
+                have = uniq[i] < c.table_len;
+            } else {
+                trow = uniq[i] - c.row_begin;
+                have = trow < c.nrows_local;
+            }
+            if (s >= 0 && have) {
+                const i64 v = c.slot_version[s];
+                const i64 srv = __ldg(&c.pv.ver[owner][trow]);
+                need = v == -1 || srv - v > pull_bound;
+                if (need) {
+                    addup = c.slot_flags[s] & F_GRAD; // Line::addup (embedding.h:92-96)
+                    live_grad = addup && c.slot_updates[s] != 0;
+                    c.slot_version[s] = srv;
+                }
+            }
+        }
+        unsigned m = __ballot_sync(FULL, need);
+        pulled += __popc(m);
+        pulled_remote += __popc(__ballot_sync(FULL, need && owner != c.pv.rank));
+        while (m) {
+            const int nr = min(__popc(m), kBulkRows);
+            if (lane == 0)
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a),
+                             "r"(row_bytes * (unsigned)nr)
+                             : "memory");
+            unsigned round = 0;
+            for (int r = 0; r < nr; r++) {
+                const int from = __ffs(m) - 1;
+                m &= m - 1;
+                round |= 1u << from;
+                const u64 rt = __shfl_sync(FULL, trow, from);
+                const float *src = c.pv.rows[__shfl_sync(FULL, owner, from)] + rt * D;
+                if (lane == 0) {
+                    const unsigned d = (unsigned)__cvta_generic_to_shared(stage + (size_t)r * D);
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(d),
+                                 "l"(src), "r"(row_bytes), "r"(bar_a)
+                                 : "memory");
+                }
+            }
+            {   // every lane waits for the round's bytes
+                unsigned done = 0;
+                while (!done)
+                    asm volatile("{\n\t.reg .pred p;\n\t"
+                                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                                 "selp.u32 %0, 1, 0, p;\n\t}"
+                                 : "=r"(done)
+                                 : "r"(bar_a), "r"(phase)
+                                 : "memory");
+                phase ^= 1u;
+            }
+            int r = 0;
+            while (round) {
+                const int from = __ffs(round) - 1;
+                round &= round - 1;
+                const i32 rs = __shfl_sync(FULL, s, from);
+                const bool ra = __shfl_sync(FULL, addup, from), rg = __shfl_sync(FULL, live_grad, from);
+                const float *row = stage + (size_t)r * D;
+                for (size_t k = lane; k < nvec; k += 32) {
+                    float4 x = *reinterpret_cast<const float4 *>(row + k * 4);
+                    if (ra) {
+                        const float4 g = rg ? V::ld(c.grad + (size_t)rs * D + k * 4) : V::zero();
+                        x = V::add(x, g);
+                    }
+                    V::st(c.data + (size_t)rs * D + k * 4, x);
+                }
+                r++;
+            }
+            __syncwarp(); // the stage is free again (generic-proxy reads done before the next async writes)
+        }
+    }
+    if (lane == 0 && pulled)
+        atomicAdd(cnt, pulled);
+    if (lane == 0 && pulled_remote)
+        atomicAdd(cnt_remote, pulled_remote);
+    __syncthreads();
+    if (threadIdx.x == 0 && *cnt)
+        atomicAdd(&c.regs->pulled, *cnt);
+    if (threadIdx.x == 0 && *cnt_remote)
+        atomicAdd(&c.regs->pulled_remote, *cnt_remote);
+}
+
 struct IndexFromSlots {
     const i32 *uslot;
     const u32 *inverse;
@@ -2290,7 +2414,30 @@ void run_sync(hb_cache *c, size_t n, int wsi) {
     if (!n)
         return;
     int grid = row_grid((n + 31) / 32);
-    if (c->width % 4 == 0)
+    // bulk-copy variant (default for rows of 16-byte multiples): $HERALD_SYNC_BULK = 0 selects the
+    // register-staged kernel
+    static const int force_bulk = [] {
+        const char *e = getenv("HERALD_SYNC_BULK");
+        return e ? atoi(e) : -1;
+    }();
+    static const int bulk_rows_env = [] {
+        const char *e = getenv("HERALD_BULK_ROWS");
+        return e ? std::max(1, std::min(32, atoi(e))) : 8;
+    }();
+    // rows per round: as configured, but a CTA's stage stays within 64 KB (D = 512: 4 rows)
+    const int bulk_rows = (int)std::max<size_t>(1, std::min<size_t>(bulk_rows_env, (64 * 1024) / (kRowWarps * c->width * sizeof(float))));
+    const size_t bulk_smem = (size_t)kRowWarps * bulk_rows * c->width * sizeof(float) + kRowWarps * 8;
+    const bool use_bulk = (force_bulk >= 0 ? force_bulk != 0 : true) && c->width % 4 == 0 &&
+                          c->width * sizeof(float) <= 8192;
+    if (use_bulk) {
+        static size_t attr_smem = 0;
+        if (bulk_smem > attr_smem) {
+            HB_CUDA(cudaFuncSetAttribute(sync_bulk_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bulk_smem));
+            attr_smem = bulk_smem;
+        }
+        HB_LAUNCH(sync_bulk_kernel<0>, grid, kRowBlock, bulk_smem, c->stream, c->view, c->ws[wsi].uniq, c->uslot[0],
+                  c->pull_bound, (u64)c->xepoch, bulk_rows);
+    } else if (c->width % 4 == 0)
         HB_LAUNCH((sync_kernel<4, 4>), grid, kRowBlock, 0, c->stream, c->view, c->ws[wsi].uniq, c->uslot[0],
                                                              c->pull_bound, (u64)c->xepoch);
     else
