@@ -2451,7 +2451,24 @@ void run_gather(hb_cache *c, size_t n, int wsi, float *dev_dest) {
         return;
     IndexFromSlots idx{c->uslot[0], c->ws[wsi].inverse};
     int grid = row_grid((n + 3) / 4);
-    if (vec4(c, dev_dest))
+    // bulk-copy (TMA) variant for wide rows: measured at D = 512 (2 KB rows) 183 -> 136 us, at D = 128
+    // (512 B rows) 52 -> 53 us; $HERALD_GATHER_BULK = 0 / 1 forces either
+    static const int force_gather_bulk = [] {
+        const char *e = getenv("HERALD_GATHER_BULK");
+        return e ? atoi(e) : -1;
+    }();
+    const bool gather_bulk = force_gather_bulk >= 0 ? force_gather_bulk != 0 : c->width * sizeof(float) >= 1024;
+    if (gather_bulk && vec4(c, dev_dest) && c->width * sizeof(float) <= 4096) {
+        const int R = (int)std::max<size_t>(1, std::min<size_t>(8, 4096 / (c->width * sizeof(float))));
+        const size_t smem = (size_t)kRowWarps * 2 * R * c->width * sizeof(float) + kRowWarps * 2 * 8;
+        static size_t attr_smem = 0;
+        if (smem > attr_smem) {
+            HB_CUDA(cudaFuncSetAttribute(gather_bulk_kernel<IndexFromSlots>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attr_smem = smem;
+        }
+        grid = std::min(row_grid((n + 31) / 32), sm_count() * 3);
+        HB_LAUNCH(gather_bulk_kernel<IndexFromSlots>, grid, kRowBlock, smem, c->stream, c->view.data, dev_dest, n, c->width, idx, R);
+    } else if (vec4(c, dev_dest))
         HB_LAUNCH((gather_rows_kernel<4, 4, IndexFromSlots>), grid, kRowBlock, 0, c->stream, c->view.data, dev_dest, n, c->width, idx);
     else
         HB_LAUNCH((gather_rows_kernel<1, 4, IndexFromSlots>), grid, kRowBlock, 0, c->stream, c->view.data, dev_dest, n, c->width, idx);

@@ -129,6 +129,86 @@ __global__ void __launch_bounds__(kRowBlock)
     }
 }
 
+__device__ __forceinline__ unsigned smem_u32(const void *p) {
+    return (unsigned)__cvta_generic_to_shared(p);
+}
+
+// ---- gather through the bulk-copy engine (1-D TMA) --------------------------------------------
+// dst[n,:] = src[index(n),:] with no register staging: a lane issues ONE bulk load of its source
+// row into the warp's shared-memory stage (cp.async.bulk global -> shared, completion on an
+// mbarrier) and, once the round's bytes have landed, ONE bulk store of the stage row to its
+// destination (cp.async.bulk shared -> global, bulk-group completion).  Two stages per warp: the
+// loads of round k + 1 are in flight while the stores of round k drain.  Rows must be multiples of
+// 16 bytes at 16-byte aligned addresses; a negative index writes zeros with plain stores.
+template <class Index>
+__global__ void __launch_bounds__(kRowBlock)
+    gather_bulk_kernel(const float *__restrict__ src, float *__restrict__ dst, size_t n, size_t D, Index index,
+                       int rows_per_round) {
+    pdl_enter();
+    extern __shared__ __align__(128) float s_gstage[]; // [kRowWarps][2][R][D], then kRowWarps x 2 mbarriers
+    const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
+    const int R = rows_per_round;
+    const unsigned row_bytes = (unsigned)(D * sizeof(float));
+    float *stage0 = s_gstage + (size_t)warp * 2 * R * D;
+    u64 *bars = reinterpret_cast<u64 *>(s_gstage + (size_t)kRowWarps * 2 * R * D) + warp * 2;
+    if (lane < 2)
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bars + lane)) : "memory");
+    __syncthreads();
+    unsigned phase[2] = {0u, 0u};
+    const size_t warp_global = (size_t)blockIdx.x * kRowWarps + warp;
+    const size_t nwarps = (size_t)gridDim.x * kRowWarps;
+    int st = 0; // stage of the next round
+    for (size_t base = warp_global * 32; base < n; base += nwarps * 32) {
+        const long long mine = base + lane < n ? index(base + lane) : -1;
+        const int rows_here = (int)min((size_t)32, n - base);
+        for (int r0 = 0; r0 < rows_here; r0 += R) {
+            const int nr = min(R, rows_here - r0);
+            float *stage = stage0 + (size_t)st * R * D;
+            const unsigned bar_a = smem_u32(bars + st);
+            // the stage's previous stores (two rounds ago) must have finished READING it
+            asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            __syncwarp();
+            const bool in_round = (int)lane >= r0 && (int)lane < r0 + nr;
+            const unsigned valid = __ballot_sync(FULL, in_round && mine >= 0);
+            if (lane == 0 && valid)
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a),
+                             "r"(row_bytes * (unsigned)__popc(valid))
+                             : "memory");
+            __syncwarp();
+            if (in_round && mine >= 0)
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                 smem_u32(stage + (size_t)(lane - r0) * D)),
+                             "l"(src + (size_t)mine * D), "r"(row_bytes), "r"(bar_a)
+                             : "memory");
+            if (valid) {
+                unsigned done = 0;
+                while (!done)
+                    asm volatile("{\n\t.reg .pred p;\n\t"
+                                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                                 "selp.u32 %0, 1, 0, p;\n\t}"
+                                 : "=r"(done)
+                                 : "r"(bar_a), "r"(phase[st])
+                                 : "memory");
+                phase[st] ^= 1u;
+            }
+            if (in_round) {
+                float *drow = dst + (base + lane) * D;
+                if (mine >= 0) {
+                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(drow),
+                                 "r"(smem_u32(stage + (size_t)(lane - r0) * D)), "r"(row_bytes)
+                                 : "memory");
+                } else {
+                    for (size_t k = 0; k < D; k += 4)
+                        *reinterpret_cast<float4 *>(drow + k) = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            st ^= 1;
+        }
+    }
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); // the stores must be complete before the grid ends
+}
+
 // ---- segment reduce by unique key, applied to a destination row -----------------------
 // Functor contract (instantiated for the cold path's vector width VEC and, as F1, for VEC = 1):
 //   bool open(u, cnt, Ctx &)   ONCE per unique key, by one thread of the plan kernel: reads (and
@@ -362,9 +442,6 @@ __device__ __forceinline__ void cp_async_16(float *smem_dst, const float *gsrc) 
 }
 
 // ---- mbarrier (shared::cta) -------------------------------------------------------------------
-__device__ __forceinline__ unsigned smem_u32(const void *p) {
-    return (unsigned)__cvta_generic_to_shared(p);
-}
 __device__ __forceinline__ void mbar_init(u64 *bar, unsigned count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
