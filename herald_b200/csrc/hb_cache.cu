@@ -140,7 +140,7 @@ __device__ __forceinline__ void wait_flags(const CacheView &c, const u64 *flags,
             if (seen >= epoch)
                 break;
             if ((++spins & 1023u) == 0 && global_timer_ns() - t0 > c.pv.timeout_ns) {
-                atomicMax(&c.regs->error, (u32)E_BARRIER);
+                atomicMax(&c.regs->xerror, (u32)E_BARRIER); // (reported by the next epilogue: op_end_body)
                 break;
             }
         }
@@ -222,7 +222,9 @@ __device__ __forceinline__ void op_end_body(const CacheView &c, const u64 *clk, 
     }
     rec->num_remote = kind == 0 ? r->pulled_remote : r->pushed_remote;
     rec->size = r->size;
-    rec->error = r->error;
+    // failures of the exchange kernels (they run on their own stream, outside any call's begin / end
+    // bracket) are reported by the first epilogue that sees them
+    rec->error = max(r->error, atomicExch(&r->xerror, 0u));
     rec->ht_occupied = r->ht_occupied;
     rec->pending = r->pending;
     rec->limit_full = r->size == c.limit;
@@ -1627,7 +1629,7 @@ __global__ void __launch_bounds__(kRowBlock) apply_linked_kernel(CacheView c, u6
             while (e1 != 0) {
                 const u32 e = e1 - 1;
                 if (n == (u32)kMaxChain) { // absurdly long chain: reported, the excess is not applied
-                    atomicMax(&c.regs->error, (u32)E_MAILBOX);
+                    atomicMax(&c.regs->xerror, (u32)E_MAILBOX);
                     break;
                 }
                 u32 j = n;
@@ -2134,6 +2136,8 @@ u64 *clk_of(hb_cache *c) {
 }
 
 void sync_all(hb_cache *c) {
+    if (c->xstream)
+        HB_CUDA(cudaStreamSynchronize(c->xstream));
     HB_CUDA(cudaStreamSynchronize(c->side));
     HB_CUDA(cudaStreamSynchronize(c->side2));
     HB_CUDA(cudaStreamSynchronize(c->h2d));
@@ -2374,6 +2378,12 @@ void release_ws_at_end(hb_cache *c, int wsi) {
 
 void end_call(hb_cache *c, int last_stage, u32 kind, size_t n, bool inserted, bool epilogue_done = false) {
     int idx = (int)(c->calls % hb_cache::kRing);
+    if (c->x_pending == 2) { // the exchange forked by the PREVIOUS call: long finished, joined for the record
+        HB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_x_done, 0));
+        c->x_pending = 0;
+    } else if (c->x_pending == 1) {
+        c->x_pending = 2;
+    }
     // the record goes straight into the host's ring (mapped pinned memory): no copy node
     if (!epilogue_done) { // (a single-GPU update's tail kernel has already written it)
         HB_LAUNCH(op_end_kernel, 1, 1, 0, c->stream, c->view, clk_of(c), last_stage, c->ring_dev + idx, kind,
@@ -2537,8 +2547,15 @@ void run_insert(hb_cache *c, size_t n, int clk_stage, cudaStream_t st) {
 // last CTA raises `applied` at every peer).  The next kernel that touches peer memory — the sync
 // of the following lookup, or the next update's owner_bounds — waits for `applied`, so the skew
 // between the ranks is absorbed by whatever runs in between.  Nothing synchronises with the host.
+// The three launches run on their own stream (`xstream`), forked after the kernels that filled the
+// mailboxes: nothing on the main stream reads what they write before it has seen the `applied` flags
+// (device side), so the update's tail and the next lookup's resolve proceed next to the apply; the
+// main stream joins it at the end of the NEXT call (by then the sync kernel has long waited for it),
+// which keeps every exchange inside the main stream's timeline one call later.
 void exchange_pushes(hb_cache *c) {
-    cudaStream_t st = c->stream;
+    HB_CUDA(cudaEventRecord(c->ev_x_fork, c->stream));
+    HB_CUDA(cudaStreamWaitEvent(c->xstream, c->ev_x_fork, 0));
+    cudaStream_t st = c->xstream;
     const int world = c->view.pv.world;
     const u64 epoch = ++c->xepoch;
     HB_LAUNCH(exchange_arrive_kernel, 1, 32, 0, st, c->view, epoch);
@@ -2548,6 +2565,8 @@ void exchange_pushes(hb_cache *c) {
     HB_LAUNCH(link_mailbox_kernel, dim3(lgrid, 2 * world), 256, 0, st, c->view, epoch);
     HB_LAUNCHED();
     const size_t groups = (per_list + 31) / 32;
+    // full width: the apply is on the critical path of the next lookup's sync (it waits for the
+    // `applied` flags); a small low-priority grid that "leaves room" was measured: 0.352 -> 0.418 ms
     const int agrid = (int)std::max<size_t>(1, std::min<size_t>((groups + kRowWarps - 1) / kRowWarps,
                                                                (size_t)sm_count() * 8 / (2 * world) + 1));
     if (c->width % 4 == 0)
@@ -2555,6 +2574,8 @@ void exchange_pushes(hb_cache *c) {
     else
         HB_LAUNCH((apply_linked_kernel<1, 4>), dim3(agrid, 2 * world), kRowBlock, 0, st, c->view, epoch);
     HB_LAUNCHED();
+    HB_CUDA(cudaEventRecord(c->ev_x_done, st));
+    c->x_pending = 1; // joined by the main stream at the end of the next call (end_call)
 }
 
 // accumulate + push of batch `batch`, then flush of pending victims, then drop dataless lines
@@ -2893,11 +2914,13 @@ int hb_cache_create(int policy, size_t limit, size_t length, size_t width, int n
     HB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     HB_CUDA(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
     HB_CUDA(cudaStreamCreateWithFlags(&c->side2, cudaStreamNonBlocking));
+    HB_CUDA(cudaStreamCreateWithFlags(&c->xstream, cudaStreamNonBlocking));
     HB_CUDA(cudaStreamCreateWithFlags(&c->h2d, cudaStreamNonBlocking));
     HB_CUDA(cudaStreamCreateWithFlags(&c->d2h, cudaStreamNonBlocking));
     for (cudaEvent_t *e : {&c->ev_ws_rel[0], &c->ev_ws_rel[1], &c->ev_sorted[0], &c->ev_sorted[1],
                            &c->ev_up, &c->ev_grads_free, &c->ev_gathered[0], &c->ev_gathered[1],
-                           &c->ev_dl[0], &c->ev_dl[1], &c->ev_producer, &c->ev_fork, &c->ev_join})
+                           &c->ev_dl[0], &c->ev_dl[1], &c->ev_producer, &c->ev_fork, &c->ev_join,
+                           &c->ev_x_fork, &c->ev_x_done})
         HB_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
     // row store: limit resident lines + slack for the running call's fresh lines and for dirty
     // victims waiting for the next push
@@ -3067,11 +3090,13 @@ int hb_cache_destroy(hb_cache *c) {
             cudaEventDestroy(e);
         for (cudaEvent_t e : {c->ev_ws_rel[0], c->ev_ws_rel[1], c->ev_sorted[0], c->ev_sorted[1],
                               c->ev_up, c->ev_grads_free, c->ev_gathered[0], c->ev_gathered[1],
-                              c->ev_dl[0], c->ev_dl[1], c->ev_producer, c->ev_fork, c->ev_join})
+                              c->ev_dl[0], c->ev_dl[1], c->ev_producer, c->ev_fork, c->ev_join,
+                              c->ev_x_fork, c->ev_x_done})
             cudaEventDestroy(e);
         cudaStreamDestroy(c->stream);
         cudaStreamDestroy(c->side);
         cudaStreamDestroy(c->side2);
+        cudaStreamDestroy(c->xstream);
         cudaStreamDestroy(c->h2d);
         cudaStreamDestroy(c->d2h);
         delete c;
@@ -3306,7 +3331,7 @@ int hb_cache_flush(hb_cache *c) {
     const int world = c->view.pv.world, rank = c->view.pv.rank;
     for (int turn = 0; turn < world; turn++) {
         if (world > 1) {
-            HB_CUDA(cudaStreamSynchronize(c->stream));
+            sync_all(c); // (the exchange stream too: the resident flush writes owner rows in place)
             HB_CHECK(hb_comm_barrier() == 0, "barrier failed");
         }
         if (turn != rank)
@@ -3459,6 +3484,7 @@ int hb_cache_wait(hb_cache *c, hb_perf *perf) {
     Guard g(c->device);
     HB_CUDA(cudaStreamSynchronize(c->stream));
     HB_CUDA(cudaStreamSynchronize(c->d2h));
+    HB_CUDA(cudaStreamSynchronize(c->xstream));
     if (c->calls) {
         int idx = (int)((c->calls - 1) % hb_cache::kRing);
         const PerfRecord &r = c->ring[idx];

@@ -176,6 +176,7 @@ struct CacheRegs {
     // multi-GPU traffic of the call (zeroed by op_begin): rows pulled from / lines pushed to a PEER
     u32 pulled_remote, pushed_remote;
     u32 tail_done; // CTAs of update_tail_kernel that have finished (zeroed by op_begin)
+    u32 xerror;    // failure raised by an exchange kernel; moved into the next call record
 };
 
 // Everything a kernel needs to address the cache (passed by value).
@@ -257,6 +258,9 @@ struct hb_cache {
     // previous call; `h2d` / `d2h` move host callers' gradients in and gathered rows out, so that
     // an upload, a download and the kernels of a third call can overlap (PCIe is full duplex).
     cudaStream_t stream = nullptr, side = nullptr, h2d = nullptr, d2h = nullptr;
+    cudaStream_t xstream = nullptr;             // multi-GPU: arrive / link / apply of an update's exchange
+    cudaEvent_t ev_x_fork = nullptr, ev_x_done = nullptr;
+    int x_pending = 0;                          // 1: forked by the running call, 2: by the previous one
     cudaStream_t side2 = nullptr;               // a lookup's insert phase, next to its sync + gather
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     int cur = 0;                                // workspace that holds the most recent lookup batch
