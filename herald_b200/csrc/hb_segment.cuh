@@ -89,15 +89,11 @@ void run_segment_reduce(KeyWorkspace &ws, const u32 *perm, const float *vals, si
     }
     if (after_plan)
         after_plan(); // (timing mark between the plan kernel and the data kernel)
-    const bool r4 = seg_rows() == 4;
-    if (v4 && r4)
+    // (four rows in flight per warp in the cold phase; the two-row variants were tuning aids)
+    if (v4)
         launch_segment_reduce<4, 4>(ws, perm, vals, D, n, hot, thr, hl, st, f4, f1);
-    else if (v4)
-        launch_segment_reduce<4, 2>(ws, perm, vals, D, n, hot, thr, hl, st, f4, f1);
-    else if (r4)
-        launch_segment_reduce<1, 4>(ws, perm, vals, D, n, hot, thr, hl, st, f1, f1);
     else
-        launch_segment_reduce<1, 2>(ws, perm, vals, D, n, hot, thr, hl, st, f1, f1);
+        launch_segment_reduce<1, 4>(ws, perm, vals, D, n, hot, thr, hl, st, f1, f1);
 }
 
 } // namespace hb
