@@ -244,11 +244,30 @@ __global__ void op_end_kernel(CacheView c, const u64 *clk, int last_stage, PerfR
 // batch 0 writes U/M/alloc_base, batch 1 (push side of push_pull) writes U2/M2/alloc_base2.
 constexpr int kResolveItems = 1; // measured: 4 per thread is slower (the probes of one thread serialise: 16 -> 19 us)
 
+// Plan: what an update adds to the resolve of its batch — the segment-reduce work item of every
+// unique (seg_plan_item: push decision, versions, mailbox header, hot lists), written by the thread
+// that has just resolved that unique and still holds its slot: one kernel and one pass over the
+// per-unique scalars less than a separate plan kernel.  NoSegPlan for lookups.
+struct NoSegPlan {
+    static constexpr bool enabled = false;
+};
+template <class F>
+struct SegPlanArgs {
+    static constexpr bool enabled = true;
+    const u32 *seg_start, *perm;
+    u32 thr;
+    HotLists hl;
+    F f;
+};
+
+template <class Plan>
 __global__ void __launch_bounds__(kScanBlock)
     resolve_kernel(CacheView c, const u64 *uniq, const u32 *num_unique, i32 *uslot, u32 *miss_list,
                    int bypass, ScanState st, u32 ntiles, const u64 *clk_in, u64 *clk_out, int batch,
-                   int dataless) {
+                   int dataless, Plan plan) {
     pdl_enter();
+    if constexpr (Plan::enabled)
+        plan.f.kernel_begin();
     const u32 tile = take_ticket(st.ticket);
     const u32 U = *num_unique;
     const u64 base = *clk_in;
@@ -347,6 +366,17 @@ __global__ void __launch_bounds__(kScanBlock)
             r->M2 = M;
         }
         *clk_out = base + U;
+    }
+    if constexpr (Plan::enabled) {
+        static_assert(kResolveItems == 1, "one unique per thread");
+        // ticket order: item i = t * TK + l holds unique u = t + l * T (hb_rows.cuh); this thread owns
+        // u = i0, or one of the padding items behind the last unique
+        const u32 TK = plan.hl.ticket_rows;
+        const u32 T = (U + TK - 1) / TK, total = T * TK;
+        const u32 u = i0;
+        const u32 i = (T && u < total) ? (u % T) * TK + u / T : total;
+        seg_plan_item(i, u, U, total, plan.seg_start, plan.perm, plan.thr, plan.hl, plan.f);
+        plan.f.kernel_end();
     }
 }
 
@@ -2407,21 +2437,28 @@ void end_call(hb_cache *c, int last_stage, u32 kind, size_t n, bool inserted, bo
 }
 
 // resolve (+ alloc) of the batch workspace `wsi` holds; `batch` = which counter set of the call
-void resolve_batch(hb_cache *c, size_t n, int batch, int wsi, bool dataless, int clk_stage,
-                   bool marks = true) {
+template <class Plan>
+void resolve_batch(hb_cache *c, size_t n, int batch, int wsi, bool dataless, int clk_stage, bool marks,
+                   Plan plan) {
     KeyWorkspace &ws = c->ws[wsi];
     cudaStream_t st = c->stream;
     if (marks)
         mark(c, 0);
-    u32 ntiles = (u32)std::max(1, ceil_div(n, kScanBlock * kResolveItems));
+    // (a planning resolve also writes the padding items behind the last unique: up to ticket_rows more)
+    const size_t cover = Plan::enabled ? n + ticket_rows() : n;
+    u32 ntiles = (u32)std::max(1, ceil_div(cover, kScanBlock * kResolveItems));
     u64 *clk = clk_of(c);
-    HB_LAUNCH(resolve_kernel, ntiles, kScanBlock, 0, st, c->view, ws.uniq, ws.num_unique, c->uslot[batch],
+    HB_LAUNCH(resolve_kernel<Plan>, ntiles, kScanBlock, 0, st, c->view, ws.uniq, ws.num_unique, c->uslot[batch],
                                                   c->miss_list[batch], c->bypass ? 1 : 0,
                                                   ws.next_scan(), ntiles, clk + clk_stage,
-                                                  clk + clk_stage + 1, batch, dataless ? 1 : 0);
+                                                  clk + clk_stage + 1, batch, dataless ? 1 : 0, plan);
     HB_LAUNCHED();
     if (marks)
         mark(c, 1);
+}
+void resolve_batch(hb_cache *c, size_t n, int batch, int wsi, bool dataless, int clk_stage,
+                   bool marks = true) {
+    resolve_batch(c, n, batch, wsi, dataless, clk_stage, marks, NoSegPlan{});
 }
 
 bool vec4(const hb_cache *c, const void *user_rows) {
@@ -2587,34 +2624,48 @@ void exchange_pushes(hb_cache *c) {
 }
 
 // accumulate + push of batch `batch`, then flush of pending victims, then drop dataless lines
-void run_accumulate(hb_cache *c, size_t n, int batch, int wsi, const float *dev_grads,
-                    const u64 *dev_push_keys, size_t n_push, bool use_plan, bool defer_cleanup = false,
-                    bool fuse_tail = false) {
-    cudaStream_t st = c->stream;
+// the accumulate functor of one update (any of its compile-time variants: same fields)
+template <int VEC, bool SC, bool SP>
+AccumulatePush<VEC, SC, SP> make_accumulate(hb_cache *c, int batch, int wsi, const u64 *dev_push_keys, size_t n_push,
+                                            bool use_plan, bool defer_cleanup) {
     KeyWorkspace &ws = c->ws[wsi];
+    const u64 *plan = use_plan ? dev_push_keys : nullptr;
+    u32 plan_n = (u32)n_push;
+    if (use_plan && !dev_push_keys) { // empty plan: nothing is pushed
+        plan = ws.uniq;
+        plan_n = 0;
+    }
+    return AccumulatePush<VEC, SC, SP>{c->view, ws.uniq, c->uslot[batch], c->push_bound, plan, plan_n,
+                                       defer_cleanup, c->grad_scale};
+}
+
+void run_owner_bounds(hb_cache *c, int wsi) {
     if (c->view.pv.world > 1) {
-        HB_LAUNCH(owner_bounds_kernel, 1, 32, 0, st, c->view, ws.uniq, ws.num_unique, (u64)c->xepoch);
+        KeyWorkspace &ws = c->ws[wsi];
+        HB_LAUNCH(owner_bounds_kernel, 1, 32, 0, c->stream, c->view, ws.uniq, ws.num_unique, (u64)c->xepoch);
         HB_LAUNCHED();
     }
+}
+
+// pre: the batch's work items were planned inside its resolve (do_update) with this setup
+void run_accumulate(hb_cache *c, size_t n, int batch, int wsi, const float *dev_grads,
+                    const u64 *dev_push_keys, size_t n_push, bool use_plan, bool defer_cleanup = false,
+                    bool fuse_tail = false, const SegSetup *pre = nullptr) {
+    cudaStream_t st = c->stream;
+    KeyWorkspace &ws = c->ws[wsi];
+    if (!pre)
+        run_owner_bounds(c, wsi);
     if (n) {
         const u32 *p = c->sorted[wsi].perm;
-        const u64 *plan = use_plan ? dev_push_keys : nullptr;
-        u32 plan_n = (u32)n_push;
-        if (use_plan && !dev_push_keys) { // empty plan: nothing is pushed
-            plan = ws.uniq;
-            plan_n = 0;
-        }
         auto go = [&](auto scaled, auto split) {
             constexpr bool SC = decltype(scaled)::value, SP = decltype(split)::value;
-            AccumulatePush<1, SC, SP> f1{c->view, ws.uniq, c->uslot[batch], c->push_bound, plan, plan_n,
-                                         defer_cleanup, c->grad_scale};
-            AccumulatePush<4, SC, SP> f4{c->view, ws.uniq, c->uslot[batch], c->push_bound, plan, plan_n,
-                                         defer_cleanup, c->grad_scale};
+            auto f1 = make_accumulate<1, SC, SP>(c, batch, wsi, dev_push_keys, n_push, use_plan, defer_cleanup);
+            auto f4 = make_accumulate<4, SC, SP>(c, batch, wsi, dev_push_keys, n_push, use_plan, defer_cleanup);
             run_segment_reduce(ws, p, dev_grads, c->width, n, vec4(c, dev_grads), c->hot_threshold, st,
                                f1, f4, [&] {
                                    if (batch == 0)
                                        mark(c, 3);
-                               }, SP);
+                               }, SP, pre);
         };
         const bool scaled = c->grad_scale != 1.0f; // x * 1.0f == x: the unscaled kernel is exact for it
         if (scaled && c->reduce_split)
@@ -2724,9 +2775,20 @@ void do_update(hb_cache *c, const void *keys, int kind, size_t n, const float *g
     const float *dgrads = stage_grads(c, grads, n);
     const u64 *dpush = use_plan ? stage_push_keys(c, push_keys, push_kind, n_push) : nullptr;
     begin_call(c, /*flush=*/true, n, w);
-    resolve_batch(c, n, 0, w, /*dataless=*/true, 0);
     const bool fuse_tail = c->view.pv.world == 1;
-    run_accumulate(c, n, 0, w, dgrads, dpush, n_push, use_plan, false, fuse_tail);
+    if (n) {
+        // the work items of the segment reduce are planned inside the resolve (multi-GPU: the owner
+        // ranges of the sorted uniques first, the plan writes mailbox headers)
+        run_owner_bounds(c, w);
+        const SegSetup su = seg_setup(c->ws[w], c->width, n, c->hot_threshold, c->reduce_split, c->stream);
+        SegPlanArgs<AccumulatePush<4>> plan{c->ws[w].seg_start, c->sorted[w].perm, su.thr, su.hl,
+                                            make_accumulate<4, false, false>(c, 0, w, dpush, n_push, use_plan, false)};
+        resolve_batch(c, n, 0, w, /*dataless=*/true, 0, true, plan);
+        run_accumulate(c, n, 0, w, dgrads, dpush, n_push, use_plan, false, fuse_tail, &su);
+    } else {
+        resolve_batch(c, n, 0, w, /*dataless=*/true, 0);
+        run_accumulate(c, n, 0, w, dgrads, dpush, n_push, use_plan, false, fuse_tail);
+    }
     end_call(c, 1, 1, n, false, fuse_tail);
     release_ws_at_end(c, w);
     if (dgrads != grads)
@@ -3754,9 +3816,9 @@ int hb_cache_touch(hb_cache *c, uint64_t key, int *found, int64_t *version, floa
     HB_LAUNCH(single_key_kernel, 1, 1, 0, st, ws.uniq, ws.num_unique, key);
     HB_LAUNCHED();
     u64 *clk = clk_of(c);
-    HB_LAUNCH(resolve_kernel, 1, kScanBlock, 0, st, c->view, ws.uniq, ws.num_unique, c->uslot[0],
+    HB_LAUNCH(resolve_kernel<NoSegPlan>, 1, kScanBlock, 0, st, c->view, ws.uniq, ws.num_unique, c->uslot[0],
                                              c->miss_list[0], c->bypass ? 1 : 0, ws.next_scan(), 1,
-                                             clk, clk + 1, 0, 0);
+                                             clk, clk + 1, 0, 0, NoSegPlan{});
     HB_LAUNCHED();
     // a miss reserved a slot for a fresh line; materialise and hand it back (lookup() alone
     // allocates nothing)
@@ -3801,8 +3863,8 @@ int hb_cache_insert(hb_cache *c, uint64_t key, int64_t version, const float *dat
         HB_LAUNCHED();
         u64 *clk = clk_of(c);
         // bypass=1: resolve as a miss without touching anything, which allocates the fresh line
-        HB_LAUNCH(resolve_kernel, 1, kScanBlock, 0, st, c->view, ws.uniq, ws.num_unique, c->uslot[0],
-                                                 c->miss_list[0], 1, ws.next_scan(), 1, clk, clk, 0, 0);
+        HB_LAUNCH(resolve_kernel<NoSegPlan>, 1, kScanBlock, 0, st, c->view, ws.uniq, ws.num_unique, c->uslot[0],
+                                                 c->miss_list[0], 1, ws.next_scan(), 1, clk, clk, 0, 0, NoSegPlan{});
         HB_LAUNCHED();
         i32 *dslot = nullptr, hslot = -1;
         dmalloc(dslot, 1);

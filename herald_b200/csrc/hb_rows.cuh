@@ -381,53 +381,63 @@ __device__ __forceinline__ u32 rows_warp_append(u32 *counter, bool pred) {
     return base + __popc(m & lanemask_lt());
 }
 
+// The work item of unique `u` at position `i` of the ticket order (a padding item when u >= U or
+// i >= total).  Warp-collective: every lane of a full warp calls it exactly once per round (the list
+// appends use ballots).  Shared by seg_plan_kernel and by kernels that plan while they still hold the
+// unique in registers (the cache's resolve, hb_cache.cu).
+template <class F>
+__device__ __forceinline__ void seg_plan_item(u32 i, u32 u, u32 U, u32 total, const u32 *__restrict__ seg_start,
+                                              const u32 *__restrict__ perm, u32 hot_threshold, const HotLists &hl,
+                                              const F &f) {
+    using Item = SegItem<typename F::Ctx>;
+    static_assert(sizeof(Item) == kSegItemBytes, "work items are 32 bytes");
+    Item *items = reinterpret_cast<Item *>(hl.items);
+    const u32 med = min(hl.med_threshold, hot_threshold);
+    Item item;
+    item.h.s0 = item.h.cnt = item.h.p0 = 0;
+    item.h.cls = SEG_SKIP;
+    item.ctx = typename F::Ctx();
+    if (i < total && u < U) {
+        item.h.s0 = seg_start[u];
+        item.h.cnt = seg_start[u + 1] - item.h.s0;
+        if (item.h.cnt > 0 && f.open((size_t)u, item.h.cnt, item.ctx)) {
+            item.h.p0 = perm[item.h.s0];
+            item.h.cls = item.h.cnt > med ? SEG_LISTED : SEG_COLD;
+        }
+    }
+    if (i < total)
+        items[i] = item;
+    const bool listed = item.h.cls == SEG_LISTED;
+    const bool a = listed && item.h.cnt > hot_threshold && item.h.cnt > kVeryHot;
+    const bool b = listed && !a && item.h.cnt > hot_threshold;
+    const bool m = listed && !a && !b;
+    const u32 pa = rows_warp_append(&hl.ctrl[0], a);
+    if (a)
+        hl.very_hot[pa] = i;
+    const u32 pb = rows_warp_append(&hl.ctrl[1], b);
+    if (b)
+        hl.hot[pb] = i;
+    const u32 pm = rows_warp_append(&hl.ctrl[4], m);
+    if (m)
+        hl.medium[pm] = i;
+}
+
 template <class F>
 __global__ void __launch_bounds__(256)
     seg_plan_kernel(const u32 *__restrict__ seg_start, const u32 *__restrict__ perm,
                     const u32 *__restrict__ num_unique, u32 hot_threshold, HotLists hl, F f) {
     pdl_enter();
-    using Item = SegItem<typename F::Ctx>;
-    static_assert(sizeof(Item) == kSegItemBytes, "work items are 32 bytes");
-    Item *items = reinterpret_cast<Item *>(hl.items);
     const u32 U = *num_unique;
     const u32 TK = hl.ticket_rows;
     const u32 T = (U + TK - 1) / TK;
     const u32 total = T * TK;
-    const u32 med = min(hl.med_threshold, hot_threshold);
     f.kernel_begin();
     const u32 stride = gridDim.x * blockDim.x;
     const u32 rounds = (total + stride - 1) / stride;
     for (u32 it = 0; it < rounds; it++) { // block-uniform trip count: the appends are warp-collective
         const u32 i = it * stride + blockIdx.x * blockDim.x + threadIdx.x;
         const u32 t = i / TK, l = i - t * TK;
-        const u32 u = t + l * T;
-        Item item;
-        item.h.s0 = item.h.cnt = item.h.p0 = 0;
-        item.h.cls = SEG_SKIP;
-        item.ctx = typename F::Ctx();
-        if (i < total && u < U) {
-            item.h.s0 = seg_start[u];
-            item.h.cnt = seg_start[u + 1] - item.h.s0;
-            if (item.h.cnt > 0 && f.open((size_t)u, item.h.cnt, item.ctx)) {
-                item.h.p0 = perm[item.h.s0];
-                item.h.cls = item.h.cnt > med ? SEG_LISTED : SEG_COLD;
-            }
-        }
-        if (i < total)
-            items[i] = item;
-        const bool listed = item.h.cls == SEG_LISTED;
-        const bool a = listed && item.h.cnt > hot_threshold && item.h.cnt > kVeryHot;
-        const bool b = listed && !a && item.h.cnt > hot_threshold;
-        const bool m = listed && !a && !b;
-        const u32 pa = rows_warp_append(&hl.ctrl[0], a);
-        if (a)
-            hl.very_hot[pa] = i;
-        const u32 pb = rows_warp_append(&hl.ctrl[1], b);
-        if (b)
-            hl.hot[pb] = i;
-        const u32 pm = rows_warp_append(&hl.ctrl[4], m);
-        if (m)
-            hl.medium[pm] = i;
+        seg_plan_item(i, t + l * T, U, total, seg_start, perm, hot_threshold, hl, f);
     }
     f.kernel_end();
 }
