@@ -414,3 +414,23 @@ def test_laia_plan_as_push_keys(oracle_impl, policy, bound):
         h.check_lines("final")
     finally:
         h.close()
+
+
+@pytest.mark.parametrize("n,V,D", [(50, 300, 8), (6000, 20000, 128), (300000, 400000, 8)])
+def test_update_of_a_different_batch_of_the_same_size(oracle_impl, n, V, D):
+    """The update's batch has the size of the batch its workspace holds but other ids: the
+    device-side comparison (same_keys) fails and the sort kernels of the side stream really run,
+    over the workspace the previous lookup filled.  Alternated with updates of the looked-up batch
+    itself (the sort kernels return at once)."""
+    rng = np.random.default_rng(n)
+    h = GpuHarness(oracle_impl, "lru", max(5, V // 10), 0, _rows(rng, V, D))
+    try:
+        for t in range(6):
+            keys = zipf_keys(rng, n, V, 1.1)
+            h.lookup(keys, "step %d" % t)
+            ukeys = keys if t % 2 else zipf_keys(rng, n, V, 1.1)
+            h.update(ukeys, rng.normal(0, 1e-3, (n, D)).astype(np.float32), None, "step %d" % t)
+        h.check_state("final")
+        h.check_lines("final")
+    finally:
+        h.close()
