@@ -239,6 +239,74 @@ __global__ void op_end_kernel(CacheView c, const u64 *clk, int last_stage, PerfR
 }
 
 // =====================================================================================
+// batched insert, step one: the plan  (cache.cc:28-35 + policy insert())
+// =====================================================================================
+constexpr int kSelUnroll = 4; // slot priorities a thread loads before it uses the first
+constexpr int kLogBlock = 512, kLogItems = 8;
+constexpr int kLogTile = kLogBlock * kLogItems; // stamps one tile of the log walk covers
+
+// The plan of a batched insert (block-wide; thread 0 decides, every thread helps zeroing): how many
+// lines the serial loop would evict (E), where the new lines' stamps start, the bins / the log span
+// of the victim selection.  `now` = the replacement clock after the batch's touches; M = regs->M.
+// Runs as the tail of the resolve's last tile (a lookup: that thread has just settled M and the
+// clock, and no other tile touches these words — one launch less in front of the victim selection)
+// or as a kernel of its own (push_pull, single keys).
+__device__ __forceinline__ void plan_insert_body(const CacheView &c, int bypass, u64 now, u64 *clk_out) {
+    __shared__ u32 s_log_tiles;
+    for (int b = threadIdx.x; b < 2 * kSelBins; b += blockDim.x)
+        c.sel_hist[b] = 0;
+    if (threadIdx.x == 0) {
+        CacheRegs *r = c.regs;
+        r->sel_done2 = 0;
+        r->sel_above = 0;
+        r->sel_fallback = 0;
+        r->sel_cut_eff = r->sel_cut ? r->sel_cut : (u32)kSelBins;
+        const u32 M = r->M, size_old = r->size, limit = c.limit;
+        u32 E = 0;
+        if (!bypass) {
+            if (c.policy == HB_POLICY_LRU) { // insert, then evict while over limit (lru_cache.cc:9-25)
+                u64 tot = (u64)size_old + M;
+                E = tot > limit ? (u32)(tot - limit) : 0;
+            } else { // evict before insert when full (lfu_cache.cc:9-20, lfuopt_cache.cc:9-26)
+                u32 F = limit > size_old ? limit - size_old : 0;
+                E = M > F ? M - F : 0;
+            }
+        }
+        r->E = E;
+        r->k_old = 0;
+        r->n_drop = bypass ? M : 0;
+        r->need_min = 0;
+        r->nv = 0;
+        r->nc = 0;
+        r->sel_done = 0;
+        r->min_use = 0xffffffffu;
+        r->min_prio = ~0ull;
+        r->ins_clock0 = now;
+        *clk_out = now + M;
+        // bins cover [floor, now): (stamp - floor) >> shift < kSelBins
+        const u64 span = now > r->floor ? now - r->floor : 1; // stamp offsets 0 .. span-1
+        const int bits = span > 1 ? 64 - __clzll((long long)(span - 1)) : 0;
+        r->sel_shift = bits > kSelBits ? (u32)(bits - kSelBits) : 0;
+        // LRU: every stamp of [floor, now) still has its own entry in the stamp log
+        const bool use_log = c.policy == HB_POLICY_LRU && E > 0 && now > r->floor &&
+                             now - r->floor <= (u64)c.log_mask + 1;
+        r->sel_use_log = use_log ? 1u : 0u;
+        r->sel_floor0 = r->floor;
+        s_log_tiles = use_log ? (u32)((now - r->floor + kLogTile - 1) / kLogTile) : 0;
+    }
+    __syncthreads();
+    // scan state of the log walk: ticket + one status word per tile
+    for (u32 w = threadIdx.x; w < s_log_tiles + 2; w += blockDim.x)
+        c.sel_scan[w] = 0;
+}
+
+__global__ void __launch_bounds__(256)
+    plan_insert_kernel(CacheView c, int bypass, const u64 *clk_in, u64 *clk_out) {
+    pdl_enter();
+    plan_insert_body(c, bypass, *clk_in, clk_out);
+}
+
+// =====================================================================================
 // resolve: policy lookup of every unique key (+ touch), ordered compaction of the misses
 // =====================================================================================
 // batch 0 writes U/M/alloc_base, batch 1 (push side of push_pull) writes U2/M2/alloc_base2.
@@ -264,7 +332,7 @@ template <class Plan>
 __global__ void __launch_bounds__(kScanBlock)
     resolve_kernel(CacheView c, const u64 *uniq, const u32 *num_unique, i32 *uslot, u32 *miss_list,
                    int bypass, ScanState st, u32 ntiles, const u64 *clk_in, u64 *clk_out, int batch,
-                   int dataless, Plan plan) {
+                   int dataless, int plan_insert, Plan plan) {
     pdl_enter();
     if constexpr (Plan::enabled)
         plan.f.kernel_begin();
@@ -367,6 +435,9 @@ __global__ void __launch_bounds__(kScanBlock)
         }
         *clk_out = base + U;
     }
+    // a lookup: the insert plan right here (this tile knows M and the clock; block-uniform branch)
+    if (plan_insert && tile == ntiles - 1)
+        plan_insert_body(c, bypass, base + U, clk_out + 1);
     if constexpr (Plan::enabled) {
         static_assert(kResolveItems == 1, "one unique per thread");
         // ticket order: item i = t * TK + l holds unique u = t + l * T (hb_rows.cuh); this thread owns
@@ -624,64 +695,8 @@ struct IndexFromSlots {
 };
 
 // =====================================================================================
-// batched insert: plan, select victims, evict, insert  (cache.cc:28-35 + policy insert())
+// batched insert: select victims, evict, insert  (cache.cc:28-35 + policy insert())
 // =====================================================================================
-constexpr int kSelUnroll = 4; // slot priorities a thread loads before it uses the first
-constexpr int kLogBlock = 512, kLogItems = 8;
-constexpr int kLogTile = kLogBlock * kLogItems; // stamps one tile of the log walk covers
-
-__global__ void __launch_bounds__(256)
-    plan_insert_kernel(CacheView c, int bypass, const u64 *clk_in, u64 *clk_out) {
-    pdl_enter();
-    __shared__ u32 s_log_tiles;
-    for (int b = threadIdx.x; b < 2 * kSelBins; b += blockDim.x)
-        c.sel_hist[b] = 0;
-    if (threadIdx.x == 0) {
-        CacheRegs *r = c.regs;
-        r->sel_done2 = 0;
-        r->sel_above = 0;
-        r->sel_fallback = 0;
-        r->sel_cut_eff = r->sel_cut ? r->sel_cut : (u32)kSelBins;
-        const u32 M = r->M, size_old = r->size, limit = c.limit;
-        u32 E = 0;
-        if (!bypass) {
-            if (c.policy == HB_POLICY_LRU) { // insert, then evict while over limit (lru_cache.cc:9-25)
-                u64 tot = (u64)size_old + M;
-                E = tot > limit ? (u32)(tot - limit) : 0;
-            } else { // evict before insert when full (lfu_cache.cc:9-20, lfuopt_cache.cc:9-26)
-                u32 F = limit > size_old ? limit - size_old : 0;
-                E = M > F ? M - F : 0;
-            }
-        }
-        r->E = E;
-        r->k_old = 0;
-        r->n_drop = bypass ? M : 0;
-        r->need_min = 0;
-        r->nv = 0;
-        r->nc = 0;
-        r->sel_done = 0;
-        r->min_use = 0xffffffffu;
-        r->min_prio = ~0ull;
-        const u64 now = *clk_in;
-        r->ins_clock0 = now;
-        *clk_out = now + M;
-        // bins cover [floor, now): (stamp - floor) >> shift < kSelBins
-        const u64 span = now > r->floor ? now - r->floor : 1; // stamp offsets 0 .. span-1
-        const int bits = span > 1 ? 64 - __clzll((long long)(span - 1)) : 0;
-        r->sel_shift = bits > kSelBits ? (u32)(bits - kSelBits) : 0;
-        // LRU: every stamp of [floor, now) still has its own entry in the stamp log
-        const bool use_log = c.policy == HB_POLICY_LRU && E > 0 && now > r->floor &&
-                             now - r->floor <= (u64)c.log_mask + 1;
-        r->sel_use_log = use_log ? 1u : 0u;
-        r->sel_floor0 = r->floor;
-        s_log_tiles = use_log ? (u32)((now - r->floor + kLogTile - 1) / kLogTile) : 0;
-    }
-    __syncthreads();
-    // scan state of the log walk: ticket + one status word per tile
-    for (u32 w = threadIdx.x; w < s_log_tiles + 2; w += blockDim.x)
-        c.sel_scan[w] = 0;
-}
-
 // LRU victim selection by walking the stamp log.  Every policy touch and insert takes the next
 // tick of the replacement clock and records `stamp_log[t & mask] = slot`, so the resident lines in
 // recency order are the entries of [floor, now) whose slot still carries that stamp.  The E oldest
@@ -2439,7 +2454,7 @@ void end_call(hb_cache *c, int last_stage, u32 kind, size_t n, bool inserted, bo
 // resolve (+ alloc) of the batch workspace `wsi` holds; `batch` = which counter set of the call
 template <class Plan>
 void resolve_batch(hb_cache *c, size_t n, int batch, int wsi, bool dataless, int clk_stage, bool marks,
-                   Plan plan) {
+                   Plan plan, bool plan_insert = false) {
     KeyWorkspace &ws = c->ws[wsi];
     cudaStream_t st = c->stream;
     if (marks)
@@ -2451,14 +2466,17 @@ void resolve_batch(hb_cache *c, size_t n, int batch, int wsi, bool dataless, int
     HB_LAUNCH(resolve_kernel<Plan>, ntiles, kScanBlock, 0, st, c->view, ws.uniq, ws.num_unique, c->uslot[batch],
                                                   c->miss_list[batch], c->bypass ? 1 : 0,
                                                   ws.next_scan(), ntiles, clk + clk_stage,
-                                                  clk + clk_stage + 1, batch, dataless ? 1 : 0, plan);
+                                                  clk + clk_stage + 1, batch, dataless ? 1 : 0,
+                                                  plan_insert ? 1 : 0, plan);
     HB_LAUNCHED();
     if (marks)
         mark(c, 1);
 }
+// plan_insert: the resolve's last tile also writes the plan of the insert that follows (run_insert
+// with planned = true)
 void resolve_batch(hb_cache *c, size_t n, int batch, int wsi, bool dataless, int clk_stage,
-                   bool marks = true) {
-    resolve_batch(c, n, batch, wsi, dataless, clk_stage, marks, NoSegPlan{});
+                   bool marks = true, bool plan_insert = false) {
+    resolve_batch(c, n, batch, wsi, dataless, clk_stage, marks, NoSegPlan{}, plan_insert);
 }
 
 bool vec4(const hb_cache *c, const void *user_rows) {
@@ -2530,11 +2548,14 @@ void run_gather(hb_cache *c, size_t n, int wsi, float *dev_dest) {
     HB_LAUNCHED();
 }
 
-void run_insert(hb_cache *c, size_t n, int clk_stage, cudaStream_t st) {
+// planned: the resolve of this batch has already written the plan (resolve_batch, plan_insert)
+void run_insert(hb_cache *c, size_t n, int clk_stage, cudaStream_t st, bool planned = false) {
     u64 *clk = clk_of(c);
-    HB_LAUNCH(plan_insert_kernel, 1, 256, 0, st, c->view, c->bypass ? 1 : 0, clk + clk_stage,
-                                          clk + clk_stage + 1);
-    HB_LAUNCHED();
+    if (!planned) {
+        HB_LAUNCH(plan_insert_kernel, 1, 256, 0, st, c->view, c->bypass ? 1 : 0, clk + clk_stage,
+                                              clk + clk_stage + 1);
+        HB_LAUNCHED();
+    }
     if (!n)
         return;
     int sgrid = lin_grid(c->view.capacity);
@@ -3318,7 +3339,7 @@ int hb_cache_lookup(hb_cache *c, const void *keys, int key_kind, size_t n, float
     int k;
     float *ddest = stage_dest(c, dest, n, &k);
     begin_call(c, false, n, w);
-    resolve_batch(c, n, 0, w, /*dataless=*/false, 0);
+    resolve_batch(c, n, 0, w, /*dataless=*/false, 0, true, /*plan_insert=*/true);
     // The insert phase (victim selection, evictions, index inserts) needs the resolve's results
     // only: it works on slot scalars and the index, never on row data, and its victims are never
     // lines of this batch — so it runs on its own stream NEXT TO sync + gather, which move the rows.
@@ -3326,7 +3347,7 @@ int hb_cache_lookup(hb_cache *c, const void *keys, int key_kind, size_t n, float
     if (fork) {
         HB_CUDA(cudaEventRecord(c->ev_fork, c->stream));
         HB_CUDA(cudaStreamWaitEvent(c->side2, c->ev_fork, 0));
-        run_insert(c, n, 1, c->side2);
+        run_insert(c, n, 1, c->side2, /*planned=*/true);
         HB_CUDA(cudaEventRecord(c->ev_join, c->side2));
     }
     run_sync(c, n, w);
@@ -3338,7 +3359,7 @@ int hb_cache_lookup(hb_cache *c, const void *keys, int key_kind, size_t n, float
     if (fork)
         HB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
     else
-        run_insert(c, n, 1, c->stream);
+        run_insert(c, n, 1, c->stream, /*planned=*/true);
     c->pending_upper += n;
     end_call(c, 2, 0, n, true);
     HB_API_END();
@@ -3818,7 +3839,7 @@ int hb_cache_touch(hb_cache *c, uint64_t key, int *found, int64_t *version, floa
     u64 *clk = clk_of(c);
     HB_LAUNCH(resolve_kernel<NoSegPlan>, 1, kScanBlock, 0, st, c->view, ws.uniq, ws.num_unique, c->uslot[0],
                                              c->miss_list[0], c->bypass ? 1 : 0, ws.next_scan(), 1,
-                                             clk, clk + 1, 0, 0, NoSegPlan{});
+                                             clk, clk + 1, 0, 0, 0, NoSegPlan{});
     HB_LAUNCHED();
     // a miss reserved a slot for a fresh line; materialise and hand it back (lookup() alone
     // allocates nothing)
@@ -3864,7 +3885,7 @@ int hb_cache_insert(hb_cache *c, uint64_t key, int64_t version, const float *dat
         u64 *clk = clk_of(c);
         // bypass=1: resolve as a miss without touching anything, which allocates the fresh line
         HB_LAUNCH(resolve_kernel<NoSegPlan>, 1, kScanBlock, 0, st, c->view, ws.uniq, ws.num_unique, c->uslot[0],
-                                                 c->miss_list[0], 1, ws.next_scan(), 1, clk, clk, 0, 0, NoSegPlan{});
+                                                 c->miss_list[0], 1, ws.next_scan(), 1, clk, clk, 0, 0, 0, NoSegPlan{});
         HB_LAUNCHED();
         i32 *dslot = nullptr, hslot = -1;
         dmalloc(dslot, 1);
