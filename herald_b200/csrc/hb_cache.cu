@@ -546,7 +546,7 @@ __global__ void __launch_bounds__(kRowBlock)
                     if (src[r] >= 0) {
                         if (ra[r])
                             x[r] = V::add(x[r], g[r]);
-                        V::st(c.data + (size_t)rs[r] * D + k * VEC, x[r]);
+                        V::st_keep(c.data + (size_t)rs[r] * D + k * VEC, x[r]);
                     }
             }
         }
@@ -668,7 +668,7 @@ __global__ void __launch_bounds__(kRowBlock)
                         const float4 g = rg ? V::ld(c.grad + (size_t)rs * D + k * 4) : V::zero();
                         x = V::add(x, g);
                     }
-                    V::st(c.data + (size_t)rs * D + k * 4, x);
+                    V::st_keep(c.data + (size_t)rs * D + k * 4, x);
                 }
                 r++;
             }

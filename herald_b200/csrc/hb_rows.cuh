@@ -34,6 +34,9 @@ struct RowVec<4> {
     static __device__ __forceinline__ T ld(const float *p) {
         return *reinterpret_cast<const float4 *>(p);
     }
+    static __device__ __forceinline__ void st_keep(float *p, const T &v) { // row the next kernels read again
+        hb::st_keep(reinterpret_cast<float4 *>(p), v);
+    }
     static __device__ __forceinline__ T ld_rmw(const float *p) { // row read once, then overwritten
         return ld_row(reinterpret_cast<const float4 *>(p));
     }
@@ -65,6 +68,9 @@ struct RowVec<1> {
     }
     static __device__ __forceinline__ T ld(const float *p) {
         return *p;
+    }
+    static __device__ __forceinline__ void st_keep(float *p, const T &v) {
+        *p = v;
     }
     static __device__ __forceinline__ T ld_rmw(const float *p) {
         return *p;
