@@ -2715,7 +2715,7 @@ void run_accumulate(hb_cache *c, size_t n, int batch, int wsi, const float *dev_
     } else if (fuse_tail) {
         // flush + release of the dataless lines + the call's epilogue in one launch
         const int idx = (int)(c->calls % hb_cache::kRing);
-        const int grid = std::max(row_grid(pend), std::max(1, lin_grid(n) / 4));
+        const int grid = std::max(row_grid(c->may_hold_dirty ? pend : 0), std::max(1, lin_grid(n) / 4));
         if (c->width % 4 == 0)
             HB_LAUNCH(update_tail_kernel<4>, grid, kRowBlock, 0, st, c->view, c->uslot[batch], c->miss_list[batch],
                       clk_of(c), 1, c->ring_dev + idx, (u32)n);
@@ -2790,6 +2790,8 @@ void do_update(hb_cache *c, const void *keys, int kind, size_t n, const float *g
     ensure_batch(c, n);
     ensure_keys_stage(c, n);
     ensure_slack(c, n);
+    if (use_plan || c->push_bound > 0)
+        c->may_hold_dirty = true; // lines outside the plan / under the bound keep their gradient
     const int w = c->cur; // the workspace of the most recent lookup: usually this very batch
     const void *dkeys = stage_keys(c, keys, kind, n, 0);
     presort(c, dkeys, kind, n, w, /*check=*/true);
@@ -3394,6 +3396,7 @@ int hb_cache_push_pull(hb_cache *c, const void *pull_keys, int pull_kind, size_t
     // the push batch is usually the previous call's pull batch (ASP prefetch,
     // ParameterServerCommunicate.py:36-38): it is checked against that workspace; the pull batch
     // goes to the other one
+    c->may_hold_dirty = true; // (deferred cleanup: a pushed line counts as dirty until the call's end)
     const int wpush = c->cur, wpull = c->cur ^ 1;
     const void *dpush = stage_keys(c, push_keys, push_kind, n_push, 1);
     presort(c, dpush, push_kind, n_push, wpush, /*check=*/true);

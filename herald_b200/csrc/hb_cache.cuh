@@ -316,6 +316,10 @@ struct hb_cache {
     size_t ticks_ring[kRing] = {};    // most replacement-clock ticks each call could take
     size_t cur_ticks = 0;             // ... the call being enqueued
     size_t pending_upper = 0;
+    // false while no call can have left a line dirty (every update so far pushed every line it touched:
+    // plain updates with push_bound <= 0): the update's tail is then sized for its other work only (its
+    // loops are grid-stride, the count of pending victims is read on the device either way)
+    bool may_hold_dirty = false;
     int key_bits = 64;
     hb::u32 hot_threshold = 64; // segments longer than this take the column-split path
     // multi-GPU
